@@ -1,0 +1,388 @@
+#!/usr/bin/env python3
+"""bench.py -- aggregate Msamples/s through the fused transform+vumeter tick (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Workload (default `cfg2`, BASELINE.json configs[1]): per GPU 1,024 independent 48 kHz stereo S16
+streams x 10 s, resident in one device ring; one step = one fused tick (ONE kernel launch) over the
+whole ring = 9.8304e8 samples, 3.93 GB of algorithmic traffic (2 B read + 2 B written per sample),
+far larger than the 126 MB L2. With N > 1 every rank holds its own 1,024 streams (streams shard
+trivially; no data-path collective) -> weak scaling; the per-stream meter rows are gathered to
+rank 0 over NCCL outside the kernel-timed region and inside the end-to-end one.
+
+`value`  device-timed (CUDA events on the engine's compute stream, max over ranks), inputs in HBM.
+`e2e`    the same work through the C ABI with pinned HOST buffers: per step every 1 s tick of the
+         10 s is uploaded, processed and downloaded through a 4-slot ring on three CUDA streams,
+         then the meter state is read back; wall clock, max over ranks.
+`roofline` algorithmic bytes / measured kernel time against MEASURED_PEAKS.json's HBM copy rate.
+`cpu_baseline` the reference's own transform.c/tee.c/vumeter.c object code (oracle/_ref) on this
+         box's host cores over a bounded sample of the same workload.
+
+`--impl reference` times only that CPU reference (all host threads) and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (channels, streams per GPU, seconds, rate, description)
+    "cfg2": (2, 1024, 10, 48000, "1,024 x 48 kHz stereo S16 streams x 10 s per GPU, one device ring, one fused tick per step"),
+    "cfg4a": (8, 4096, 2, 48000, "4,096 x 48 kHz 8-channel S16 streams x 2 s per GPU, per-channel gain + 8-channel meter"),
+    "cfg5": (2, 65536, 1, 48000, "65,536 x 48 kHz stereo S16 streams x 1 s in total, sharded by stream across the GPUs"),
+}
+
+
+def gain_table(first_stream: int, n: int, channels: int):
+    """scale = 1000 + s % 9000 (general division), gains around 3/4 with some
+    streams above 1.0 (clipping). Every stream has an active, non-unity gain."""
+    s = np.arange(first_stream, first_stream + n)
+    scale = (1000 + s % 9000).astype(np.uint16)
+    gain = (scale[:, None].astype(np.int64) * 3 // 4 + 37 * ((s[:, None] + np.arange(channels)) % 64)).astype(np.uint16)
+    return scale, gain
+
+
+def synth_block(first_stream: int, n: int, channels: int, frames: int, out: np.ndarray, first_frame: int = 0):
+    """Synthetic 1 kHz tone at 48 kHz (48-sample period), phase-shifted per stream and channel, with
+    every 16th stream replaced by full-range hash noise to exercise the clamp and the tie-breaks."""
+    period = np.round(32766 * np.sin(2 * np.pi * np.arange(48) / 48)).astype(np.int16)
+    tiled = np.tile(period, frames // 48 + 3)
+    for i in range(n):
+        s = first_stream + i
+        row = out[i]
+        if s % 16 == 5:
+            rng = np.random.default_rng(s * 1000003 + first_frame)
+            row[: frames * channels] = rng.integers(-32768, 32768, size=frames * channels).astype(np.int16)
+            continue
+        for c in range(channels):
+            off = (first_frame + 7 * s + 3 * c) % 48
+            row[c: frames * channels: channels] = tiled[off: off + frames]
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def cpu_reference_run(channels, rate, seconds, budget_s=12.0, threads=None, streams=None):
+    """The reference's own CPU path (oracle/_ref: mem -> transform -> tee -> {consumer, vumeter},
+    1,024-byte pulls, result every 20 reads) over `streams` streams of the workload on `threads`
+    pthreads, repeated until ~budget_s seconds have been spent. Falls back to the oracle port."""
+    from oracle import pyoracle
+    threads = threads or os.cpu_count() or 1
+    frames = rate * seconds
+    ref = pyoracle.ref()
+    streams = streams or max(threads, min(4 * threads, 256))
+    # keep the sample's memory bounded (~1 GB of input)
+    while streams * frames * channels * 2 > (1 << 30) and frames > rate:
+        frames //= 2
+    pcm = np.empty((streams, frames * channels), dtype=np.int16)
+    synth_block(0, streams, channels, frames, pcm)
+    scale, gain = gain_table(0, streams, channels)
+    samples_per_pass = streams * frames * channels
+    passes, spent = 0, 0.0
+    if ref is not None:
+        kind = "reference"
+        while spent < budget_s and passes < 4096:
+            sec, _, _ = ref.bench(pcm, channels, scale, gain, rate=rate, pull=1024, result_every=20, threads=threads)
+            spent += sec
+            passes += 1
+    else:
+        kind = "port"
+        port = pyoracle.port()
+        fr = np.full(streams, frames, dtype=np.uint32)
+        while spent < budget_s and passes < 4096:
+            work = pcm.copy()
+            _, sec = port.batch(work, fr, channels, scale, gain, threads=threads)
+            spent += sec
+            passes += 1
+    msps = samples_per_pass * passes / spent / 1e6
+    sample = (f"{streams} streams x {frames / rate:g} s x {channels} ch ({samples_per_pass / 1e6:.1f} Msamples) x "
+              f"{passes} passes, {'reference objects, 1024-byte pulls through tee, result every 20 reads' if kind == 'reference' else 'oracle port, whole-buffer calls'}")
+    return {"value": msps, "unit": "Msamples/s", "cores": threads, "kind": kind, "sample": sample,
+            "seconds": spent}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank, world, local = dist_env()
+    channels, streams_per_gpu, seconds, rate, desc = WORKLOADS[args.workload]
+    scaling = "weak"
+    if args.workload == "cfg5":
+        streams_per_gpu //= max(world, 1)
+        scaling = "strong"
+    frames = rate * seconds
+    samples_per_step_rank = streams_per_gpu * frames * channels
+    config = {"workload": f"{args.workload}: {desc}", "streams_per_gpu": streams_per_gpu, "channels": channels,
+              "rate_hz": rate, "seconds_per_stream": seconds, "gains": "every stream active, scale 1000+s%9000, gain ~0.75..3.1",
+              "l2": "inputs (>=1.5 GB per GPU) far larger than the 126 MB L2; no flush needed",
+              "sharding": "by stream, one process per GPU, no data-path collective"}
+
+    # ---------------------------------------------------------------- reference arm (CPU only)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        runs = []
+        for _ in range(args.warmup if args.warmup < 2 else 1):
+            cpu_reference_run(channels, rate, seconds, budget_s=1.0)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            runs.append(cpu_reference_run(channels, rate, seconds, budget_s=max(1.0, 60.0 / max(args.steps, 1))))
+        wall = time.perf_counter() - t0
+        value = float(np.mean([r["value"] for r in runs]))
+        base = dict(runs[-1]); base["value"] = value
+        line = {"impl": "reference", "metric": "aggregate Msamples/s through transform+vumeter", "value": value,
+                "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": scaling,
+                "vs_baseline": None, "dtype": "int32 (S16 in/out, int64 power)", "data": "synthetic",
+                "config": config, "cpu_baseline": base,
+                "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- our arm
+    from __graft_entry__ import load_package
+    cm = load_package()
+    if cm.lib().cmgpu_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device visible; the hot path has no CPU fallback")
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    first_stream = rank * streams_per_gpu
+    scale, gain = gain_table(first_stream, streams_per_gpu, channels)
+
+    # ---- device-resident run: the whole workload in one ring slot, out of place so that the
+    #      input stays pristine across steps
+    eng = cm.Engine(channels, streams_per_gpu, frames, ring_slots=1, device=local,
+                    flags=cm.SEPARATE_OUT | cm.NO_PINNED)
+    eng.set_gain_table(scale, gain)
+    chunk = max(1, (256 << 20) // (frames * channels * 2))
+    stage = np.empty((streams_per_gpu, eng.stride // 2), dtype=np.int16)
+    for lo in range(0, streams_per_gpu, chunk):
+        hi = min(streams_per_gpu, lo + chunk)
+        synth_block(first_stream + lo, hi - lo, channels, frames, stage[lo:hi])
+    eng.submit(0, stage)
+    eng.sync()
+
+    clocks = ClockSampler(local)
+    eng.time_process(args.warmup)
+    eng.reset_meters()
+    launches0 = eng.launch_count()
+    barrier()
+    clocks.start()
+    ms_total = eng.time_process(args.steps)
+    barrier()
+    clk = clocks.stop()
+    launches = eng.launch_count() - launches0
+    ms_total = max_over_ranks(ms_total)
+    ms_step = ms_total / args.steps
+    value = samples_per_step_rank * world / (ms_step * 1e-3) / 1e6
+
+    # meter sanity on what was just measured: K identical ticks -> K * frames frames per stream
+    snap = eng.snapshot(0, min(4, streams_per_gpu))
+    assert int(snap[0].frames) == args.steps * frames, "meter did not see every timed tick"
+    kernel = eng.kernel_name()
+    peak, peak_src = measured_peak()
+    alg_bytes = 4.0 * samples_per_step_rank
+    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": kernel, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_step,
+                "frac_of_nominal_8TBps": achieved / 8000.0}
+    prof = ROOT / "profiles" / "traffic.json"
+    if prof.exists():
+        try:
+            roofline["traffic"] = json.loads(prof.read_text()).get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    eng.close()
+    del stage
+
+    # ---- end to end through the C ABI with host buffers: 1 s ticks through a 4-slot ring
+    e2e = None
+    if not args.no_e2e:
+        tick_frames = rate
+        n_ticks = seconds
+        e2e_steps = args.e2e_steps or min(args.steps, 5)
+        eng = cm.Engine(channels, streams_per_gpu, tick_frames, ring_slots=4, device=local, flags=cm.NO_PINNED)
+        eng.set_gain_table(scale, gain)
+        shape = (n_ticks, streams_per_gpu, eng.stride // 2)
+        pin_in, pin_out = cm.PinnedArray(shape), cm.PinnedArray(shape)
+        for t in range(n_ticks):
+            for lo in range(0, streams_per_gpu, 256):
+                hi = min(streams_per_gpu, lo + 256)
+                synth_block(first_stream + lo, hi - lo, channels, tick_frames, pin_in.array[t, lo:hi], t * tick_frames)
+        meter_rows = None
+
+        def e2e_step():
+            nonlocal meter_rows
+            for t in range(n_ticks):
+                slot = t % 4
+                eng.submit(slot, pin_in.array[t])
+                eng.process(slot)
+                eng.fetch(slot, pin_out.array[t])
+            eng.sync()
+            if dist is not None:
+                gather_meters(cm, eng, dist, rank, world)
+            meter_rows = eng.snapshot(reset=True)      # D2H of the integer meter state, then reset
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        wall = max_over_ranks(time.perf_counter() - t0)
+        assert int(meter_rows[0].frames) == frames
+        slot_bytes = streams_per_gpu * eng.stride
+        meter_bytes = streams_per_gpu * eng.meter_row_u64() * 8
+        e2e = {"value": samples_per_step_rank * world * e2e_steps / wall / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": n_ticks * slot_bytes, "d2h_bytes_per_step": n_ticks * slot_bytes + meter_bytes,
+               "steps": e2e_steps, "ms_per_step": 1e3 * wall / e2e_steps,
+               "how": f"{n_ticks} ticks of {tick_frames} frames per step through a 4-slot ring, pinned host buffers, "
+                      "upload/compute/download on three CUDA streams, meter snapshot (+ NCCL gather to rank 0 when N>1) per step"}
+        eng.close()
+        pin_in.free(); pin_out.free()
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_reference_run(channels, rate, seconds, budget_s=12.0)
+        cpu.pop("seconds", None)
+
+    if rank == 0:
+        line = {"metric": "aggregate Msamples/s through transform+vumeter", "value": value, "unit": "Msamples/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+                "dtype": "int32 (S16 in/out, int64 power)", "data": "synthetic", "config": config,
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def gather_meters(cm, eng, dist, rank, world):
+    """Per-stream meter rows of every rank to rank 0 over NCCL (the only collective on the path)."""
+    import torch
+    n = eng.max_streams * eng.meter_row_u64()
+    # wrap the engine's device meter table without copying
+    class _Dev:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (eng.device_meters(), False), "version": 2}
+    mine = torch.as_tensor(_Dev(), device="cuda")
+    out = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, out, dst=0)
+    torch.cuda.synchronize()
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

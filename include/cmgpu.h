@@ -1,0 +1,183 @@
+/* include/cmgpu.h -- the thin C ABI beneath the coolmic_transform_* / coolmic_vumeter_* API.
+ *
+ * B200-native batch engine for the one data-parallel hot path of libcoolmic-dsp:
+ *   coolmic_transform  (per-channel integer master gain on interleaved S16,
+ *                       reference src/transform.c:101-124)
+ *   coolmic_vumeter    (per-channel + global first-occurrence signed peak and exact
+ *                       int64 sum of squares, reference src/vumeter.c:161-177, and the dB
+ *                       finaliser, reference src/vumeter.c:189-218)
+ * fused into one pass over a device-resident ring of interleaved S16 stream-blocks.
+ *
+ * Plain C types only: pointers and sizes, no CUDA or torch types in any signature. Every
+ * int-returning entry point returns a COOLMIC_ERROR_*-compatible code (reference
+ * include/coolmic-dsp/coolmic-dsp.h:35-49): 0 ok, -1 generic (any CUDA error), -9 NULL
+ * argument, -10 invalid argument, -11 out of memory, -12 busy. There is NO CPU fallback:
+ * without a usable CUDA device cmgpu_ctx_create() fails and everything else refuses.
+ *
+ * Vocabulary
+ *   stream        one independent PCM stream (= one coolmic_transform_t + coolmic_vumeter_t pair)
+ *   stream-block  `block_frames` frames of one stream: block_frames * channels S16 samples,
+ *                 stored contiguously; its byte stride in a slot is rounded up to 16
+ *   slot          one tick of the ring: [max_streams] stream-blocks, device resident
+ *   tick          one cmgpu_process() over a slot: ONE fused kernel launch over all streams
+ *
+ * Which reference interface each entry point replaces is noted beside it.
+ */
+#ifndef CMGPU_H
+#define CMGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMGPU_MAX_CHANNELS 16      /* COOLMIC_DSP_TRANSFORM_MAX_CHANNELS, transform.h:35; vumeter.h:42 */
+
+#define CMGPU_OK            0      /* COOLMIC_ERROR_NONE    */
+#define CMGPU_ERR_GENERIC  (-1)    /* COOLMIC_ERROR_GENERIC */
+#define CMGPU_ERR_NOSYS    (-8)    /* COOLMIC_ERROR_NOSYS   */
+#define CMGPU_ERR_FAULT    (-9)    /* COOLMIC_ERROR_FAULT   */
+#define CMGPU_ERR_INVAL   (-10)    /* COOLMIC_ERROR_INVAL   */
+#define CMGPU_ERR_NOMEM   (-11)    /* COOLMIC_ERROR_NOMEM   */
+#define CMGPU_ERR_BUSY    (-12)    /* COOLMIC_ERROR_BUSY    */
+
+/* cmgpu_ctx_create flags */
+#define CMGPU_SEPARATE_OUT   0x1u  /* transformed PCM goes to a second ring instead of in place
+                                      (the reference works in place, transform.c:120) */
+#define CMGPU_NO_PINNED      0x2u  /* do not allocate the pinned host staging rings */
+#define CMGPU_FORCE_GENERIC  0x4u  /* always use the any-channel-count kernel (test hook) */
+
+/* cmgpu_process flags */
+#define CMGPU_TRANSFORM      0x1u  /* apply the gain tables (else pass PCM through untouched) */
+#define CMGPU_METER          0x2u  /* accumulate the meters over what the slot holds afterwards */
+#define CMGPU_FUSED          (CMGPU_TRANSFORM | CMGPU_METER)
+
+typedef struct cmgpu_ctx cmgpu_ctx_t;
+
+/* Integer meter state of one stream between reset and result: the exact content of
+ * struct coolmic_vumeter's accumulators (vumeter.c:48-56) in decoded form. */
+typedef struct cmgpu_meter_state {
+    uint64_t frames;                              /* result.frames                     */
+    int64_t  power[CMGPU_MAX_CHANNELS];           /* power[c] = sum of squares         */
+    int16_t  channel_peak[CMGPU_MAX_CHANNELS];    /* result.channel_peak[c]            */
+    int16_t  global_peak;                         /* result.global_peak                */
+    int16_t  reserved[3];
+} cmgpu_meter_state_t;
+
+/* Same members as coolmic_vumeter_result_t (vumeter.h:48-83) with fixed-width types. */
+typedef struct cmgpu_result {
+    uint32_t rate;
+    uint32_t channels;
+    uint64_t frames;
+    int16_t  global_peak;
+    double   global_power;
+    int16_t  channel_peak[CMGPU_MAX_CHANNELS];
+    double   channel_power[CMGPU_MAX_CHANNELS];
+} cmgpu_result_t;
+
+/* ---- library ------------------------------------------------------------------ */
+const char *cmgpu_version(void);
+int         cmgpu_device_count(void);                 /* 0 when no CUDA device is usable   */
+const char *cmgpu_last_error(void);                   /* thread-local text of the last failure */
+
+/* Page-locked host memory for callers that stream whole slots from their own buffers
+ * (cmgpu_submit / cmgpu_fetch are asynchronous only for page-locked memory). */
+void *cmgpu_host_alloc(size_t bytes);
+void  cmgpu_host_free(void *p);
+
+/* ---- context: one per (GPU, channel count) -------------------------------------- */
+/* All streams of a context share `channels` (1..16) and `block_frames` (>= 1). `ring_slots`
+ * (>= 1) stream-block sets are resident on the device; with pinned staging the same number
+ * exist in page-locked host memory. Returns NULL on error (see cmgpu_last_error()). */
+cmgpu_ctx_t *cmgpu_ctx_create(int device, unsigned channels, unsigned max_streams,
+                              unsigned ring_slots, unsigned block_frames, unsigned flags);
+void         cmgpu_ctx_destroy(cmgpu_ctx_t *ctx);
+
+unsigned cmgpu_channels(const cmgpu_ctx_t *ctx);
+unsigned cmgpu_max_streams(const cmgpu_ctx_t *ctx);
+unsigned cmgpu_ring_slots(const cmgpu_ctx_t *ctx);
+unsigned cmgpu_block_frames(const cmgpu_ctx_t *ctx);
+size_t   cmgpu_block_stride(const cmgpu_ctx_t *ctx);  /* bytes between stream-blocks in a slot */
+size_t   cmgpu_slot_bytes(const cmgpu_ctx_t *ctx);    /* max_streams * block_stride          */
+/* How many streams a tick covers (default max_streams). Lets one context serve fewer. */
+int      cmgpu_set_active_streams(cmgpu_ctx_t *ctx, unsigned n);
+
+/* ---- gain tables (replaces coolmic_transform_set_master_gain, transform.c:195-222) -- */
+/* Reference adaptation rules for one stream: n==0 || scale==0 || gain==NULL disables;
+ * n==channels copies; n==1 broadcasts; n==2 on a mono stream averages; anything else is
+ * CMGPU_ERR_INVAL and the previous setting is kept. Takes effect at the next tick. */
+int cmgpu_stream_set_gain(cmgpu_ctx_t *ctx, unsigned stream, unsigned n, uint16_t scale,
+                          const uint16_t *gain);
+/* Bulk form: scale[count], gain[count][channels], already per-channel. */
+int cmgpu_set_gain_table(cmgpu_ctx_t *ctx, unsigned first, unsigned count,
+                         const uint16_t *scale, const uint16_t *gain);
+/* Reads back what the device will use (after adaptation). */
+int cmgpu_stream_get_gain(const cmgpu_ctx_t *ctx, unsigned stream, uint16_t *scale,
+                          uint16_t gain[CMGPU_MAX_CHANNELS]);
+
+/* ---- ring I/O (replaces the byte shuffling of transform.c:126-165 and tee.c:137-206) --- */
+void *cmgpu_host_slot(cmgpu_ctx_t *ctx, unsigned slot);      /* pinned staging, in/out     */
+void *cmgpu_device_slot(cmgpu_ctx_t *ctx, unsigned slot);    /* device input ring          */
+void *cmgpu_device_out_slot(cmgpu_ctx_t *ctx, unsigned slot);/* == input ring when in place */
+/* Valid frames per stream for a slot: frames[active_streams] (each <= block_frames) or
+ * NULL for "every stream-block is full". Copied; applies to subsequent ticks of the slot. */
+int cmgpu_slot_set_frames(cmgpu_ctx_t *ctx, unsigned slot, const uint32_t *frames);
+/* Host -> device copy of a slot on the upload stream. `host` NULL = the pinned staging slot.
+ * Asynchronous when the source is page-locked. */
+int cmgpu_submit(cmgpu_ctx_t *ctx, unsigned slot, const void *host);
+/* One tick: ONE fused kernel launch over all active streams of the slot, on the compute
+ * stream, ordered after the slot's last submit. Asynchronous. */
+int cmgpu_process(cmgpu_ctx_t *ctx, unsigned slot, unsigned flags);
+/* Device -> host copy of the slot's (transformed) PCM on the download stream, ordered after
+ * the slot's last tick. `host` NULL = the pinned staging slot. Asynchronous if page-locked. */
+int cmgpu_fetch(cmgpu_ctx_t *ctx, unsigned slot, void *host);
+/* Wait for everything queued on the context. */
+int cmgpu_sync(cmgpu_ctx_t *ctx);
+/* Wait until the slot's last fetch (or tick, if none) has completed. */
+int cmgpu_slot_wait(cmgpu_ctx_t *ctx, unsigned slot);
+
+/* ---- meters (replaces coolmic_vumeter_read/result/reset, vumeter.c:93-99,138-218) ------ */
+/* Integer state of streams [first, first+count), waiting for queued ticks first. With
+ * `reset` the device state is cleared in the same stream-ordered step. */
+int cmgpu_meter_snapshot(cmgpu_ctx_t *ctx, unsigned first, unsigned count,
+                         cmgpu_meter_state_t *out, int reset);
+int cmgpu_meter_reset(cmgpu_ctx_t *ctx, unsigned first, unsigned count);
+/* coolmic_vumeter_result for one stream: CMGPU_ERR_INVAL (and no reset) if no frames were
+ * metered; otherwise fills *out (dB computed on the host with the reference's expression and
+ * the same libm) and resets the stream's meter. */
+int cmgpu_meter_result(cmgpu_ctx_t *ctx, unsigned stream, uint32_t rate, cmgpu_result_t *out);
+/* The finaliser alone (vumeter.c:198-212) on a snapshot: pure host arithmetic. */
+int cmgpu_finalise(const cmgpu_meter_state_t *state, uint32_t rate, unsigned channels,
+                   cmgpu_result_t *out);
+/* Device-side raw meter table for collectives: [max_streams][cmgpu_meter_row_u64()] uint64,
+ * row = { peak_key[channels], power[channels], frames, 0 }. cmgpu_meter_decode() turns rows
+ * gathered from other ranks into states on the host. */
+void    *cmgpu_device_meters(cmgpu_ctx_t *ctx);
+unsigned cmgpu_meter_row_u64(const cmgpu_ctx_t *ctx);
+int      cmgpu_meter_decode(const uint64_t *rows, unsigned count, unsigned channels,
+                            cmgpu_meter_state_t *out);
+
+/* ---- measurement ---------------------------------------------------------------- */
+/* Runs `reps` ticks over slots first_slot .. first_slot+n_slots-1 (cyclically) and returns the
+ * device time in milliseconds between CUDA events recorded on the compute stream around them. */
+int cmgpu_time_process(cmgpu_ctx_t *ctx, unsigned first_slot, unsigned n_slots, unsigned reps,
+                       unsigned flags, float *ms);
+/* Number of kernel launches this context has issued so far. */
+uint64_t cmgpu_launch_count(const cmgpu_ctx_t *ctx);
+/* Name of the kernel variant cmgpu_process would pick for the current shape (for logs). */
+const char *cmgpu_kernel_name(const cmgpu_ctx_t *ctx);
+
+/* ---- host-side gain arithmetic self-check (no device work) ------------------------ */
+/* The kernel divides by multiplying with a per-(stream,channel) reciprocal. This evaluates
+ * that integer recipe on the host for one sample so that tests can prove, exhaustively over
+ * all 65,536 inputs, that it equals trunc(x*gain/scale) saturated. Not a data path. */
+int cmgpu_recipe_eval(uint16_t gain, uint16_t scale, int16_t x);
+/* The same for every x: out[i] = recipe(x = i - 32768), i = 0..65535. */
+int cmgpu_recipe_table(uint16_t gain, uint16_t scale, int16_t out[65536]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

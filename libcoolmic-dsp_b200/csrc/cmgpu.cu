@@ -1,0 +1,804 @@
+// cmgpu.cu -- C-ABI batch engine (include/cmgpu.h) on top of the fused kernels.
+//
+// Host side of the hot path: owns the device ring, the per-stream gain recipes, the
+// per-stream meter rows, three CUDA streams (upload / compute / download) and the events
+// that order a slot's submit -> tick -> fetch. No PyTorch, no CPU fallback: every data-path
+// entry point ends in a CUDA call and fails with CMGPU_ERR_GENERIC if that call fails.
+#include "cmgpu_kernels.cuh"
+
+#include "../../include/cmgpu.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+using cmgpu::GainRow;
+using cmgpu::TickArgs;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(CMGPU_ERR_GENERIC, "%s failed: %s", #call, cudaGetErrorString(e__));       \
+    } while (0)
+
+// ---- the gain recipe (see GainRow in cmgpu_kernels.cuh, proof in DESIGN.md) ---------------
+struct RecipeHost {
+    uint32_t mw, addm, mul;
+};
+
+RecipeHost make_recipe(uint16_t g, uint16_t d)
+{
+    // d != 0 here. ratio = g/d in [0, 65535].
+    unsigned pre = 0;
+    if (g >= d) {
+        // 2^t <= g/d < 2^(t+1)  ->  pre = t + 1, so that M = floor(2^(32-pre) g/d) + 1 lies in [2^31, 2^32)
+        unsigned t = 0;
+        while (((uint64_t)d << (t + 1)) <= (uint64_t)g)
+            t++;
+        pre = t + 1;
+    }
+    const unsigned k = 32 - pre;
+    const uint64_t M = (((uint64_t)g << k) / d) + 1;       // g < 2^16, k <= 32: fits
+    RecipeHost r;
+    r.mw = (uint32_t)M;
+    r.addm = (M >> 31) ? 0xffffffffu : 0u;                  // M < 2^32 always
+    r.mul = 1u << pre;
+    return r;
+}
+
+int recipe_eval(const RecipeHost &r, int x)
+{
+    // bit-for-bit what apply_gain<true>() does on the device, in plain integer C
+    const int32_t X = (int32_t)((uint32_t)x * r.mul);
+    const int32_t mh = (int32_t)(((int64_t)X * (int64_t)(int32_t)r.mw) >> 32);
+    const int32_t hi = (int32_t)((uint32_t)mh + ((uint32_t)X & r.addm));
+    int32_t y = (int32_t)((uint32_t)hi + ((uint32_t)X >> 31));
+    if (y > 32767)
+        y = 32767;
+    if (y < -32768)
+        y = -32768;
+    return y;
+}
+
+unsigned ceil_log2(uint32_t v)
+{
+    unsigned b = 0;
+    while ((1ull << b) < v)
+        b++;
+    return b;
+}
+
+}  // namespace
+
+struct cmgpu_ctx {
+    int device = 0;
+    unsigned channels = 0, max_streams = 0, active = 0, slots = 0, block_frames = 0, flags = 0;
+    size_t stride = 0, slot_bytes = 0;
+    unsigned row_u64 = 0, pbits = 0;
+    uint64_t tick_seq = 0;
+    uint64_t launches = 0;
+    int num_sms = 0;
+
+    uint8_t *d_in = nullptr, *d_out = nullptr;     // rings
+    uint8_t *h_ring = nullptr;                     // pinned staging ring
+    GainRow *d_gains = nullptr;
+    std::vector<GainRow> h_gains;
+    std::vector<uint16_t> h_scale, h_gain;         // adapted settings, [stream], [stream][channels]
+    unsigned dirty_lo = 0, dirty_hi = 0;           // gain rows to upload: [lo, hi)
+    unsigned long long *d_meters = nullptr;
+    uint32_t *d_frames = nullptr;                  // [slots][max_streams]
+    std::vector<char> has_frames;
+    std::vector<uint64_t> scratch;                 // snapshot staging
+
+    cudaStream_t s_up = nullptr, s_cmp = nullptr, s_down = nullptr;
+    std::vector<cudaEvent_t> ev_up, ev_cmp, ev_down;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    std::mutex mu;
+
+    // launch plan (depends on shape only)
+    int plan_g = 32;              // lanes per item (fast kernels); 0 = generic kernel
+    uint32_t plan_items = 1, plan_per_item = 0;
+    int plan_grid_cap = 0;
+    char kname[64] = "";
+};
+
+namespace {
+
+template <int C, int G>
+cudaError_t launch_fast(const TickArgs &a, int grid, cudaStream_t st)
+{
+    cmgpu::fused_tick<C, G><<<grid, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int C>
+cudaError_t launch_fast_g(int g, const TickArgs &a, int grid, cudaStream_t st)
+{
+    switch (g) {
+    case 8:
+        if (C == 16)
+            return cudaErrorInvalidValue;
+        return launch_fast<C, (C == 16 ? 16 : 8)>(a, grid, st);
+    case 16:
+        return launch_fast<C, 16>(a, grid, st);
+    default:
+        return launch_fast<C, 32>(a, grid, st);
+    }
+}
+
+cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int grid)
+{
+    if (c->plan_g == 0) {
+        cmgpu::generic_tick<<<grid, 128, 0, c->s_cmp>>>(a, (int)c->channels);
+        return cudaGetLastError();
+    }
+    switch (c->channels) {
+    case 1:  return launch_fast_g<1>(c->plan_g, a, grid, c->s_cmp);
+    case 2:  return launch_fast_g<2>(c->plan_g, a, grid, c->s_cmp);
+    case 4:  return launch_fast_g<4>(c->plan_g, a, grid, c->s_cmp);
+    case 8:  return launch_fast_g<8>(c->plan_g, a, grid, c->s_cmp);
+    case 16: return launch_fast_g<16>(c->plan_g, a, grid, c->s_cmp);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+template <typename K>
+int occupancy(K kernel, int threads)
+{
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1)
+        n = 1;
+    return n;
+}
+
+int fast_occupancy(unsigned channels, int g)
+{
+    using namespace cmgpu;
+#define OCC(C, G) occupancy(fused_tick<C, G>, 256)
+    switch (channels) {
+    case 1:  return g == 8 ? OCC(1, 8) : g == 16 ? OCC(1, 16) : OCC(1, 32);
+    case 2:  return g == 8 ? OCC(2, 8) : g == 16 ? OCC(2, 16) : OCC(2, 32);
+    case 4:  return g == 8 ? OCC(4, 8) : g == 16 ? OCC(4, 16) : OCC(4, 32);
+    case 8:  return g == 8 ? OCC(8, 8) : g == 16 ? OCC(8, 16) : OCC(8, 32);
+    default: return g == 16 ? OCC(16, 16) : OCC(16, 32);
+    }
+#undef OCC
+}
+
+// Decide how a tick is cut into work items. Shape-only, so done once per context.
+void make_plan(cmgpu_ctx *c)
+{
+    const unsigned C = c->channels;
+    const bool fast = !(c->flags & CMGPU_FORCE_GENERIC) && (C == 1 || C == 2 || C == 4 || C == 8 || C == 16);
+    if (!fast) {
+        // generic: one warp per item, 32 frames per step; aim for <= 2048 frames per item
+        const uint32_t target = 2048;
+        uint32_t items = (c->block_frames + target - 1) / target;
+        uint32_t per = (c->block_frames + items - 1) / items;
+        per = (per + 31u) & ~31u;
+        items = (c->block_frames + per - 1) / per;
+        c->plan_g = 0;
+        c->plan_items = items;
+        c->plan_per_item = per;
+        c->plan_grid_cap = c->num_sms * occupancy(cmgpu::generic_tick, 128);
+        snprintf(c->kname, sizeof(c->kname), "generic_tick<C=%u>", C);
+        return;
+    }
+    const uint32_t nvec = (uint32_t)(c->stride / 16);
+    int g = 32;
+    if (nvec <= 64 && C != 16)
+        g = 8;
+    else if (nvec <= 256)
+        g = 16;
+    // aim for ~32 KiB (2048 vectors) per item, a multiple of 4 steps of the group
+    const uint32_t target = 2048;
+    uint32_t items = (nvec + target - 1) / target;
+    uint32_t per = (nvec + items - 1) / items;
+    const uint32_t quantum = (uint32_t)g * 4u;
+    per = (per + quantum - 1) / quantum * quantum;
+    items = (nvec + per - 1) / per;
+    c->plan_g = g;
+    c->plan_items = items;
+    c->plan_per_item = per;
+    c->plan_grid_cap = c->num_sms * fast_occupancy(C, g);
+    snprintf(c->kname, sizeof(c->kname), "fused_tick<C=%u,G=%d>", C, g);
+}
+
+int upload_gains_locked(cmgpu_ctx *c)
+{
+    if (c->dirty_lo >= c->dirty_hi)
+        return CMGPU_OK;
+    // pageable source: the runtime stages it before returning, later edits cannot race
+    CU(cudaMemcpyAsync(c->d_gains + c->dirty_lo, c->h_gains.data() + c->dirty_lo,
+                       sizeof(GainRow) * (c->dirty_hi - c->dirty_lo), cudaMemcpyHostToDevice, c->s_cmp));
+    c->dirty_lo = c->max_streams;
+    c->dirty_hi = 0;
+    return CMGPU_OK;
+}
+
+void mark_dirty(cmgpu_ctx *c, unsigned lo, unsigned hi)
+{
+    if (lo < c->dirty_lo)
+        c->dirty_lo = lo;
+    if (hi > c->dirty_hi)
+        c->dirty_hi = hi;
+}
+
+void set_row(cmgpu_ctx *c, unsigned s, uint16_t scale, const uint16_t *gain)
+{
+    GainRow &r = c->h_gains[s];
+    memset(&r, 0, sizeof(r));
+    c->h_scale[s] = scale;
+    bool identity = (scale == 0);
+    if (scale) {
+        bool unity = true;
+        for (unsigned ch = 0; ch < c->channels; ch++) {
+            c->h_gain[(size_t)s * c->channels + ch] = gain[ch];
+            RecipeHost h = make_recipe(gain[ch], scale);
+            r.mw[ch] = h.mw;
+            r.addm[ch] = h.addm;
+            r.mul[ch] = h.mul;
+            unity = unity && gain[ch] == scale;
+        }
+        identity = unity;     // trunc(x*d/d) == x and x is already inside the clamp range
+    }
+    for (unsigned ch = scale ? c->channels : 0; ch < 16; ch++)
+        r.mul[ch] = 1;
+    r.flags = identity ? cmgpu::kGainIdentity : 0;
+}
+
+int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags)
+{
+    int rc = upload_gains_locked(c);
+    if (rc)
+        return rc;
+    TickArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = c->d_in + (size_t)slot * c->slot_bytes;
+    a.out = (c->d_out ? c->d_out : c->d_in) + (size_t)slot * c->slot_bytes;
+    a.frames = c->has_frames[slot] ? c->d_frames + (size_t)slot * c->max_streams : nullptr;
+    a.gains = c->d_gains;
+    a.meters = c->d_meters;
+    a.pos_base = (c->tick_seq << c->pbits) & cmgpu::kKeyPosMask;
+    a.n_streams = c->active;
+    a.block_frames = c->block_frames;
+    a.stride_bytes = (uint32_t)c->stride;
+    a.items_per_block = c->plan_items;
+    a.per_item = c->plan_per_item;
+    a.row_u64 = c->row_u64;
+    a.transform = (flags & CMGPU_TRANSFORM) ? 1u : 0u;
+    a.meter = (flags & CMGPU_METER) ? 1u : 0u;
+    c->tick_seq++;
+    if (!c->active)
+        return CMGPU_OK;
+
+    const uint64_t items = (uint64_t)c->active * c->plan_items;
+    const uint64_t per_cta = c->plan_g ? 256u / (unsigned)c->plan_g : 4u;
+    uint64_t grid = (items + per_cta - 1) / per_cta;
+    if (grid > (uint64_t)c->plan_grid_cap)
+        grid = (uint64_t)c->plan_grid_cap;
+    CU(launch_tick(c, a, (int)grid));
+    c->launches++;
+    return CMGPU_OK;
+}
+
+void decode_row(const uint64_t *row, unsigned C, cmgpu_meter_state_t *st)
+{
+    memset(st, 0, sizeof(*st));
+    st->frames = row[2 * C];
+    uint32_t best_mag = 0;
+    uint64_t best_order = 0;
+    for (unsigned c = 0; c < C; c++) {
+        const uint64_t key = row[c];
+        const uint32_t mag = (uint32_t)(key >> cmgpu::kKeyMagShift);
+        const uint64_t pos = (~(key >> 1)) & cmgpu::kKeyPosMask;
+        const int v = (key & 1ull) ? -(int)mag : (int)mag;
+        st->channel_peak[c] = (int16_t)v;
+        st->power[c] = (int64_t)row[C + c];
+        // global peak (vumeter.c:163-168): first sample in interleaved order with the overall
+        // largest magnitude = the channel winner with the smallest (frame, channel)
+        if (mag) {
+            const uint64_t order = pos * 16u + c;
+            if (mag > best_mag || (mag == best_mag && order < best_order)) {
+                best_mag = mag;
+                best_order = order;
+                st->global_peak = (int16_t)v;
+            }
+        }
+    }
+}
+
+double power_db(double mean_square)
+{
+    // vumeter.c:204-205: p = 20*log10(sqrt(p)/32768); p = fmin(p, 0)
+    double p = 20. * log10(sqrt(mean_square) / 32768.);
+    return fmin(p, 0.);
+}
+
+bool slot_ok(const cmgpu_ctx *c, unsigned slot) { return c && slot < c->slots; }
+
+}  // namespace
+
+extern "C" {
+
+const char *cmgpu_version(void) { return "coolmic-b200 0.1 (sm_100a)"; }
+
+const char *cmgpu_last_error(void) { return g_err; }
+
+int cmgpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void *cmgpu_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        fail(CMGPU_ERR_NOMEM, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+
+void cmgpu_host_free(void *p)
+{
+    if (p)
+        cudaFreeHost(p);
+}
+
+cmgpu_ctx_t *cmgpu_ctx_create(int device, unsigned channels, unsigned max_streams, unsigned ring_slots,
+                              unsigned block_frames, unsigned flags)
+{
+    if (!channels || channels > CMGPU_MAX_CHANNELS || !max_streams || !ring_slots || !block_frames) {
+        fail(CMGPU_ERR_INVAL, "cmgpu_ctx_create: channels 1..16, streams, slots and block_frames must be non-zero");
+        return nullptr;
+    }
+    const uint64_t raw = (uint64_t)block_frames * channels * 2u;
+    if (raw > 0x7ffffff0ull) {
+        fail(CMGPU_ERR_INVAL, "cmgpu_ctx_create: stream-block of %llu bytes is too large", (unsigned long long)raw);
+        return nullptr;
+    }
+    int ndev = cmgpu_device_count();
+    if (device < 0 || device >= ndev) {
+        fail(CMGPU_ERR_GENERIC, "cmgpu_ctx_create: CUDA device %d not available (%d devices); there is no CPU fallback",
+             device, ndev);
+        return nullptr;
+    }
+    cmgpu_ctx *c = new (std::nothrow) cmgpu_ctx;
+    if (!c) {
+        fail(CMGPU_ERR_NOMEM, "out of host memory");
+        return nullptr;
+    }
+    c->device = device;
+    c->channels = channels;
+    c->max_streams = c->active = max_streams;
+    c->slots = ring_slots;
+    c->block_frames = block_frames;
+    c->flags = flags;
+    c->stride = (size_t)((raw + 15u) & ~15ull);
+    c->slot_bytes = c->stride * max_streams;
+    c->row_u64 = 2 * channels + 2;
+    c->pbits = ceil_log2(block_frames) ? ceil_log2(block_frames) : 1;
+
+    auto bail = [&](const char *what, cudaError_t e) -> cmgpu_ctx_t * {
+        fail(e == cudaErrorMemoryAllocation ? CMGPU_ERR_NOMEM : CMGPU_ERR_GENERIC, "cmgpu_ctx_create: %s: %s", what,
+             cudaGetErrorString(e));
+        cmgpu_ctx_destroy(c);
+        return nullptr;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess)
+        return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return bail("cudaGetDeviceProperties", e);
+    c->num_sms = prop.multiProcessorCount;
+    const size_t ring = c->slot_bytes * ring_slots;
+    if ((e = cudaMalloc(&c->d_in, ring)) != cudaSuccess)
+        return bail("cudaMalloc(ring)", e);
+    if ((flags & CMGPU_SEPARATE_OUT) && (e = cudaMalloc(&c->d_out, ring)) != cudaSuccess)
+        return bail("cudaMalloc(out ring)", e);
+    if ((e = cudaMemset(c->d_in, 0, ring)) != cudaSuccess || (c->d_out && (e = cudaMemset(c->d_out, 0, ring)) != cudaSuccess))
+        return bail("cudaMemset", e);
+    if (!(flags & CMGPU_NO_PINNED) && (e = cudaMallocHost(&c->h_ring, ring)) != cudaSuccess)
+        return bail("cudaMallocHost(staging)", e);
+    if (c->h_ring)
+        memset(c->h_ring, 0, ring);
+    if ((e = cudaMalloc(&c->d_gains, sizeof(GainRow) * max_streams)) != cudaSuccess)
+        return bail("cudaMalloc(gains)", e);
+    if ((e = cudaMalloc(&c->d_meters, sizeof(uint64_t) * c->row_u64 * max_streams)) != cudaSuccess)
+        return bail("cudaMalloc(meters)", e);
+    if ((e = cudaMemset(c->d_meters, 0, sizeof(uint64_t) * c->row_u64 * max_streams)) != cudaSuccess)
+        return bail("cudaMemset(meters)", e);
+    if ((e = cudaMalloc(&c->d_frames, sizeof(uint32_t) * (size_t)max_streams * ring_slots)) != cudaSuccess)
+        return bail("cudaMalloc(frames)", e);
+    if ((e = cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->s_cmp, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail("cudaStreamCreate", e);
+    c->ev_up.assign(ring_slots, nullptr);
+    c->ev_cmp.assign(ring_slots, nullptr);
+    c->ev_down.assign(ring_slots, nullptr);
+    for (unsigned i = 0; i < ring_slots; i++) {
+        if ((e = cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&c->ev_cmp[i], cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&c->ev_down[i], cudaEventDisableTiming)) != cudaSuccess)
+            return bail("cudaEventCreate", e);
+    }
+    if ((e = cudaEventCreate(&c->ev_t0)) != cudaSuccess || (e = cudaEventCreate(&c->ev_t1)) != cudaSuccess)
+        return bail("cudaEventCreate", e);
+
+    c->has_frames.assign(ring_slots, 0);
+    c->h_gains.resize(max_streams);
+    c->h_scale.assign(max_streams, 0);
+    c->h_gain.assign((size_t)max_streams * channels, 0);
+    for (unsigned s = 0; s < max_streams; s++)
+        set_row(c, s, 0, nullptr);
+    c->dirty_lo = 0;
+    c->dirty_hi = max_streams;
+    make_plan(c);
+    return c;
+}
+
+void cmgpu_ctx_destroy(cmgpu_ctx_t *c)
+{
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto ev : c->ev_up) if (ev) cudaEventDestroy(ev);
+    for (auto ev : c->ev_cmp) if (ev) cudaEventDestroy(ev);
+    for (auto ev : c->ev_down) if (ev) cudaEventDestroy(ev);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    if (c->s_up) cudaStreamDestroy(c->s_up);
+    if (c->s_cmp) cudaStreamDestroy(c->s_cmp);
+    if (c->s_down) cudaStreamDestroy(c->s_down);
+    cudaFree(c->d_in);
+    cudaFree(c->d_out);
+    cudaFree(c->d_gains);
+    cudaFree(c->d_meters);
+    cudaFree(c->d_frames);
+    if (c->h_ring)
+        cudaFreeHost(c->h_ring);
+    cudaGetLastError();
+    delete c;
+}
+
+unsigned cmgpu_channels(const cmgpu_ctx_t *c) { return c ? c->channels : 0; }
+unsigned cmgpu_max_streams(const cmgpu_ctx_t *c) { return c ? c->max_streams : 0; }
+unsigned cmgpu_ring_slots(const cmgpu_ctx_t *c) { return c ? c->slots : 0; }
+unsigned cmgpu_block_frames(const cmgpu_ctx_t *c) { return c ? c->block_frames : 0; }
+size_t cmgpu_block_stride(const cmgpu_ctx_t *c) { return c ? c->stride : 0; }
+size_t cmgpu_slot_bytes(const cmgpu_ctx_t *c) { return c ? c->slot_bytes : 0; }
+uint64_t cmgpu_launch_count(const cmgpu_ctx_t *c) { return c ? c->launches : 0; }
+const char *cmgpu_kernel_name(const cmgpu_ctx_t *c) { return c ? c->kname : ""; }
+unsigned cmgpu_meter_row_u64(const cmgpu_ctx_t *c) { return c ? c->row_u64 : 0; }
+void *cmgpu_device_meters(cmgpu_ctx_t *c) { return c ? c->d_meters : nullptr; }
+
+int cmgpu_set_active_streams(cmgpu_ctx_t *c, unsigned n)
+{
+    if (!c)
+        return fail(CMGPU_ERR_FAULT, "NULL context");
+    if (n > c->max_streams)
+        return fail(CMGPU_ERR_INVAL, "active streams %u > max_streams %u", n, c->max_streams);
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->active = n;
+    return CMGPU_OK;
+}
+
+int cmgpu_stream_set_gain(cmgpu_ctx_t *c, unsigned stream, unsigned n, uint16_t scale, const uint16_t *gain)
+{
+    if (!c)
+        return fail(CMGPU_ERR_FAULT, "NULL context");
+    if (stream >= c->max_streams)
+        return fail(CMGPU_ERR_INVAL, "stream %u out of range", stream);
+    std::lock_guard<std::mutex> lk(c->mu);
+    uint16_t g[CMGPU_MAX_CHANNELS];
+    // transform.c:200-221
+    if (!n || !scale || !gain) {
+        set_row(c, stream, 0, nullptr);
+    } else if (n == c->channels) {
+        memcpy(g, gain, sizeof(uint16_t) * n);
+        set_row(c, stream, scale, g);
+    } else if (n == 1) {
+        for (unsigned ch = 0; ch < c->channels; ch++)
+            g[ch] = gain[0];
+        set_row(c, stream, scale, g);
+    } else if (n == 2 && c->channels == 1) {
+        g[0] = (uint16_t)(((uint32_t)gain[0] + (uint32_t)gain[1]) / 2u);
+        set_row(c, stream, scale, g);
+    } else {
+        return fail(CMGPU_ERR_INVAL, "gain for %u channels cannot be mapped onto %u", n, c->channels);
+    }
+    mark_dirty(c, stream, stream + 1);
+    return CMGPU_OK;
+}
+
+int cmgpu_set_gain_table(cmgpu_ctx_t *c, unsigned first, unsigned count, const uint16_t *scale, const uint16_t *gain)
+{
+    if (!c || !scale || !gain)
+        return fail(CMGPU_ERR_FAULT, "NULL argument");
+    if ((uint64_t)first + count > c->max_streams)
+        return fail(CMGPU_ERR_INVAL, "stream range out of bounds");
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (unsigned i = 0; i < count; i++)
+        set_row(c, first + i, scale[i], gain + (size_t)i * c->channels);
+    if (count)
+        mark_dirty(c, first, first + count);
+    return CMGPU_OK;
+}
+
+int cmgpu_stream_get_gain(const cmgpu_ctx_t *c, unsigned stream, uint16_t *scale, uint16_t gain[CMGPU_MAX_CHANNELS])
+{
+    if (!c || !scale || !gain)
+        return fail(CMGPU_ERR_FAULT, "NULL argument");
+    if (stream >= c->max_streams)
+        return fail(CMGPU_ERR_INVAL, "stream %u out of range", stream);
+    *scale = c->h_scale[stream];
+    for (unsigned ch = 0; ch < CMGPU_MAX_CHANNELS; ch++)
+        gain[ch] = ch < c->channels ? c->h_gain[(size_t)stream * c->channels + ch] : 0;
+    return CMGPU_OK;
+}
+
+void *cmgpu_host_slot(cmgpu_ctx_t *c, unsigned slot)
+{
+    return slot_ok(c, slot) && c->h_ring ? c->h_ring + (size_t)slot * c->slot_bytes : nullptr;
+}
+void *cmgpu_device_slot(cmgpu_ctx_t *c, unsigned slot)
+{
+    return slot_ok(c, slot) ? c->d_in + (size_t)slot * c->slot_bytes : nullptr;
+}
+void *cmgpu_device_out_slot(cmgpu_ctx_t *c, unsigned slot)
+{
+    return slot_ok(c, slot) ? (c->d_out ? c->d_out : c->d_in) + (size_t)slot * c->slot_bytes : nullptr;
+}
+
+int cmgpu_slot_set_frames(cmgpu_ctx_t *c, unsigned slot, const uint32_t *frames)
+{
+    if (!slot_ok(c, slot))
+        return fail(c ? CMGPU_ERR_INVAL : CMGPU_ERR_FAULT, "bad context or slot");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!frames) {
+        c->has_frames[slot] = 0;
+        return CMGPU_OK;
+    }
+    for (unsigned s = 0; s < c->active; s++)
+        if (frames[s] > c->block_frames)
+            return fail(CMGPU_ERR_INVAL, "stream %u: %u frames > block_frames %u", s, frames[s], c->block_frames);
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(c->d_frames + (size_t)slot * c->max_streams, frames, sizeof(uint32_t) * c->active,
+                       cudaMemcpyHostToDevice, c->s_cmp));
+    c->has_frames[slot] = 1;
+    return CMGPU_OK;
+}
+
+int cmgpu_submit(cmgpu_ctx_t *c, unsigned slot, const void *host)
+{
+    if (!slot_ok(c, slot))
+        return fail(c ? CMGPU_ERR_INVAL : CMGPU_ERR_FAULT, "bad context or slot");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!host)
+        host = c->h_ring ? c->h_ring + (size_t)slot * c->slot_bytes : nullptr;
+    if (!host)
+        return fail(CMGPU_ERR_FAULT, "no host buffer and no pinned staging");
+    CU(cudaSetDevice(c->device));
+    // the slot must not be overwritten while its previous tick or download is in flight
+    CU(cudaStreamWaitEvent(c->s_up, c->ev_cmp[slot], 0));
+    CU(cudaStreamWaitEvent(c->s_up, c->ev_down[slot], 0));
+    CU(cudaMemcpyAsync(c->d_in + (size_t)slot * c->slot_bytes, host, c->stride * c->active, cudaMemcpyHostToDevice,
+                       c->s_up));
+    CU(cudaEventRecord(c->ev_up[slot], c->s_up));
+    return CMGPU_OK;
+}
+
+int cmgpu_process(cmgpu_ctx_t *c, unsigned slot, unsigned flags)
+{
+    if (!slot_ok(c, slot))
+        return fail(c ? CMGPU_ERR_INVAL : CMGPU_ERR_FAULT, "bad context or slot");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamWaitEvent(c->s_cmp, c->ev_up[slot], 0));
+    CU(cudaStreamWaitEvent(c->s_cmp, c->ev_down[slot], 0));
+    int rc = launch_locked(c, slot, flags);
+    if (rc)
+        return rc;
+    CU(cudaEventRecord(c->ev_cmp[slot], c->s_cmp));
+    return CMGPU_OK;
+}
+
+int cmgpu_fetch(cmgpu_ctx_t *c, unsigned slot, void *host)
+{
+    if (!slot_ok(c, slot))
+        return fail(c ? CMGPU_ERR_INVAL : CMGPU_ERR_FAULT, "bad context or slot");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!host)
+        host = c->h_ring ? c->h_ring + (size_t)slot * c->slot_bytes : nullptr;
+    if (!host)
+        return fail(CMGPU_ERR_FAULT, "no host buffer and no pinned staging");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamWaitEvent(c->s_down, c->ev_cmp[slot], 0));
+    CU(cudaStreamWaitEvent(c->s_down, c->ev_up[slot], 0));
+    const uint8_t *src = (c->d_out ? c->d_out : c->d_in) + (size_t)slot * c->slot_bytes;
+    CU(cudaMemcpyAsync(host, src, c->stride * c->active, cudaMemcpyDeviceToHost, c->s_down));
+    CU(cudaEventRecord(c->ev_down[slot], c->s_down));
+    return CMGPU_OK;
+}
+
+int cmgpu_sync(cmgpu_ctx_t *c)
+{
+    if (!c)
+        return fail(CMGPU_ERR_FAULT, "NULL context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->s_up));
+    CU(cudaStreamSynchronize(c->s_cmp));
+    CU(cudaStreamSynchronize(c->s_down));
+    return CMGPU_OK;
+}
+
+int cmgpu_slot_wait(cmgpu_ctx_t *c, unsigned slot)
+{
+    if (!slot_ok(c, slot))
+        return fail(c ? CMGPU_ERR_INVAL : CMGPU_ERR_FAULT, "bad context or slot");
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventSynchronize(c->ev_up[slot]));
+    CU(cudaEventSynchronize(c->ev_cmp[slot]));
+    CU(cudaEventSynchronize(c->ev_down[slot]));
+    return CMGPU_OK;
+}
+
+int cmgpu_meter_decode(const uint64_t *rows, unsigned count, unsigned channels, cmgpu_meter_state_t *out)
+{
+    if (!rows || !out)
+        return fail(CMGPU_ERR_FAULT, "NULL argument");
+    if (!channels || channels > CMGPU_MAX_CHANNELS)
+        return fail(CMGPU_ERR_INVAL, "channels out of range");
+    const unsigned row = 2 * channels + 2;
+    for (unsigned i = 0; i < count; i++)
+        decode_row(rows + (size_t)i * row, channels, out + i);
+    return CMGPU_OK;
+}
+
+int cmgpu_meter_snapshot(cmgpu_ctx_t *c, unsigned first, unsigned count, cmgpu_meter_state_t *out, int reset)
+{
+    if (!c || !out)
+        return fail(CMGPU_ERR_FAULT, "NULL argument");
+    if ((uint64_t)first + count > c->max_streams)
+        return fail(CMGPU_ERR_INVAL, "stream range out of bounds");
+    if (!count)
+        return CMGPU_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    const size_t n = (size_t)count * c->row_u64;
+    c->scratch.resize(n);
+    unsigned long long *src = c->d_meters + (size_t)first * c->row_u64;
+    CU(cudaMemcpyAsync(c->scratch.data(), src, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->s_cmp));
+    if (reset)
+        CU(cudaMemsetAsync(src, 0, n * sizeof(uint64_t), c->s_cmp));
+    CU(cudaStreamSynchronize(c->s_cmp));
+    for (unsigned i = 0; i < count; i++)
+        decode_row(c->scratch.data() + (size_t)i * c->row_u64, c->channels, out + i);
+    return CMGPU_OK;
+}
+
+int cmgpu_meter_reset(cmgpu_ctx_t *c, unsigned first, unsigned count)
+{
+    if (!c)
+        return fail(CMGPU_ERR_FAULT, "NULL context");
+    if ((uint64_t)first + count > c->max_streams)
+        return fail(CMGPU_ERR_INVAL, "stream range out of bounds");
+    if (!count)
+        return CMGPU_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->d_meters + (size_t)first * c->row_u64, 0, sizeof(uint64_t) * c->row_u64 * count, c->s_cmp));
+    return CMGPU_OK;
+}
+
+int cmgpu_finalise(const cmgpu_meter_state_t *st, uint32_t rate, unsigned channels, cmgpu_result_t *out)
+{
+    if (!st || !out)
+        return fail(CMGPU_ERR_FAULT, "NULL argument");
+    if (!channels || channels > CMGPU_MAX_CHANNELS)
+        return fail(CMGPU_ERR_INVAL, "channels out of range");
+    if (!st->frames)
+        return CMGPU_ERR_INVAL;                     // vumeter.c:198-199
+    memset(out, 0, sizeof(*out));
+    out->rate = rate;
+    out->channels = channels;
+    out->frames = st->frames;
+    out->global_peak = st->global_peak;
+    int64_t all = 0;
+    for (unsigned ch = 0; ch < channels; ch++) {
+        all += st->power[ch];
+        out->channel_peak[ch] = st->channel_peak[ch];
+        // vumeter.c:203: signed integer division first, then the conversion to double
+        out->channel_power[ch] = power_db((double)(st->power[ch] / (int64_t)st->frames));
+    }
+    // vumeter.c:209: unsigned division by frames * channels
+    out->global_power = power_db((double)((uint64_t)all / (uint64_t)(st->frames * (uint64_t)channels)));
+    return CMGPU_OK;
+}
+
+int cmgpu_meter_result(cmgpu_ctx_t *c, unsigned stream, uint32_t rate, cmgpu_result_t *out)
+{
+    if (!c || !out)
+        return fail(CMGPU_ERR_FAULT, "NULL argument");
+    cmgpu_meter_state_t st;
+    int rc = cmgpu_meter_snapshot(c, stream, 1, &st, 0);
+    if (rc)
+        return rc;
+    rc = cmgpu_finalise(&st, rate, c->channels, out);
+    if (rc)
+        return rc;
+    return cmgpu_meter_reset(c, stream, 1);
+}
+
+int cmgpu_time_process(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, unsigned reps, unsigned flags, float *ms)
+{
+    if (!c || !ms)
+        return fail(CMGPU_ERR_FAULT, "NULL argument");
+    if (!n_slots || (uint64_t)first_slot + n_slots > c->slots)
+        return fail(CMGPU_ERR_INVAL, "slot range out of bounds");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->s_up));
+    CU(cudaStreamSynchronize(c->s_down));
+    int rc = upload_gains_locked(c);
+    if (rc)
+        return rc;
+    CU(cudaEventRecord(c->ev_t0, c->s_cmp));
+    for (unsigned r = 0; r < reps; r++) {
+        rc = launch_locked(c, first_slot + r % n_slots, flags);
+        if (rc)
+            return rc;
+    }
+    CU(cudaEventRecord(c->ev_t1, c->s_cmp));
+    CU(cudaEventSynchronize(c->ev_t1));
+    CU(cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
+    return CMGPU_OK;
+}
+
+int cmgpu_recipe_eval(uint16_t gain, uint16_t scale, int16_t x)
+{
+    if (!scale)
+        return x;
+    return recipe_eval(make_recipe(gain, scale), x);
+}
+
+int cmgpu_recipe_table(uint16_t gain, uint16_t scale, int16_t out[65536])
+{
+    if (!out)
+        return fail(CMGPU_ERR_FAULT, "NULL argument");
+    RecipeHost r = make_recipe(gain, scale ? scale : 1);
+    for (int i = 0; i < 65536; i++)
+        out[i] = (int16_t)(scale ? recipe_eval(r, i - 32768) : i - 32768);
+    return CMGPU_OK;
+}
+
+}  // extern "C"

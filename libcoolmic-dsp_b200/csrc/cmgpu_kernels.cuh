@@ -1,0 +1,449 @@
+// cmgpu_kernels.cuh -- the fused transform + vumeter kernels (sm_100a).
+//
+// One launch ("tick") walks every active stream-block of a ring slot exactly once:
+//   128-bit coalesced load -> per-sample gain (exact truncating division by multiplying with a
+//   per-(stream,channel) reciprocal) -> saturate -> 128-bit store, and in the same pass the
+//   meter's per-channel first-occurrence peak + exact sum of squares, reduced with warp
+//   shuffles and merged into the per-stream state with 64-bit atomics.
+//
+// What is being computed (reference file:line):
+//   transform.c:110-123   y = clamp16(trunc((int64)x * gain[c] / scale))
+//   vumeter.c:161-175     peak[c] = first sample with the largest |y|; power[c] += y*y
+//
+// HBM-bound integer work: no tensor cores (no contraction exists), no shared memory (no reuse).
+// Algorithmic traffic: 2 B read + 2 B written per sample; the meter adds none.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace cmgpu {
+
+// ---- device tables ---------------------------------------------------------------------
+
+// Per-stream gain recipe, one row per stream (device resident, 16-byte aligned).
+// For channel c:   X  = x * mul[c]                      (mul = 2^pre, pre in 0..16)
+//                  hi = mulhi_s32(X, (int)mw[c]) + (X & addm[c])
+//                  y  = clamp16(hi + (X >>> 31))
+// which equals trunc(x*g/d) for every int16 x wherever the true quotient is inside the clamp
+// range and clamps identically outside (proof: DESIGN.md "Exact division"; exhaustive test:
+// tests/test_recipe.py through cmgpu_recipe_eval()).
+struct GainRow {
+    uint32_t mw[16];     // low 32 bits of M = floor(2^k * g/d) + 1
+    uint32_t addm[16];   // all-ones when M >= 2^31 (then mulhi_s32 misses +X), else 0
+    uint32_t mul[16];    // 2^pre
+    uint32_t flags;      // bit 0: identity (scale == 0, or every gain[c] == scale)
+    uint32_t pad[3];
+};
+static_assert(sizeof(GainRow) == 208, "GainRow layout");
+
+constexpr uint32_t kGainIdentity = 1u;
+
+// Meter row per stream: { peak_key[C], power[C], frames, 0 } as uint64.
+// peak_key = mag(17 bits) << 47 | (~position & (2^46-1)) << 1 | negative
+// so that a 64-bit atomicMax keeps the largest magnitude and, among equals, the earliest
+// position -- exactly the strict '>' update of vumeter.c:163. position = tick << pbits | frame.
+constexpr int      kKeyMagShift = 47;
+constexpr uint64_t kKeyPosMask = (1ull << 46) - 1ull;
+
+struct TickArgs {
+    const uint8_t *in;          // slot base (device)
+    uint8_t *out;               // == in when working in place
+    const uint32_t *frames;     // valid frames per stream, or nullptr = block_frames each
+    const GainRow *gains;
+    unsigned long long *meters;
+    uint64_t pos_base;          // tick sequence number << pbits
+    uint32_t n_streams;
+    uint32_t block_frames;
+    uint32_t stride_bytes;      // bytes between stream-blocks (multiple of 16)
+    uint32_t items_per_block;   // work items (chunks) per stream-block
+    uint32_t per_item;          // vectors (fast kernels) or frames (generic kernel) per item
+    uint32_t row_u64;           // meter row length in uint64
+    uint32_t transform;         // apply gains (else identity for every stream)
+    uint32_t meter;             // accumulate meters
+};
+
+// ---- small helpers -----------------------------------------------------------------------
+
+__device__ __forceinline__ uint4 ld_stream(const uint8_t *p)
+{
+    return __ldcs(reinterpret_cast<const uint4 *>(p));
+}
+__device__ __forceinline__ void st_stream(uint8_t *p, uint4 v)
+{
+    __stcs(reinterpret_cast<uint4 *>(p), v);
+}
+
+__device__ __forceinline__ uint64_t shfl_xor64(unsigned mask, uint64_t v, int off)
+{
+    uint32_t lo = __shfl_xor_sync(mask, (uint32_t)v, off);
+    uint32_t hi = __shfl_xor_sync(mask, (uint32_t)(v >> 32), off);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ uint64_t make_key(uint32_t mag, uint64_t pos)
+{
+    return mag ? (((uint64_t)mag << kKeyMagShift) | (((~pos) & kKeyPosMask) << 1)) : 0ull;
+}
+
+// One sample through the gain recipe (see GainRow).
+struct Recipe {
+    int mw;
+    int addm;
+    int mul;
+};
+
+template <bool GAIN>
+__device__ __forceinline__ int apply_gain(int x, const Recipe &r)
+{
+    if (!GAIN)
+        return x;
+    int X = x * r.mul;
+    int hi = __mulhi(X, r.mw) + (X & r.addm);
+    int y = hi + (int)((unsigned)X >> 31);
+    return max(min(y, 32767), -32768);
+}
+
+// ---- fast kernels: channel counts that divide (or are a multiple of) one 16-byte vector -----
+//
+// Work item = (stream, chunk of `per_item` consecutive 16-byte vectors of its stream-block),
+// owned by a group of G lanes (G = 8, 16 or 32; small stream-blocks use small groups so that no
+// lane idles). Lane l of the group visits vectors v0 + l + G*i, i = 0,1,...: every load/store
+// instruction of a group touches one contiguous G*16-byte run.
+//
+// Per lane the 8 sample slots of its vectors map to fixed channels, so the meter keeps 8
+// (key, power) register pairs and never indexes dynamically. In-loop peak key (32 bit):
+//   mag << 16 | (0xFFFF - i)   -> max() keeps the largest magnitude, then the earliest visit.
+// Order of time inside an item is (i, lane, slot), which the reduction preserves by widening
+// to the 64-bit position key before lanes are combined.
+
+template <int C>
+struct Shape {
+    static constexpr int kPerLane = C < 8 ? C : 8;      // distinct channels a lane sees
+    static constexpr int kLanesPerFrame = C <= 8 ? 1 : C / 8;
+    static constexpr int kFramesPerVec8 = 8 / kPerLane; // frames per vector when C <= 8
+};
+
+template <int C, bool GAIN, bool METER, bool MASKED>
+__device__ __forceinline__ uint4 do_vector(uint4 w, const Recipe (&rc)[Shape<C>::kPerLane], uint32_t radd,
+                                           uint32_t (&kmax)[8], uint64_t (&pacc)[8], int nvalid)
+{
+    constexpr int P = Shape<C>::kPerLane;
+    uint32_t in[4] = {w.x, w.y, w.z, w.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int k0 = 2 * j, k1 = 2 * j + 1;
+        int x0 = (int)(short)(in[j] & 0xffffu);
+        int x1 = (int)in[j] >> 16;
+        int y0 = apply_gain<GAIN>(x0, rc[k0 % P]);
+        int y1 = apply_gain<GAIN>(x1, rc[k1 % P]);
+        int m0 = y0, m1 = y1;
+        if (MASKED) {
+            // samples past the valid frames: pass through, invisible to the meter
+            if (k0 >= nvalid) { y0 = x0; m0 = 0; }
+            if (k1 >= nvalid) { y1 = x1; m1 = 0; }
+        }
+        if (METER) {
+            uint32_t a0 = (uint32_t)abs(m0), a1 = (uint32_t)abs(m1);
+            kmax[k0] = max(kmax[k0], (a0 << 16) + radd);
+            kmax[k1] = max(kmax[k1], (a1 << 16) + radd);
+            pacc[k0] += (uint64_t)(a0 * a0);
+            pacc[k1] += (uint64_t)(a1 * a1);
+        }
+        o[j] = ((uint32_t)y0 & 0xffffu) | ((uint32_t)y1 << 16);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+template <int C, int G, bool GAIN, bool STORE, bool METER>
+__device__ __forceinline__ void run_item(const TickArgs &a, uint32_t s, uint32_t v0, uint32_t v1,
+                                         uint32_t valid_bytes, uint32_t gl, unsigned gmask)
+{
+    constexpr int P = Shape<C>::kPerLane;
+    constexpr int UNROLL = 4;
+    const size_t base = (size_t)s * a.stride_bytes;
+    const uint8_t *in = a.in + base;
+    uint8_t *out = a.out + base;
+
+    Recipe rc[P];
+    if (GAIN) {
+        const GainRow *g = a.gains + s;
+        // C == 16: even lanes own channels 0-7, odd lanes 8-15 (v0 and G are even)
+        const int cbase = (C == 16) ? (int)(gl & 1u) * 8 : 0;
+#pragma unroll
+        for (int c = 0; c < P; c++) {
+            rc[c].mw = (int)__ldg(&g->mw[cbase + c]);
+            rc[c].addm = (int)__ldg(&g->addm[cbase + c]);
+            rc[c].mul = (int)__ldg(&g->mul[cbase + c]);
+        }
+    }
+
+    uint32_t kmax[8];
+    uint64_t pacc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        kmax[k] = 0;
+        pacc[k] = 0;
+    }
+
+    const uint32_t vfull = min(v1, valid_bytes >> 4);     // vectors [v0, vfull) are entirely valid
+    const uint32_t first = v0 + gl;
+    // number of this lane's vectors below vfull
+    const uint32_t n_i = first < vfull ? (vfull - first + (G - 1)) / G : 0;
+
+    uint32_t i = 0;
+    for (; i + UNROLL <= n_i; i += UNROLL) {
+        uint4 w[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++)
+            w[u] = ld_stream(in + (size_t)(first + (i + u) * G) * 16);
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            uint4 o = do_vector<C, GAIN, METER, false>(w[u], rc, 0xffffu - (i + u), kmax, pacc, 8);
+            if (STORE)
+                st_stream(out + (size_t)(first + (i + u) * G) * 16, o);
+        }
+    }
+    for (; i < n_i; i++) {
+        uint4 w = ld_stream(in + (size_t)(first + i * G) * 16);
+        uint4 o = do_vector<C, GAIN, METER, false>(w, rc, 0xffffu - i, kmax, pacc, 8);
+        if (STORE)
+            st_stream(out + (size_t)(first + i * G) * 16, o);
+    }
+    // the one vector that straddles the end of the valid frames, if it lies in this item
+    if (vfull < v1 && (vfull << 4) < valid_bytes && ((vfull - v0) % G) == gl) {
+        const uint32_t it = (vfull - v0) / G;
+        const int nvalid = (int)((valid_bytes - (vfull << 4)) >> 1);
+        uint4 w = ld_stream(in + (size_t)vfull * 16);
+        uint4 o = do_vector<C, GAIN, METER, true>(w, rc, 0xffffu - it, kmax, pacc, nvalid);
+        if (STORE)
+            st_stream(out + (size_t)vfull * 16, o);
+    }
+
+    if (!METER)
+        return;
+
+    // ---- widen to position keys, fold slots of the same channel, combine lanes -------------
+    uint64_t kc[P], pc[P];
+#pragma unroll
+    for (int c = 0; c < P; c++) {
+        kc[c] = 0;
+        pc[c] = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t mag = kmax[k] >> 16;
+        const uint32_t it = 0xffffu - (kmax[k] & 0xffffu);
+        const uint32_t v = first + it * G;
+        // frame index of slot k of vector v inside the stream-block
+        const uint32_t frame = (C <= 8) ? (v * (uint32_t)Shape<C>::kFramesPerVec8 + (uint32_t)(k / P))
+                                        : (v >> 1);
+        const uint64_t key = make_key(mag, a.pos_base + frame);
+        kc[k % P] = max(kc[k % P], key);
+        pc[k % P] += pacc[k];
+    }
+#pragma unroll
+    for (int off = G / 2; off >= Shape<C>::kLanesPerFrame; off >>= 1) {
+#pragma unroll
+        for (int c = 0; c < P; c++) {
+            kc[c] = max(kc[c], shfl_xor64(gmask, kc[c], off));
+            pc[c] += shfl_xor64(gmask, pc[c], off);
+        }
+    }
+
+    // lane L publishes one channel: C <= 8 -> channel L; C == 16 -> channel 8*(L&1) + (L>>1)
+    uint64_t key = 0, pw = 0;
+    const int sel = (C == 16) ? (int)(gl >> 1) : (int)gl;
+#pragma unroll
+    for (int c = 0; c < P; c++) {
+        if (sel == c) {
+            key = kc[c];
+            pw = pc[c];
+        }
+    }
+    const int ch = (C == 16) ? (int)((gl & 1u) * 8u + (gl >> 1)) : (int)gl;
+    __syncwarp(gmask);       // make the item's stores visible to the lane that re-reads a sample
+    if ((int)gl < C) {
+        unsigned long long *row = a.meters + (size_t)s * a.row_u64;
+        if (key) {
+            // the sign of the winning sample: re-read it from where it was written
+            const uint64_t pos = (~(key >> 1)) & kKeyPosMask;
+            const uint32_t frame = (uint32_t)(pos - a.pos_base);
+            const volatile int16_t *y = reinterpret_cast<const volatile int16_t *>(out);
+            const int yv = y[(size_t)frame * C + ch];
+            atomicMax(row + ch, (unsigned long long)(key | (yv < 0 ? 1ull : 0ull)));
+        }
+        if (pw)
+            atomicAdd(row + C + ch, (unsigned long long)pw);
+    }
+}
+
+template <int C, int G>
+__global__ void __launch_bounds__(256) fused_tick(const TickArgs a)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gl = threadIdx.x & (G - 1);
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(uint32_t)(G - 1)));
+    const uint32_t groups_per_cta = 256 / G;
+    const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block;
+    const uint64_t stride = (uint64_t)gridDim.x * groups_per_cta;
+
+    for (uint64_t item = (uint64_t)blockIdx.x * groups_per_cta + threadIdx.x / G; item < n_items; item += stride) {
+        const uint32_t s = (uint32_t)(item / a.items_per_block);
+        const uint32_t chunk = (uint32_t)(item - (uint64_t)s * a.items_per_block);
+        const uint32_t nfr = a.frames ? min(__ldg(a.frames + s), a.block_frames) : a.block_frames;
+        const uint32_t valid_bytes = nfr * (uint32_t)(2 * C);
+        const uint32_t nvec = (valid_bytes + 15u) >> 4;
+        const uint32_t v0 = chunk * a.per_item;
+        const uint32_t v1 = min(v0 + a.per_item, nvec);
+
+        if (a.meter && chunk == 0 && gl == 0 && nfr)
+            atomicAdd(a.meters + (size_t)s * a.row_u64 + 2 * C, (unsigned long long)nfr);
+        if (v0 >= v1)
+            continue;
+
+        const bool identity = !a.transform || (__ldg(&a.gains[s].flags) & kGainIdentity);
+        const bool inplace = (a.in == a.out);
+        if (a.meter) {
+            if (!identity)
+                run_item<C, G, true, true, true>(a, s, v0, v1, valid_bytes, gl, gmask);
+            else if (inplace)
+                run_item<C, G, false, false, true>(a, s, v0, v1, valid_bytes, gl, gmask);
+            else
+                run_item<C, G, false, true, true>(a, s, v0, v1, valid_bytes, gl, gmask);
+        } else {
+            if (!identity)
+                run_item<C, G, true, true, false>(a, s, v0, v1, valid_bytes, gl, gmask);
+            else if (!inplace)
+                run_item<C, G, false, true, false>(a, s, v0, v1, valid_bytes, gl, gmask);
+        }
+    }
+}
+
+// ---- generic kernel: any channel count 1..16 -------------------------------------------------
+//
+// Work item = (stream, chunk of `per_item` frames), one warp per item, lane l visits frames
+// f0 + l + 32*i and walks the frame's channels with 16-bit accesses. Used for channel counts
+// that do not tile a 16-byte vector (3, 5, 6, 7, 9..15) and as an independently written
+// cross-check of the fast kernels (CMGPU_FORCE_GENERIC).
+
+template <bool GAIN, bool STORE, bool METER>
+__device__ __forceinline__ void run_item_generic(const TickArgs &a, int C, uint32_t s, uint32_t f0, uint32_t f1,
+                                                 uint32_t lane)
+{
+    const size_t base = (size_t)s * a.stride_bytes;
+    const int16_t *in = reinterpret_cast<const int16_t *>(a.in + base);
+    int16_t *out = reinterpret_cast<int16_t *>(a.out + base);
+
+    Recipe rc[16];
+    uint32_t kmax[16];
+    uint64_t pacc[16];
+#pragma unroll
+    for (int c = 0; c < 16; c++) {
+        kmax[c] = 0;
+        pacc[c] = 0;
+        rc[c].mw = rc[c].addm = 0;
+        rc[c].mul = 1;
+        if (GAIN && c < C) {
+            const GainRow *g = a.gains + s;
+            rc[c].mw = (int)__ldg(&g->mw[c]);
+            rc[c].addm = (int)__ldg(&g->addm[c]);
+            rc[c].mul = (int)__ldg(&g->mul[c]);
+        }
+    }
+
+    uint32_t i = 0;
+    for (uint32_t f = f0 + lane; f < f1; f += 32, i++) {
+        const size_t o = (size_t)f * C;
+        const uint32_t radd = 0xffffu - i;
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            if (c < C) {
+                const int x = in[o + c];
+                const int y = apply_gain<GAIN>(x, rc[c]);
+                if (STORE)
+                    out[o + c] = (int16_t)y;
+                if (METER) {
+                    const uint32_t m = (uint32_t)abs(y);
+                    kmax[c] = max(kmax[c], (m << 16) + radd);
+                    pacc[c] += (uint64_t)(m * m);
+                }
+            }
+        }
+    }
+    if (!METER)
+        return;
+
+    uint64_t key = 0, pw = 0;
+#pragma unroll
+    for (int c = 0; c < 16; c++) {
+        if (c < C) {
+            const uint32_t mag = kmax[c] >> 16;
+            const uint32_t it = 0xffffu - (kmax[c] & 0xffffu);
+            uint64_t k = make_key(mag, a.pos_base + (f0 + lane + 32u * it));
+            uint64_t p = pacc[c];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                k = max(k, shfl_xor64(0xffffffffu, k, off));
+                p += shfl_xor64(0xffffffffu, p, off);
+            }
+            if ((int)lane == c) {
+                key = k;
+                pw = p;
+            }
+        }
+    }
+    __syncwarp();
+    if ((int)lane < C) {
+        unsigned long long *row = a.meters + (size_t)s * a.row_u64;
+        if (key) {
+            const uint64_t pos = (~(key >> 1)) & kKeyPosMask;
+            const uint32_t frame = (uint32_t)(pos - a.pos_base);
+            const volatile int16_t *y = out;
+            const int yv = y[(size_t)frame * C + lane];
+            atomicMax(row + lane, (unsigned long long)(key | (yv < 0 ? 1ull : 0ull)));
+        }
+        if (pw)
+            atomicAdd(row + C + lane, (unsigned long long)pw);
+    }
+}
+
+__global__ void __launch_bounds__(128) generic_tick(const TickArgs a, const int C)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps_per_cta = 128 / 32;
+    const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block;
+    const uint64_t stride = (uint64_t)gridDim.x * warps_per_cta;
+
+    for (uint64_t item = (uint64_t)blockIdx.x * warps_per_cta + threadIdx.x / 32; item < n_items; item += stride) {
+        const uint32_t s = (uint32_t)(item / a.items_per_block);
+        const uint32_t chunk = (uint32_t)(item - (uint64_t)s * a.items_per_block);
+        const uint32_t nfr = a.frames ? min(__ldg(a.frames + s), a.block_frames) : a.block_frames;
+        const uint32_t f0 = chunk * a.per_item;
+        const uint32_t f1 = min(f0 + a.per_item, nfr);
+
+        if (a.meter && chunk == 0 && lane == 0 && nfr)
+            atomicAdd(a.meters + (size_t)s * a.row_u64 + 2 * C, (unsigned long long)nfr);
+        if (f0 >= f1)
+            continue;
+
+        const bool identity = !a.transform || (__ldg(&a.gains[s].flags) & kGainIdentity);
+        const bool inplace = (a.in == a.out);
+        if (a.meter) {
+            if (!identity)
+                run_item_generic<true, true, true>(a, C, s, f0, f1, lane);
+            else if (inplace)
+                run_item_generic<false, false, true>(a, C, s, f0, f1, lane);
+            else
+                run_item_generic<false, true, true>(a, C, s, f0, f1, lane);
+        } else {
+            if (!identity)
+                run_item_generic<true, true, false>(a, C, s, f0, f1, lane);
+            else if (!inplace)
+                run_item_generic<false, true, false>(a, C, s, f0, f1, lane);
+        }
+    }
+}
+
+}  // namespace cmgpu

@@ -30,3 +30,22 @@ def ref():
     if r is None:
         pytest.skip("oracle/_ref (the reference's own object code) is not available here")
     return r
+
+
+def load_package():
+    """Import libcoolmic-dsp_b200/ (hyphenated directory) as module `libcoolmic_dsp_b200`."""
+    import importlib.util
+    name = "libcoolmic_dsp_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    pkg = ROOT / "libcoolmic-dsp_b200"
+    spec = importlib.util.spec_from_file_location(name, pkg / "__init__.py", submodule_search_locations=[str(pkg)])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture(scope="session")
+def cm():
+    return load_package()
