@@ -40,6 +40,7 @@ WORKLOADS = {
     # name: (channels, streams per GPU, seconds, rate, description)
     "cfg2": (2, 1024, 10, 48000, "1,024 x 48 kHz stereo S16 streams x 10 s per GPU, one device ring, one fused tick per step"),
     "cfg4a": (8, 4096, 2, 48000, "4,096 x 48 kHz 8-channel S16 streams x 2 s per GPU, per-channel gain + 8-channel meter"),
+    "l2fit": (2, 256, 1, 24000, "DIAGNOSTIC ONLY: 256 stereo streams x 24,000 frames (24.6 MB in + 24.6 MB out, L2 resident)"),
     "cfg5": (2, 65536, 1, 48000, "65,536 x 48 kHz stereo S16 streams x 1 s in total, sharded by stream across the GPUs"),
 }
 
@@ -185,6 +186,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="fused", choices=["fused", "transform", "meter", "copy"],
+                    help="diagnostic: which parts of the tick run in the device-timed loop (default: fused = the product)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
@@ -204,6 +207,8 @@ def main():
               "rate_hz": rate, "seconds_per_stream": seconds, "gains": "every stream active, scale 1000+s%9000, gain ~0.75..3.1",
               "l2": "inputs (>=1.5 GB per GPU) far larger than the 126 MB L2; no flush needed",
               "sharding": "by stream, one process per GPU, no data-path collective"}
+    if args.mode != "fused":
+        config["diagnostic_mode"] = args.mode
 
     # ---------------------------------------------------------------- reference arm (CPU only)
     if args.impl == "reference":
@@ -271,13 +276,14 @@ def main():
     eng.submit(0, stage)
     eng.sync()
 
+    pflags = {"fused": cm.FUSED, "transform": cm.TRANSFORM, "meter": cm.METER, "copy": 0}[args.mode]
     clocks = ClockSampler(local)
-    eng.time_process(args.warmup)
+    eng.time_process(args.warmup, flags=pflags)
     eng.reset_meters()
     launches0 = eng.launch_count()
     barrier()
     clocks.start()
-    ms_total = eng.time_process(args.steps)
+    ms_total = eng.time_process(args.steps, flags=pflags)
     barrier()
     clk = clocks.stop()
     launches = eng.launch_count() - launches0
@@ -287,7 +293,7 @@ def main():
 
     # meter sanity on what was just measured: K identical ticks -> K * frames frames per stream
     snap = eng.snapshot(0, min(4, streams_per_gpu))
-    assert int(snap[0].frames) == args.steps * frames, "meter did not see every timed tick"
+    assert int(snap[0].frames) == (args.steps * frames if pflags & cm.METER else 0), "meter did not see every timed tick"
     kernel = eng.kernel_name()
     peak, peak_src = measured_peak()
     alg_bytes = 4.0 * samples_per_step_rank

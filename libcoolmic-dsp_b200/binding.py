@@ -9,7 +9,8 @@ from pathlib import Path
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "lib" / "libcoolmic_b200.so"
+import os
+LIB_PATH = Path(os.environ.get("CMGPU_LIB", PKG / "lib" / "libcoolmic_b200.so"))
 MAX_CH = 16
 
 SEPARATE_OUT, NO_PINNED, FORCE_GENERIC = 0x1, 0x2, 0x4

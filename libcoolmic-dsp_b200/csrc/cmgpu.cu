@@ -114,74 +114,91 @@ struct cmgpu_ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     std::mutex mu;
 
+    // streams grouped by gain mode (GM_IDENTITY / GM_MASKED / GM_ADDALL): one launch per group
+    std::vector<uint32_t> h_ids[3];
+    uint32_t *d_ids = nullptr;                     // [3][max_streams]
+    bool classes_dirty = true;
+
     // launch plan (depends on shape only)
     int plan_g = 32;              // lanes per item (fast kernels); 0 = generic kernel
     uint32_t plan_items = 1, plan_per_item = 0;
-    int plan_grid_cap = 0;
+    int grid_cap[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // resident CTAs per (gain mode, meter) kernel
     char kname[64] = "";
 };
 
 namespace {
 
+using TickKernel = void (*)(const TickArgs);
+
 template <int C, int G>
-cudaError_t launch_fast(const TickArgs &a, int grid, cudaStream_t st)
+TickKernel fast_kernel(int gm, bool meter)
 {
-    cmgpu::fused_tick<C, G><<<grid, 256, 0, st>>>(a);
-    return cudaGetLastError();
+    using namespace cmgpu;
+    switch (gm) {
+    case GM_IDENTITY: return meter ? fused_tick<C, G, GM_IDENTITY, true> : fused_tick<C, G, GM_IDENTITY, false>;
+    case GM_ADDALL:   return meter ? fused_tick<C, G, GM_ADDALL, true> : fused_tick<C, G, GM_ADDALL, false>;
+    default:          return meter ? fused_tick<C, G, GM_MASKED, true> : fused_tick<C, G, GM_MASKED, false>;
+    }
 }
 
 template <int C>
-cudaError_t launch_fast_g(int g, const TickArgs &a, int grid, cudaStream_t st)
+TickKernel fast_kernel_g(int g, int gm, bool meter)
 {
-    switch (g) {
-    case 8:
-        if (C == 16)
-            return cudaErrorInvalidValue;
-        return launch_fast<C, (C == 16 ? 16 : 8)>(a, grid, st);
-    case 16:
-        return launch_fast<C, 16>(a, grid, st);
-    default:
-        return launch_fast<C, 32>(a, grid, st);
-    }
+    if (g == 8 && C != 16)
+        return fast_kernel<C, (C == 16 ? 32 : 8)>(gm, meter);
+    return fast_kernel<C, 32>(gm, meter);
 }
 
-cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int grid)
-{
-    if (c->plan_g == 0) {
-        cmgpu::generic_tick<<<grid, 128, 0, c->s_cmp>>>(a, (int)c->channels);
-        return cudaGetLastError();
-    }
-    switch (c->channels) {
-    case 1:  return launch_fast_g<1>(c->plan_g, a, grid, c->s_cmp);
-    case 2:  return launch_fast_g<2>(c->plan_g, a, grid, c->s_cmp);
-    case 4:  return launch_fast_g<4>(c->plan_g, a, grid, c->s_cmp);
-    case 8:  return launch_fast_g<8>(c->plan_g, a, grid, c->s_cmp);
-    case 16: return launch_fast_g<16>(c->plan_g, a, grid, c->s_cmp);
-    default: return cudaErrorInvalidValue;
-    }
-}
+using GenericKernel = void (*)(const TickArgs, const int);
 
-template <typename K>
-int occupancy(K kernel, int threads)
-{
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n < 1)
-        n = 1;
-    return n;
-}
-
-int fast_occupancy(unsigned channels, int g)
+GenericKernel generic_kernel(int gm, bool meter)
 {
     using namespace cmgpu;
-#define OCC(C, G) occupancy(fused_tick<C, G>, 256)
-    switch (channels) {
-    case 1:  return g == 8 ? OCC(1, 8) : g == 16 ? OCC(1, 16) : OCC(1, 32);
-    case 2:  return g == 8 ? OCC(2, 8) : g == 16 ? OCC(2, 16) : OCC(2, 32);
-    case 4:  return g == 8 ? OCC(4, 8) : g == 16 ? OCC(4, 16) : OCC(4, 32);
-    case 8:  return g == 8 ? OCC(8, 8) : g == 16 ? OCC(8, 16) : OCC(8, 32);
-    default: return g == 16 ? OCC(16, 16) : OCC(16, 32);
+    switch (gm) {
+    case GM_IDENTITY: return meter ? generic_tick<GM_IDENTITY, true> : generic_tick<GM_IDENTITY, false>;
+    // the generic kernel has no add-all specialisation: the masked recipe covers it
+    default:          return meter ? generic_tick<GM_MASKED, true> : generic_tick<GM_MASKED, false>;
     }
-#undef OCC
+}
+
+TickKernel pick_fast(const cmgpu_ctx *c, int gm, bool meter)
+{
+    switch (c->channels) {
+    case 1:  return fast_kernel_g<1>(c->plan_g, gm, meter);
+    case 2:  return fast_kernel_g<2>(c->plan_g, gm, meter);
+    case 4:  return fast_kernel_g<4>(c->plan_g, gm, meter);
+    case 8:  return fast_kernel_g<8>(c->plan_g, gm, meter);
+    default: return fast_kernel_g<16>(c->plan_g, gm, meter);
+    }
+}
+
+int resident_ctas(cmgpu_ctx *c, int gm, bool meter)
+{
+    int &cap = c->grid_cap[gm][meter ? 1 : 0];
+    if (cap)
+        return cap;
+    int n = 0;
+    cudaError_t e = c->plan_g ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pick_fast(c, gm, meter), 256, 0)
+                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, generic_kernel(gm, meter), 128, 0);
+    if (e != cudaSuccess || n < 1)
+        n = 1;
+    cap = n * c->num_sms;
+    return cap;
+}
+
+cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter)
+{
+    const uint64_t items = (uint64_t)a.n_streams * a.items_per_block;
+    const uint64_t per_cta = c->plan_g ? 256u / (unsigned)c->plan_g : 4u;
+    uint64_t grid = (items + per_cta - 1) / per_cta;
+    const uint64_t cap = (uint64_t)resident_ctas(c, gm, meter);
+    if (grid > cap)
+        grid = cap;
+    if (c->plan_g == 0)
+        generic_kernel(gm, meter)<<<(unsigned)grid, 128, 0, c->s_cmp>>>(a, (int)c->channels);
+    else
+        pick_fast(c, gm, meter)<<<(unsigned)grid, 256, 0, c->s_cmp>>>(a);
+    return cudaGetLastError();
 }
 
 // Decide how a tick is cut into work items. Shape-only, so done once per context.
@@ -199,18 +216,16 @@ void make_plan(cmgpu_ctx *c)
         c->plan_g = 0;
         c->plan_items = items;
         c->plan_per_item = per;
-        c->plan_grid_cap = c->num_sms * occupancy(cmgpu::generic_tick, 128);
         snprintf(c->kname, sizeof(c->kname), "generic_tick<C=%u>", C);
         return;
     }
     const uint32_t nvec = (uint32_t)(c->stride / 16);
-    int g = 32;
-    if (nvec <= 64 && C != 16)
-        g = 8;
-    else if (nvec <= 256)
-        g = 16;
+    // stream-blocks of up to 1 KiB are walked by 8-lane groups so that no lane idles
+    const int g = (nvec <= 64 && C != 16) ? 8 : 32;
     // aim for ~32 KiB (2048 vectors) per item, a multiple of 4 steps of the group
-    const uint32_t target = 2048;
+    uint32_t target = 2048;
+    if (const char *e = getenv("CMGPU_ITEM_VECS"))          // tuning hook
+        target = (uint32_t)strtoul(e, nullptr, 10) ? (uint32_t)strtoul(e, nullptr, 10) : target;
     uint32_t items = (nvec + target - 1) / target;
     uint32_t per = (nvec + items - 1) / items;
     const uint32_t quantum = (uint32_t)g * 4u;
@@ -219,7 +234,6 @@ void make_plan(cmgpu_ctx *c)
     c->plan_g = g;
     c->plan_items = items;
     c->plan_per_item = per;
-    c->plan_grid_cap = c->num_sms * fast_occupancy(C, g);
     snprintf(c->kname, sizeof(c->kname), "fused_tick<C=%u,G=%d>", C, g);
 }
 
@@ -237,6 +251,7 @@ int upload_gains_locked(cmgpu_ctx *c)
 
 void mark_dirty(cmgpu_ctx *c, unsigned lo, unsigned hi)
 {
+    c->classes_dirty = true;
     if (lo < c->dirty_lo)
         c->dirty_lo = lo;
     if (hi > c->dirty_hi)
@@ -263,7 +278,34 @@ void set_row(cmgpu_ctx *c, unsigned s, uint16_t scale, const uint16_t *gain)
     }
     for (unsigned ch = scale ? c->channels : 0; ch < 16; ch++)
         r.mul[ch] = 1;
-    r.flags = identity ? cmgpu::kGainIdentity : 0;
+    bool addall = scale != 0;
+    for (unsigned ch = 0; ch < c->channels && addall; ch++)
+        addall = r.addm[ch] == 0xffffffffu;
+    r.flags = (identity ? cmgpu::kGainIdentity : 0) | (addall ? cmgpu::kGainAddAll : 0);
+}
+
+int gain_mode_of(const GainRow &r)
+{
+    if (r.flags & cmgpu::kGainIdentity)
+        return cmgpu::GM_IDENTITY;
+    return (r.flags & cmgpu::kGainAddAll) ? cmgpu::GM_ADDALL : cmgpu::GM_MASKED;
+}
+
+int rebuild_classes_locked(cmgpu_ctx *c)
+{
+    for (auto &v : c->h_ids)
+        v.clear();
+    for (unsigned s = 0; s < c->active; s++)
+        c->h_ids[gain_mode_of(c->h_gains[s])].push_back(s);
+    for (int k = 0; k < 3; k++) {
+        // a group that is the whole contiguous range needs no list on the device
+        if (c->h_ids[k].empty() || c->h_ids[k].size() == c->active)
+            continue;
+        CU(cudaMemcpyAsync(c->d_ids + (size_t)k * c->max_streams, c->h_ids[k].data(),
+                           sizeof(uint32_t) * c->h_ids[k].size(), cudaMemcpyHostToDevice, c->s_cmp));
+    }
+    c->classes_dirty = false;
+    return CMGPU_OK;
 }
 
 int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags)
@@ -271,6 +313,8 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags)
     int rc = upload_gains_locked(c);
     if (rc)
         return rc;
+    const bool meter = (flags & CMGPU_METER) != 0;
+    const bool transform = (flags & CMGPU_TRANSFORM) != 0;
     TickArgs a;
     memset(&a, 0, sizeof(a));
     a.in = c->d_in + (size_t)slot * c->slot_bytes;
@@ -279,25 +323,43 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags)
     a.gains = c->d_gains;
     a.meters = c->d_meters;
     a.pos_base = (c->tick_seq << c->pbits) & cmgpu::kKeyPosMask;
-    a.n_streams = c->active;
     a.block_frames = c->block_frames;
     a.stride_bytes = (uint32_t)c->stride;
     a.items_per_block = c->plan_items;
     a.per_item = c->plan_per_item;
     a.row_u64 = c->row_u64;
-    a.transform = (flags & CMGPU_TRANSFORM) ? 1u : 0u;
-    a.meter = (flags & CMGPU_METER) ? 1u : 0u;
     c->tick_seq++;
     if (!c->active)
         return CMGPU_OK;
+    const bool separate = c->d_out != nullptr;
 
-    const uint64_t items = (uint64_t)c->active * c->plan_items;
-    const uint64_t per_cta = c->plan_g ? 256u / (unsigned)c->plan_g : 4u;
-    uint64_t grid = (items + per_cta - 1) / per_cta;
-    if (grid > (uint64_t)c->plan_grid_cap)
-        grid = (uint64_t)c->plan_grid_cap;
-    CU(launch_tick(c, a, (int)grid));
-    c->launches++;
+    if (!transform) {
+        // every stream passes through untouched
+        if (!meter && !separate)
+            return CMGPU_OK;
+        a.stream_ids = nullptr;
+        a.n_streams = c->active;
+        a.store = separate ? 1u : 0u;
+        CU(launch_tick(c, a, cmgpu::GM_IDENTITY, meter));
+        c->launches++;
+        return CMGPU_OK;
+    }
+    if (c->classes_dirty && (rc = rebuild_classes_locked(c)))
+        return rc;
+    for (int gm = 0; gm < 3; gm++) {
+        const size_t n = c->h_ids[gm].size();
+        if (!n)
+            continue;
+        a.store = (gm != cmgpu::GM_IDENTITY || separate) ? 1u : 0u;
+        if (!a.store && !meter)
+            continue;
+        a.stream_ids = (n == c->active) ? nullptr : c->d_ids + (size_t)gm * c->max_streams;
+        a.n_streams = (uint32_t)n;
+        // the generic kernel folds add-all into the masked recipe
+        const int kgm = (c->plan_g == 0 && gm == cmgpu::GM_ADDALL) ? cmgpu::GM_MASKED : gm;
+        CU(launch_tick(c, a, kgm, meter));
+        c->launches++;
+    }
     return CMGPU_OK;
 }
 
@@ -435,6 +497,8 @@ cmgpu_ctx_t *cmgpu_ctx_create(int device, unsigned channels, unsigned max_stream
         return bail("cudaMalloc(meters)", e);
     if ((e = cudaMemset(c->d_meters, 0, sizeof(uint64_t) * c->row_u64 * max_streams)) != cudaSuccess)
         return bail("cudaMemset(meters)", e);
+    if ((e = cudaMalloc(&c->d_ids, sizeof(uint32_t) * 3 * (size_t)max_streams)) != cudaSuccess)
+        return bail("cudaMalloc(stream lists)", e);
     if ((e = cudaMalloc(&c->d_frames, sizeof(uint32_t) * (size_t)max_streams * ring_slots)) != cudaSuccess)
         return bail("cudaMalloc(frames)", e);
     if ((e = cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -484,6 +548,7 @@ void cmgpu_ctx_destroy(cmgpu_ctx_t *c)
     cudaFree(c->d_gains);
     cudaFree(c->d_meters);
     cudaFree(c->d_frames);
+    cudaFree(c->d_ids);
     if (c->h_ring)
         cudaFreeHost(c->h_ring);
     cudaGetLastError();
@@ -509,6 +574,7 @@ int cmgpu_set_active_streams(cmgpu_ctx_t *c, unsigned n)
         return fail(CMGPU_ERR_INVAL, "active streams %u > max_streams %u", n, c->max_streams);
     std::lock_guard<std::mutex> lk(c->mu);
     c->active = n;
+    c->classes_dirty = true;
     return CMGPU_OK;
 }
 

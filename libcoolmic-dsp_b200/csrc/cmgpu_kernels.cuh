@@ -17,6 +17,13 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#ifndef CMGPU_UNROLL
+#define CMGPU_UNROLL 4      // register slots of the rolling prefetch ring per lane
+#endif
+#ifndef CMGPU_MIN_CTAS
+#define CMGPU_MIN_CTAS 3    // resident 256-thread CTAs per SM the fast kernels are compiled for
+#endif
+
 namespace cmgpu {
 
 // ---- device tables ---------------------------------------------------------------------
@@ -37,7 +44,11 @@ struct GainRow {
 };
 static_assert(sizeof(GainRow) == 208, "GainRow layout");
 
-constexpr uint32_t kGainIdentity = 1u;
+constexpr uint32_t kGainIdentity = 1u;   // flags bit 0: y = x for every channel
+constexpr uint32_t kGainAddAll = 2u;     // flags bit 1: addm is all-ones for every channel
+
+// How a work item applies its stream's recipe (warp-uniform, chosen per item from flags).
+enum GainMode { GM_IDENTITY = 0, GM_MASKED = 1, GM_ADDALL = 2 };
 
 // Meter row per stream: { peak_key[C], power[C], frames, 0 } as uint64.
 // peak_key = mag(17 bits) << 47 | (~position & (2^46-1)) << 1 | negative
@@ -50,6 +61,7 @@ struct TickArgs {
     const uint8_t *in;          // slot base (device)
     uint8_t *out;               // == in when working in place
     const uint32_t *frames;     // valid frames per stream, or nullptr = block_frames each
+    const uint32_t *stream_ids; // streams this launch covers, or nullptr = 0 .. n_streams-1
     const GainRow *gains;
     unsigned long long *meters;
     uint64_t pos_base;          // tick sequence number << pbits
@@ -59,8 +71,7 @@ struct TickArgs {
     uint32_t items_per_block;   // work items (chunks) per stream-block
     uint32_t per_item;          // vectors (fast kernels) or frames (generic kernel) per item
     uint32_t row_u64;           // meter row length in uint64
-    uint32_t transform;         // apply gains (else identity for every stream)
-    uint32_t meter;             // accumulate meters
+    uint32_t store;             // write PCM to `out` (0 only for identity streams in place)
 };
 
 // ---- small helpers -----------------------------------------------------------------------
@@ -93,14 +104,17 @@ struct Recipe {
     int mul;
 };
 
-template <bool GAIN>
+template <int GM>
 __device__ __forceinline__ int apply_gain(int x, const Recipe &r)
 {
-    if (!GAIN)
+    if (GM == GM_IDENTITY)
         return x;
-    int X = x * r.mul;
-    int hi = __mulhi(X, r.mw) + (X & r.addm);
-    int y = hi + (int)((unsigned)X >> 31);
+    const int X = x * r.mul;
+    int y;
+    if (GM == GM_ADDALL)
+        y = __mulhi(X, r.mw) + (X + (int)((unsigned)X >> 31));      // IMAD.HI with addend, LEA.HI
+    else
+        y = __mulhi(X, r.mw) + (X & r.addm) + (int)((unsigned)X >> 31);
     return max(min(y, 32767), -32768);
 }
 
@@ -124,9 +138,9 @@ struct Shape {
     static constexpr int kFramesPerVec8 = 8 / kPerLane; // frames per vector when C <= 8
 };
 
-template <int C, bool GAIN, bool METER, bool MASKED>
+template <int C, int GM, bool METER, bool MASKED>
 __device__ __forceinline__ uint4 do_vector(uint4 w, const Recipe (&rc)[Shape<C>::kPerLane], uint32_t radd,
-                                           uint32_t (&kmax)[8], uint64_t (&pacc)[8], int nvalid)
+                                           uint32_t (&kmax)[8], uint64_t (&pacc)[Shape<C>::kPerLane], int nvalid)
 {
     constexpr int P = Shape<C>::kPerLane;
     uint32_t in[4] = {w.x, w.y, w.z, w.w};
@@ -136,8 +150,8 @@ __device__ __forceinline__ uint4 do_vector(uint4 w, const Recipe (&rc)[Shape<C>:
         const int k0 = 2 * j, k1 = 2 * j + 1;
         int x0 = (int)(short)(in[j] & 0xffffu);
         int x1 = (int)in[j] >> 16;
-        int y0 = apply_gain<GAIN>(x0, rc[k0 % P]);
-        int y1 = apply_gain<GAIN>(x1, rc[k1 % P]);
+        int y0 = apply_gain<GM>(x0, rc[k0 % P]);
+        int y1 = apply_gain<GM>(x1, rc[k1 % P]);
         int m0 = y0, m1 = y1;
         if (MASKED) {
             // samples past the valid frames: pass through, invisible to the meter
@@ -145,79 +159,110 @@ __device__ __forceinline__ uint4 do_vector(uint4 w, const Recipe (&rc)[Shape<C>:
             if (k1 >= nvalid) { y1 = x1; m1 = 0; }
         }
         if (METER) {
-            uint32_t a0 = (uint32_t)abs(m0), a1 = (uint32_t)abs(m1);
+            const uint32_t a0 = (uint32_t)abs(m0), a1 = (uint32_t)abs(m1);
             kmax[k0] = max(kmax[k0], (a0 << 16) + radd);
             kmax[k1] = max(kmax[k1], (a1 << 16) + radd);
-            pacc[k0] += (uint64_t)(a0 * a0);
-            pacc[k1] += (uint64_t)(a1 * a1);
+            // exact: |y| <= 32768, so y*y <= 2^30; one IMAD.WIDE with 64-bit accumulate per sample
+            pacc[k0 % P] += (uint64_t)((int64_t)m0 * (int64_t)m0);
+            pacc[k1 % P] += (uint64_t)((int64_t)m1 * (int64_t)m1);
         }
         o[j] = ((uint32_t)y0 & 0xffffu) | ((uint32_t)y1 << 16);
     }
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-template <int C, int G, bool GAIN, bool STORE, bool METER>
+template <int C, int G, int GM, bool METER>
 __device__ __forceinline__ void run_item(const TickArgs &a, uint32_t s, uint32_t v0, uint32_t v1,
                                          uint32_t valid_bytes, uint32_t gl, unsigned gmask)
 {
     constexpr int P = Shape<C>::kPerLane;
-    constexpr int UNROLL = 4;
+    constexpr int UNROLL = CMGPU_UNROLL;
     const size_t base = (size_t)s * a.stride_bytes;
     const uint8_t *in = a.in + base;
     uint8_t *out = a.out + base;
 
     Recipe rc[P];
-    if (GAIN) {
+#pragma unroll
+    for (int c = 0; c < P; c++) {
+        rc[c].mw = rc[c].addm = 0;
+        rc[c].mul = 1;
+    }
+    if (GM != GM_IDENTITY) {
         const GainRow *g = a.gains + s;
         // C == 16: even lanes own channels 0-7, odd lanes 8-15 (v0 and G are even)
         const int cbase = (C == 16) ? (int)(gl & 1u) * 8 : 0;
 #pragma unroll
         for (int c = 0; c < P; c++) {
             rc[c].mw = (int)__ldg(&g->mw[cbase + c]);
-            rc[c].addm = (int)__ldg(&g->addm[cbase + c]);
             rc[c].mul = (int)__ldg(&g->mul[cbase + c]);
+            if (GM == GM_MASKED)
+                rc[c].addm = (int)__ldg(&g->addm[cbase + c]);
         }
     }
 
     uint32_t kmax[8];
-    uint64_t pacc[8];
+    uint64_t pacc[P];
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < 8; k++)
         kmax[k] = 0;
-        pacc[k] = 0;
-    }
+#pragma unroll
+    for (int c = 0; c < P; c++)
+        pacc[c] = 0;
 
     const uint32_t vfull = min(v1, valid_bytes >> 4);     // vectors [v0, vfull) are entirely valid
     const uint32_t first = v0 + gl;
     // number of this lane's vectors below vfull
     const uint32_t n_i = first < vfull ? (vfull - first + (G - 1)) / G : 0;
+    const uint8_t *src = in + (size_t)first * 16;
+    uint8_t *dst = out + (size_t)first * 16;
+    constexpr size_t kStep = (size_t)G * 16;              // bytes between a lane's consecutive vectors
 
-    uint32_t i = 0;
-    for (; i + UNROLL <= n_i; i += UNROLL) {
-        uint4 w[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++)
-            w[u] = ld_stream(in + (size_t)(first + (i + u) * G) * 16);
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            uint4 o = do_vector<C, GAIN, METER, false>(w[u], rc, 0xffffu - (i + u), kmax, pacc, 8);
-            if (STORE)
-                st_stream(out + (size_t)(first + (i + u) * G) * 16, o);
+    // Double-buffered batches: a lane requests UNROLL consecutive vectors of its stride
+    // back-to-back (the warp's requests then cover UNROLL*G*16 contiguous bytes at once, which
+    // is what HBM rows like), one whole batch ahead of the batch it is computing on. Two
+    // register sets alternate roles, so nothing is ever copied.
+    uint4 bufA[UNROLL], bufB[UNROLL];
+    const uint32_t nb = n_i / UNROLL;                     // full batches of this lane
+#define CMGPU_LOAD_BATCH(buf, b)                                                        \
+    _Pragma("unroll") for (int u = 0; u < UNROLL; u++)                                  \
+        buf[u] = ld_stream(src + (size_t)((b) * UNROLL + u) * kStep);
+#define CMGPU_DO_BATCH(buf, b)                                                          \
+    _Pragma("unroll") for (int u = 0; u < UNROLL; u++) {                                \
+        const uint32_t iu = (b) * UNROLL + u;                                           \
+        const uint4 o = do_vector<C, GM, METER, false>(buf[u], rc, 0xffffu - iu, kmax, pacc, 8); \
+        if (a.store)                                                                    \
+            st_stream(dst + (size_t)iu * kStep, o);                                     \
+    }
+    if (nb > 0) {
+        CMGPU_LOAD_BATCH(bufA, 0u)
+    }
+    for (uint32_t b = 0; b < nb; b += 2) {
+        if (b + 1 < nb) {
+            CMGPU_LOAD_BATCH(bufB, b + 1)
+        }
+        CMGPU_DO_BATCH(bufA, b)
+        if (b + 2 < nb) {
+            CMGPU_LOAD_BATCH(bufA, b + 2)
+        }
+        if (b + 1 < nb) {
+            CMGPU_DO_BATCH(bufB, b + 1)
         }
     }
-    for (; i < n_i; i++) {
-        uint4 w = ld_stream(in + (size_t)(first + i * G) * 16);
-        uint4 o = do_vector<C, GAIN, METER, false>(w, rc, 0xffffu - i, kmax, pacc, 8);
-        if (STORE)
-            st_stream(out + (size_t)(first + i * G) * 16, o);
+#undef CMGPU_LOAD_BATCH
+#undef CMGPU_DO_BATCH
+    for (uint32_t i = nb * UNROLL; i < n_i; i++) {
+        const uint4 w = ld_stream(src + (size_t)i * kStep);
+        const uint4 o = do_vector<C, GM, METER, false>(w, rc, 0xffffu - i, kmax, pacc, 8);
+        if (a.store)
+            st_stream(dst + (size_t)i * kStep, o);
     }
     // the one vector that straddles the end of the valid frames, if it lies in this item
     if (vfull < v1 && (vfull << 4) < valid_bytes && ((vfull - v0) % G) == gl) {
         const uint32_t it = (vfull - v0) / G;
         const int nvalid = (int)((valid_bytes - (vfull << 4)) >> 1);
         uint4 w = ld_stream(in + (size_t)vfull * 16);
-        uint4 o = do_vector<C, GAIN, METER, true>(w, rc, 0xffffu - it, kmax, pacc, nvalid);
-        if (STORE)
+        uint4 o = do_vector<C, GM, METER, true>(w, rc, 0xffffu - it, kmax, pacc, nvalid);
+        if (a.store)
             st_stream(out + (size_t)vfull * 16, o);
     }
 
@@ -225,12 +270,10 @@ __device__ __forceinline__ void run_item(const TickArgs &a, uint32_t s, uint32_t
         return;
 
     // ---- widen to position keys, fold slots of the same channel, combine lanes -------------
-    uint64_t kc[P], pc[P];
+    uint64_t kc[P];
 #pragma unroll
-    for (int c = 0; c < P; c++) {
+    for (int c = 0; c < P; c++)
         kc[c] = 0;
-        pc[c] = 0;
-    }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const uint32_t mag = kmax[k] >> 16;
@@ -241,14 +284,13 @@ __device__ __forceinline__ void run_item(const TickArgs &a, uint32_t s, uint32_t
                                         : (v >> 1);
         const uint64_t key = make_key(mag, a.pos_base + frame);
         kc[k % P] = max(kc[k % P], key);
-        pc[k % P] += pacc[k];
     }
 #pragma unroll
     for (int off = G / 2; off >= Shape<C>::kLanesPerFrame; off >>= 1) {
 #pragma unroll
         for (int c = 0; c < P; c++) {
             kc[c] = max(kc[c], shfl_xor64(gmask, kc[c], off));
-            pc[c] += shfl_xor64(gmask, pc[c], off);
+            pacc[c] += shfl_xor64(gmask, pacc[c], off);
         }
     }
 
@@ -259,7 +301,7 @@ __device__ __forceinline__ void run_item(const TickArgs &a, uint32_t s, uint32_t
     for (int c = 0; c < P; c++) {
         if (sel == c) {
             key = kc[c];
-            pw = pc[c];
+            pw = pacc[c];
         }
     }
     const int ch = (C == 16) ? (int)((gl & 1u) * 8u + (gl >> 1)) : (int)gl;
@@ -279,8 +321,11 @@ __device__ __forceinline__ void run_item(const TickArgs &a, uint32_t s, uint32_t
     }
 }
 
-template <int C, int G>
-__global__ void __launch_bounds__(256) fused_tick(const TickArgs a)
+// One kernel per (channel shape, group width, gain mode, meter on/off): every work item of a
+// launch runs the same straight-line code. A tick whose streams differ in gain mode is issued as
+// one launch per mode present, each over its own stream list.
+template <int C, int G, int GM, bool METER>
+__global__ void __launch_bounds__(256, CMGPU_MIN_CTAS) fused_tick(const __grid_constant__ TickArgs a)
 {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gl = threadIdx.x & (G - 1);
@@ -290,34 +335,19 @@ __global__ void __launch_bounds__(256) fused_tick(const TickArgs a)
     const uint64_t stride = (uint64_t)gridDim.x * groups_per_cta;
 
     for (uint64_t item = (uint64_t)blockIdx.x * groups_per_cta + threadIdx.x / G; item < n_items; item += stride) {
-        const uint32_t s = (uint32_t)(item / a.items_per_block);
-        const uint32_t chunk = (uint32_t)(item - (uint64_t)s * a.items_per_block);
+        const uint32_t si = (uint32_t)(item / a.items_per_block);
+        const uint32_t chunk = (uint32_t)(item - (uint64_t)si * a.items_per_block);
+        const uint32_t s = a.stream_ids ? __ldg(a.stream_ids + si) : si;
         const uint32_t nfr = a.frames ? min(__ldg(a.frames + s), a.block_frames) : a.block_frames;
         const uint32_t valid_bytes = nfr * (uint32_t)(2 * C);
         const uint32_t nvec = (valid_bytes + 15u) >> 4;
         const uint32_t v0 = chunk * a.per_item;
         const uint32_t v1 = min(v0 + a.per_item, nvec);
 
-        if (a.meter && chunk == 0 && gl == 0 && nfr)
+        if (METER && chunk == 0 && gl == 0 && nfr)
             atomicAdd(a.meters + (size_t)s * a.row_u64 + 2 * C, (unsigned long long)nfr);
-        if (v0 >= v1)
-            continue;
-
-        const bool identity = !a.transform || (__ldg(&a.gains[s].flags) & kGainIdentity);
-        const bool inplace = (a.in == a.out);
-        if (a.meter) {
-            if (!identity)
-                run_item<C, G, true, true, true>(a, s, v0, v1, valid_bytes, gl, gmask);
-            else if (inplace)
-                run_item<C, G, false, false, true>(a, s, v0, v1, valid_bytes, gl, gmask);
-            else
-                run_item<C, G, false, true, true>(a, s, v0, v1, valid_bytes, gl, gmask);
-        } else {
-            if (!identity)
-                run_item<C, G, true, true, false>(a, s, v0, v1, valid_bytes, gl, gmask);
-            else if (!inplace)
-                run_item<C, G, false, true, false>(a, s, v0, v1, valid_bytes, gl, gmask);
-        }
+        if (v0 < v1)
+            run_item<C, G, GM, METER>(a, s, v0, v1, valid_bytes, gl, gmask);
     }
 }
 
@@ -328,7 +358,7 @@ __global__ void __launch_bounds__(256) fused_tick(const TickArgs a)
 // that do not tile a 16-byte vector (3, 5, 6, 7, 9..15) and as an independently written
 // cross-check of the fast kernels (CMGPU_FORCE_GENERIC).
 
-template <bool GAIN, bool STORE, bool METER>
+template <int GM, bool METER>
 __device__ __forceinline__ void run_item_generic(const TickArgs &a, int C, uint32_t s, uint32_t f0, uint32_t f1,
                                                  uint32_t lane)
 {
@@ -345,7 +375,7 @@ __device__ __forceinline__ void run_item_generic(const TickArgs &a, int C, uint3
         pacc[c] = 0;
         rc[c].mw = rc[c].addm = 0;
         rc[c].mul = 1;
-        if (GAIN && c < C) {
+        if (GM != GM_IDENTITY && c < C) {
             const GainRow *g = a.gains + s;
             rc[c].mw = (int)__ldg(&g->mw[c]);
             rc[c].addm = (int)__ldg(&g->addm[c]);
@@ -361,8 +391,8 @@ __device__ __forceinline__ void run_item_generic(const TickArgs &a, int C, uint3
         for (int c = 0; c < 16; c++) {
             if (c < C) {
                 const int x = in[o + c];
-                const int y = apply_gain<GAIN>(x, rc[c]);
-                if (STORE)
+                const int y = apply_gain<GM>(x, rc[c]);
+                if (a.store)
                     out[o + c] = (int16_t)y;
                 if (METER) {
                     const uint32_t m = (uint32_t)abs(y);
@@ -409,7 +439,8 @@ __device__ __forceinline__ void run_item_generic(const TickArgs &a, int C, uint3
     }
 }
 
-__global__ void __launch_bounds__(128) generic_tick(const TickArgs a, const int C)
+template <int GM, bool METER>
+__global__ void __launch_bounds__(128) generic_tick(const __grid_constant__ TickArgs a, const int C)
 {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_per_cta = 128 / 32;
@@ -417,32 +448,17 @@ __global__ void __launch_bounds__(128) generic_tick(const TickArgs a, const int 
     const uint64_t stride = (uint64_t)gridDim.x * warps_per_cta;
 
     for (uint64_t item = (uint64_t)blockIdx.x * warps_per_cta + threadIdx.x / 32; item < n_items; item += stride) {
-        const uint32_t s = (uint32_t)(item / a.items_per_block);
-        const uint32_t chunk = (uint32_t)(item - (uint64_t)s * a.items_per_block);
+        const uint32_t si = (uint32_t)(item / a.items_per_block);
+        const uint32_t chunk = (uint32_t)(item - (uint64_t)si * a.items_per_block);
+        const uint32_t s = a.stream_ids ? __ldg(a.stream_ids + si) : si;
         const uint32_t nfr = a.frames ? min(__ldg(a.frames + s), a.block_frames) : a.block_frames;
         const uint32_t f0 = chunk * a.per_item;
         const uint32_t f1 = min(f0 + a.per_item, nfr);
 
-        if (a.meter && chunk == 0 && lane == 0 && nfr)
+        if (METER && chunk == 0 && lane == 0 && nfr)
             atomicAdd(a.meters + (size_t)s * a.row_u64 + 2 * C, (unsigned long long)nfr);
-        if (f0 >= f1)
-            continue;
-
-        const bool identity = !a.transform || (__ldg(&a.gains[s].flags) & kGainIdentity);
-        const bool inplace = (a.in == a.out);
-        if (a.meter) {
-            if (!identity)
-                run_item_generic<true, true, true>(a, C, s, f0, f1, lane);
-            else if (inplace)
-                run_item_generic<false, false, true>(a, C, s, f0, f1, lane);
-            else
-                run_item_generic<false, true, true>(a, C, s, f0, f1, lane);
-        } else {
-            if (!identity)
-                run_item_generic<true, true, false>(a, C, s, f0, f1, lane);
-            else if (!inplace)
-                run_item_generic<false, true, false>(a, C, s, f0, f1, lane);
-        }
+        if (f0 < f1)
+            run_item_generic<GM, METER>(a, C, s, f0, f1, lane);
     }
 }
 
