@@ -260,7 +260,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    first_stream = rank * streams_per_gpu
+    first_stream = rank * streams_per_gpu      # == sharding.stream_range(world * streams_per_gpu, world, rank)[0]
     scale, gain = gain_table(first_stream, streams_per_gpu, channels)
 
     # ---- device-resident run: the whole workload in one ring slot, out of place so that the
@@ -379,13 +379,8 @@ def main():
 def gather_meters(cm, eng, dist, rank, world):
     """Per-stream meter rows of every rank to rank 0 over NCCL (the only collective on the path)."""
     import torch
-    n = eng.max_streams * eng.meter_row_u64()
-    # wrap the engine's device meter table without copying
-    class _Dev:
-        __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (eng.device_meters(), False), "version": 2}
-    mine = torch.as_tensor(_Dev(), device="cuda")
-    out = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-    dist.gather(mine, out, dst=0)
+    mine = cm.sharding.wrap_device_rows(eng.device_meters(), eng.max_streams * eng.meter_row_u64())
+    out = cm.sharding.gather_rows(mine, dist, rank, world)
     torch.cuda.synchronize()
     return out
 

@@ -1,0 +1,97 @@
+/* include/coolmic_b200_shim.h -- the reference's public transform / vumeter / iohandle entry
+ * points, exported by libcoolmic_b200.so on top of the cmgpu_* batch engine (include/cmgpu.h).
+ *
+ * Same names, argument meaning, ownership and error behaviour as libcoolmic-dsp, so that the
+ * objects drop into the existing pull chain  snddev -> transform -> tee -> {enc, vumeter}:
+ *
+ *   coolmic_iohandle_new/read/eof        reference include/coolmic-dsp/iohandle.h:54-66, src/iohandle.c:54-113
+ *   coolmic_transform_new/attach_iohandle/get_iohandle/set_master_gain
+ *                                        reference include/coolmic-dsp/transform.h:41-53, src/transform.c:65-222
+ *   coolmic_vumeter_new/reset/attach_iohandle/read/result
+ *                                        reference include/coolmic-dsp/vumeter.h:86-107, src/vumeter.c:69-218
+ *
+ * Objects are libigloo-style reference-counted objects: the first member is a base carrying the
+ * reference count; igloo_ro_ref()/igloo_ro_unref() semantics are provided by coolmic_b200_ref()
+ * / coolmic_b200_unref() when the library is built stand-alone (libigloo is an external,
+ * un-vendored dependency of the reference). When built into libcoolmic-dsp proper, compile the
+ * csrc/host sources with -DCOOLMIC_B200_WITH_IGLOO and they use <igloo/ro.h> directly.
+ *
+ * The arithmetic of every read runs on the GPU (one tick of a private one-stream cmgpu context
+ * per object); there is no CPU implementation behind these calls. Thousands of streams should
+ * use the batch engine in cmgpu.h directly -- see INTEGRATION.md.
+ */
+#ifndef COOLMIC_B200_SHIM_H
+#define COOLMIC_B200_SHIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include <sys/types.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef COOLMIC_ERROR_NONE
+#define COOLMIC_ERROR_NONE      (0)
+#define COOLMIC_ERROR_GENERIC   (-1)
+#define COOLMIC_ERROR_NOSYS     (-8)
+#define COOLMIC_ERROR_FAULT     (-9)
+#define COOLMIC_ERROR_INVAL     (-10)
+#define COOLMIC_ERROR_NOMEM     (-11)
+#endif
+
+#define COOLMIC_B200_MAX_CHANNELS 16
+
+#ifdef COOLMIC_B200_WITH_IGLOO
+#include <igloo/ro.h>
+typedef igloo_ro_t coolmic_b200_ro_t;
+#else
+typedef void *coolmic_b200_ro_t;                 /* what igloo_ro_t is to callers: any object */
+int coolmic_b200_ref(coolmic_b200_ro_t object);  /* igloo_ro_ref:   0, or non-zero for NULL */
+int coolmic_b200_unref(coolmic_b200_ro_t object);/* igloo_ro_unref: frees at zero            */
+#endif
+
+typedef struct coolmic_iohandle  coolmic_iohandle_t;
+typedef struct coolmic_transform coolmic_transform_t;
+typedef struct coolmic_vumeter   coolmic_vumeter_t;
+
+/* Field-for-field the reference's result type (vumeter.h:48-83); 192 bytes on LP64. */
+typedef struct {
+    uint_least32_t rate;
+    unsigned int   channels;
+    size_t         frames;
+    int16_t        global_peak;
+    double         global_power;
+    int16_t        channel_peak[COOLMIC_B200_MAX_CHANNELS];
+    double         channel_power[COOLMIC_B200_MAX_CHANNELS];
+} coolmic_vumeter_result_t;
+
+coolmic_iohandle_t *coolmic_iohandle_new(const char *name, coolmic_b200_ro_t associated, void *userdata,
+                                         int (*free)(void *), ssize_t (*read)(void *, void *, size_t),
+                                         int (*eof)(void *));
+ssize_t             coolmic_iohandle_read(coolmic_iohandle_t *self, void *buffer, size_t len);
+int                 coolmic_iohandle_eof(coolmic_iohandle_t *self);
+
+coolmic_transform_t *coolmic_transform_new(const char *name, coolmic_b200_ro_t associated,
+                                           uint_least32_t rate, unsigned int channels);
+int                  coolmic_transform_attach_iohandle(coolmic_transform_t *self, coolmic_iohandle_t *handle);
+coolmic_iohandle_t  *coolmic_transform_get_iohandle(coolmic_transform_t *self);
+int                  coolmic_transform_set_master_gain(coolmic_transform_t *self, unsigned int channels,
+                                                       uint16_t scale, const uint16_t *gain);
+
+coolmic_vumeter_t *coolmic_vumeter_new(const char *name, coolmic_b200_ro_t associated,
+                                       uint_least32_t rate, unsigned int channels);
+int                coolmic_vumeter_reset(coolmic_vumeter_t *self);
+int                coolmic_vumeter_attach_iohandle(coolmic_vumeter_t *self, coolmic_iohandle_t *handle);
+ssize_t            coolmic_vumeter_read(coolmic_vumeter_t *self, ssize_t maxlen);
+int                coolmic_vumeter_result(coolmic_vumeter_t *self, coolmic_vumeter_result_t *result);
+
+/* Which CUDA device the objects created from now on use (default 0, or $COOLMIC_B200_DEVICE). */
+int coolmic_b200_set_device(int device);
+/* Kernel launches issued on behalf of shim objects so far (evidence that reads run on the GPU). */
+uint64_t coolmic_b200_shim_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -12,3 +12,4 @@ from .binding import (  # noqa: F401
     LIB_PATH, Engine, CmgpuError, MeterState, Result, lib, build_library,
     PinnedArray, state_dict, FUSED, TRANSFORM, METER, SEPARATE_OUT, NO_PINNED, FORCE_GENERIC,
 )
+from . import sharding  # noqa: F401,E402

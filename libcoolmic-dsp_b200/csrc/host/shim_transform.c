@@ -1,0 +1,184 @@
+/* host/shim_transform.c -- coolmic_transform_* on the GPU.
+ *
+ * Same contract as reference src/transform.c: a pull stage that hands out whole frames only,
+ * carries the bytes of an unfinished frame to the next read (transform.c:126-165), applies the
+ * per-channel master gain (transform.c:101-124) and adapts gain vectors of a different width
+ * (transform.c:195-222). The gain itself runs as one tick of a private one-stream cmgpu context:
+ * pulled bytes -> pinned slot -> H2D -> fused_tick (transform only) -> D2H -> caller's buffer.
+ */
+#include "shim_internal.h"
+
+#include <string.h>
+
+#define SHIM_BLOCK_BYTES 8192u        /* the most the chain ever asks for at once (tee.c:91-97) */
+
+struct coolmic_transform {
+    shim_base_t base;
+    coolmic_iohandle_t *io;
+    unsigned char carry[2 * COOLMIC_B200_MAX_CHANNELS - 1];
+    size_t carry_fill;
+    uint_least32_t rate;
+    unsigned int channels;
+    /* setting kept on the host so that it survives until the context exists */
+    unsigned int gain_n;
+    uint16_t gain_scale;
+    uint16_t gain[COOLMIC_B200_MAX_CHANNELS];
+    int gain_dirty;
+    cmgpu_ctx_t *ctx;
+    unsigned int block_frames;
+};
+
+static void transform_destroy(void *self)
+{
+    coolmic_transform_t *t = self;
+    shim_unref(t->io);
+    if (t->ctx)
+        cmgpu_ctx_destroy(t->ctx);
+}
+
+coolmic_transform_t *coolmic_transform_new(const char *name, coolmic_b200_ro_t associated,
+                                           uint_least32_t rate, unsigned int channels)
+{
+    coolmic_transform_t *t;
+    (void)name, (void)associated;
+    /* the reference indexes gain[16] with `channels` unchecked (transform.c:69-70); refuse instead */
+    if (!rate || !channels || channels > COOLMIC_B200_MAX_CHANNELS)
+        return NULL;
+    t = shim_alloc(sizeof(*t), transform_destroy);
+    if (!t)
+        return NULL;
+    t->rate = rate;
+    t->channels = channels;
+    t->block_frames = SHIM_BLOCK_BYTES / (2u * channels);
+    return t;
+}
+
+int coolmic_transform_attach_iohandle(coolmic_transform_t *self, coolmic_iohandle_t *handle)
+{
+    if (!self)
+        return COOLMIC_ERROR_FAULT;
+    shim_unref(self->io);               /* NULL-safe, like igloo_ro_unref */
+    self->io = handle;
+    shim_ref(handle);
+    return COOLMIC_ERROR_NONE;
+}
+
+int coolmic_transform_set_master_gain(coolmic_transform_t *self, unsigned int channels, uint16_t scale,
+                                      const uint16_t *gain)
+{
+    unsigned int c;
+    if (!self)
+        return COOLMIC_ERROR_FAULT;
+    if (!channels || !scale || !gain) {
+        self->gain_scale = 0;
+    } else if (channels == self->channels) {
+        memcpy(self->gain, gain, sizeof(*gain) * channels);
+        self->gain_scale = scale;
+    } else if (channels == 1) {
+        for (c = 0; c < self->channels; c++)
+            self->gain[c] = gain[0];
+        self->gain_scale = scale;
+    } else if (channels == 2 && self->channels == 1) {
+        self->gain[0] = (uint16_t)(((uint32_t)gain[0] + (uint32_t)gain[1]) / 2u);
+        self->gain_scale = scale;
+    } else {
+        return COOLMIC_ERROR_INVAL;     /* previous setting stays in force */
+    }
+    self->gain_n = self->channels;
+    self->gain_dirty = 1;
+    return COOLMIC_ERROR_NONE;
+}
+
+static int transform_device_ready(coolmic_transform_t *t)
+{
+    if (!t->ctx) {
+        t->ctx = cmgpu_ctx_create(shim_device(), t->channels, 1, 1, t->block_frames, 0);
+        if (!t->ctx)
+            return -1;
+        t->gain_dirty = 1;
+    }
+    if (t->gain_dirty) {
+        if (cmgpu_stream_set_gain(t->ctx, 0, t->gain_scale ? t->channels : 0, t->gain_scale, t->gain) != CMGPU_OK)
+            return -1;
+        t->gain_dirty = 0;
+    }
+    return 0;
+}
+
+/* whole frames in `buffer`, in place, on the GPU */
+static int transform_process(coolmic_transform_t *t, void *buffer, size_t frames)
+{
+    const size_t framesize = 2u * t->channels;
+    if (!frames || !t->gain_scale)      /* transform.c:107-108: no gain set, nothing to do */
+        return 0;
+    if (transform_device_ready(t) != 0)
+        return -1;
+    while (frames) {
+        uint32_t n = frames > t->block_frames ? t->block_frames : (uint32_t)frames;
+        uint64_t before = cmgpu_launch_count(t->ctx);
+        void *slot = cmgpu_host_slot(t->ctx, 0);
+        memcpy(slot, buffer, n * framesize);
+        if (cmgpu_slot_set_frames(t->ctx, 0, &n) != CMGPU_OK || cmgpu_submit(t->ctx, 0, NULL) != CMGPU_OK ||
+            cmgpu_process(t->ctx, 0, CMGPU_TRANSFORM) != CMGPU_OK || cmgpu_fetch(t->ctx, 0, NULL) != CMGPU_OK ||
+            cmgpu_sync(t->ctx) != CMGPU_OK)
+            return -1;
+        memcpy(buffer, slot, n * framesize);
+        shim_count_launches(cmgpu_launch_count(t->ctx) - before);
+        buffer = (char *)buffer + n * framesize;
+        frames -= n;
+    }
+    return 0;
+}
+
+static ssize_t transform_read(void *userdata, void *buffer, size_t len)
+{
+    coolmic_transform_t *t = userdata;
+    const size_t framesize = 2u * t->channels;
+    size_t have = 0, rest;
+    ssize_t r;
+
+    len -= len % framesize;
+    if (!len)
+        return 0;
+    if (t->carry_fill) {                /* an unfinished frame from last time goes first */
+        memcpy(buffer, t->carry, t->carry_fill);
+        have = t->carry_fill;
+        t->carry_fill = 0;
+    }
+    r = coolmic_iohandle_read(t->io, (char *)buffer + have, len - have);
+    if (r > 0)
+        have += (size_t)r;
+    rest = have % framesize;
+    if (rest) {
+        memcpy(t->carry, (char *)buffer + have - rest, rest);
+        t->carry_fill = rest;
+        have -= rest;
+    }
+    if (transform_process(t, buffer, have / framesize) != 0)
+        return -1;                      /* any CUDA failure is a read error; no CPU fallback */
+    return (ssize_t)have;
+}
+
+static int transform_eof(void *userdata)
+{
+    coolmic_transform_t *t = userdata;
+    if (!t->io)
+        return 1;
+    return coolmic_iohandle_eof(t->io);
+}
+
+static int transform_release(void *userdata)
+{
+    return shim_unref(userdata);
+}
+
+coolmic_iohandle_t *coolmic_transform_get_iohandle(coolmic_transform_t *self)
+{
+    coolmic_iohandle_t *h;
+    if (shim_ref(self) != COOLMIC_ERROR_NONE)
+        return NULL;
+    h = coolmic_iohandle_new(NULL, NULL, self, transform_release, transform_read, transform_eof);
+    if (!h)
+        shim_unref(self);
+    return h;
+}

@@ -1,0 +1,225 @@
+/* tests/shim_harness.c -- drives the product's coolmic_* object shim (include/coolmic_b200_shim.h)
+ * exactly the way oracle/ref_harness.c drives the reference's objects, so that the same Python
+ * test code can run both and compare. Test code only. */
+#include <stdint.h>
+#include <string.h>
+#include <sys/types.h>
+
+#include "../include/coolmic_b200_shim.h"
+
+typedef struct shimh_result {
+    int32_t  rc;
+    uint32_t rate;
+    uint32_t channels;
+    int32_t  global_peak;
+    uint64_t frames;
+    double   global_power;
+    int32_t  channel_peak[16];
+    double   channel_power[16];
+} shimh_result_t;
+
+static void flatten(shimh_result_t *dst, int rc, const coolmic_vumeter_result_t *src)
+{
+    unsigned c;
+    memset(dst, 0, sizeof(*dst));
+    dst->rc = rc;
+    if (rc != COOLMIC_ERROR_NONE)
+        return;
+    dst->rate = src->rate;
+    dst->channels = src->channels;
+    dst->global_peak = src->global_peak;
+    dst->frames = src->frames;
+    dst->global_power = src->global_power;
+    for (c = 0; c < 16; c++) {
+        dst->channel_peak[c] = src->channel_peak[c];
+        dst->channel_power[c] = src->channel_power[c];
+    }
+}
+
+typedef struct memsrc {
+    const char *data;
+    size_t len, pos, chunk;
+    int fail_at_end;        /* report -1 instead of 0 once exhausted */
+} memsrc_t;
+
+static ssize_t memsrc_read(void *userdata, void *buffer, size_t len)
+{
+    memsrc_t *m = userdata;
+    size_t n = m->len - m->pos;
+    if (!n && m->fail_at_end)
+        return -1;
+    if (n > len)
+        n = len;
+    if (m->chunk && n > m->chunk)
+        n = m->chunk;
+    memcpy(buffer, m->data + m->pos, n);
+    m->pos += n;
+    return (ssize_t)n;
+}
+
+static int memsrc_eof(void *userdata)
+{
+    memsrc_t *m = userdata;
+    return m->pos >= m->len;
+}
+
+unsigned shimh_sizeof_result(void) { return (unsigned)sizeof(coolmic_vumeter_result_t); }
+
+long shimh_transform(const void *in, size_t in_bytes, unsigned rate, unsigned channels,
+                     int set_gain, unsigned gain_n, unsigned scale, const uint16_t *gain,
+                     size_t src_chunk, size_t pull, void *out, size_t out_cap, int *gain_rc)
+{
+    memsrc_t mem = { in, in_bytes, 0, src_chunk, 0 };
+    coolmic_iohandle_t *src, *h;
+    coolmic_transform_t *tr;
+    size_t done = 0;
+
+    tr = coolmic_transform_new("tr", NULL, rate, channels);
+    if (!tr)
+        return -1;
+    if (set_gain) {
+        int rc = coolmic_transform_set_master_gain(tr, gain_n, (uint16_t)scale, gain);
+        if (gain_rc)
+            *gain_rc = rc;
+    }
+    src = coolmic_iohandle_new("memsrc", NULL, &mem, NULL, memsrc_read, memsrc_eof);
+    coolmic_transform_attach_iohandle(tr, src);
+    coolmic_b200_unref(src);
+    h = coolmic_transform_get_iohandle(tr);
+    if (!pull)
+        pull = 1024;
+    for (;;) {
+        size_t want = out_cap - done < pull ? out_cap - done : pull;
+        ssize_t r;
+        if (!want)
+            break;
+        r = coolmic_iohandle_read(h, (char *)out + done, want);
+        if (r <= 0)
+            break;
+        done += (size_t)r;
+    }
+    coolmic_b200_unref(h);
+    coolmic_b200_unref(tr);
+    return (long)done;
+}
+
+long shimh_vumeter(const void *in, size_t in_bytes, unsigned rate, unsigned channels,
+                   size_t src_chunk, long maxlen, unsigned result_every,
+                   shimh_result_t *results, size_t results_cap)
+{
+    memsrc_t mem = { in, in_bytes, 0, src_chunk, 0 };
+    coolmic_iohandle_t *src;
+    coolmic_vumeter_t *vu;
+    coolmic_vumeter_result_t res;
+    size_t n = 0;
+    unsigned good = 0;
+
+    vu = coolmic_vumeter_new("vu", NULL, rate, channels);
+    if (!vu)
+        return -1;
+    src = coolmic_iohandle_new("memsrc", NULL, &mem, NULL, memsrc_read, memsrc_eof);
+    coolmic_vumeter_attach_iohandle(vu, src);
+    coolmic_b200_unref(src);
+    for (;;) {
+        ssize_t r = coolmic_vumeter_read(vu, maxlen);
+        if (r <= 0)
+            break;
+        if (result_every && ++good == result_every) {
+            int rc = coolmic_vumeter_result(vu, &res);
+            good = 0;
+            if (n < results_cap)
+                flatten(&results[n++], rc, &res);
+        }
+    }
+    {
+        int rc = coolmic_vumeter_result(vu, &res);
+        if (n < results_cap)
+            flatten(&results[n++], rc, &res);
+    }
+    coolmic_b200_unref(vu);
+    return (long)n;
+}
+
+/* mem -> transform -> vumeter, the meter pulling straight from the transform's handle */
+long shimh_chain(const void *in, size_t in_bytes, unsigned rate, unsigned channels,
+                 int set_gain, unsigned gain_n, unsigned scale, const uint16_t *gain,
+                 size_t src_chunk, long maxlen, unsigned result_every,
+                 shimh_result_t *results, size_t results_cap)
+{
+    memsrc_t mem = { in, in_bytes, 0, src_chunk, 0 };
+    coolmic_iohandle_t *src, *h;
+    coolmic_transform_t *tr;
+    coolmic_vumeter_t *vu;
+    coolmic_vumeter_result_t res;
+    size_t n = 0;
+    unsigned good = 0;
+
+    tr = coolmic_transform_new("tr", NULL, rate, channels);
+    vu = coolmic_vumeter_new("vu", NULL, rate, channels);
+    if (!tr || !vu)
+        return -1;
+    if (set_gain)
+        coolmic_transform_set_master_gain(tr, gain_n, (uint16_t)scale, gain);
+    src = coolmic_iohandle_new("memsrc", NULL, &mem, NULL, memsrc_read, memsrc_eof);
+    coolmic_transform_attach_iohandle(tr, src);
+    coolmic_b200_unref(src);
+    h = coolmic_transform_get_iohandle(tr);
+    coolmic_vumeter_attach_iohandle(vu, h);
+    coolmic_b200_unref(h);
+    for (;;) {
+        ssize_t r = coolmic_vumeter_read(vu, maxlen);
+        if (r <= 0)
+            break;
+        if (result_every && ++good == result_every) {
+            int rc = coolmic_vumeter_result(vu, &res);
+            good = 0;
+            if (n < results_cap)
+                flatten(&results[n++], rc, &res);
+        }
+    }
+    {
+        int rc = coolmic_vumeter_result(vu, &res);
+        if (n < results_cap)
+            flatten(&results[n++], rc, &res);
+    }
+    coolmic_b200_unref(vu);
+    coolmic_b200_unref(tr);
+    return (long)n;
+}
+
+/* argument checks that need no device */
+int shimh_null_checks(void)
+{
+    coolmic_vumeter_result_t res;
+    int bad = 0;
+    bad |= coolmic_transform_new("t", NULL, 0, 2) != NULL;
+    bad |= coolmic_transform_new("t", NULL, 48000, 0) != NULL;
+    bad |= coolmic_transform_new("t", NULL, 48000, 17) != NULL;
+    bad |= coolmic_vumeter_new("v", NULL, 0, 2) != NULL;
+    bad |= coolmic_vumeter_new("v", NULL, 48000, 0) != NULL;
+    bad |= coolmic_transform_attach_iohandle(NULL, NULL) != COOLMIC_ERROR_FAULT;
+    bad |= coolmic_transform_set_master_gain(NULL, 1, 1, NULL) != COOLMIC_ERROR_FAULT;
+    bad |= coolmic_vumeter_attach_iohandle(NULL, NULL) != COOLMIC_ERROR_FAULT;
+    bad |= coolmic_vumeter_reset(NULL) != COOLMIC_ERROR_FAULT;
+    bad |= coolmic_vumeter_read(NULL, -1) != -1;
+    bad |= coolmic_vumeter_result(NULL, &res) != COOLMIC_ERROR_FAULT;
+    bad |= coolmic_iohandle_new("h", NULL, NULL, NULL, NULL, NULL) != NULL;
+    bad |= coolmic_iohandle_read(NULL, &res, 4) != COOLMIC_ERROR_FAULT;
+    bad |= coolmic_iohandle_eof(NULL) != COOLMIC_ERROR_FAULT;
+    {
+        /* lifecycle without ever touching the device: new -> set gain -> INVAL case -> unref */
+        coolmic_transform_t *t = coolmic_transform_new("t", NULL, 48000, 3);
+        uint16_t g[3] = { 1, 2, 3 };
+        coolmic_vumeter_t *v = coolmic_vumeter_new("v", NULL, 48000, 2);
+        bad |= !t || !v;
+        bad |= coolmic_transform_set_master_gain(t, 3, 2, g) != COOLMIC_ERROR_NONE;
+        bad |= coolmic_transform_set_master_gain(t, 2, 2, g) != COOLMIC_ERROR_INVAL;
+        bad |= coolmic_transform_set_master_gain(t, 1, 2, g) != COOLMIC_ERROR_NONE;
+        bad |= coolmic_transform_set_master_gain(t, 0, 0, NULL) != COOLMIC_ERROR_NONE;
+        bad |= coolmic_vumeter_result(v, &res) != COOLMIC_ERROR_INVAL;     /* no frames yet */
+        bad |= coolmic_vumeter_reset(v) != COOLMIC_ERROR_NONE;
+        coolmic_b200_unref(t);
+        coolmic_b200_unref(v);
+    }
+    return bad;
+}

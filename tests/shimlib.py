@@ -1,0 +1,79 @@
+"""ctypes driver for tests/shim_harness.c: the product's coolmic_* objects behind the same
+transform()/vumeter() call shape as oracle.pyoracle.RefLib, so tests read alike for both."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from oracle.pyoracle import Result, _bytes, _res_dict, _u16
+
+ROOT = Path(__file__).resolve().parents[1]
+LIBDIR = ROOT / "libcoolmic-dsp_b200" / "lib"
+SO = Path(__file__).resolve().parent / "_build" / "libshimh.so"
+
+
+def build() -> Path:
+    src = Path(__file__).resolve().parent / "shim_harness.c"
+    if SO.exists() and SO.stat().st_mtime > max(src.stat().st_mtime, (LIBDIR / "libcoolmic_b200.so").stat().st_mtime):
+        return SO
+    SO.parent.mkdir(exist_ok=True)
+    subprocess.run(["gcc", "-std=gnu11", "-O2", "-g", "-fPIC", "-Wall", "-Wextra", "-shared", "-o", str(SO), str(src),
+                    "-L", str(LIBDIR), "-lcoolmic_b200", f"-Wl,-rpath,{LIBDIR}"], check=True)
+    return SO
+
+
+class ShimLib:
+    kind = "b200 shim"
+
+    def __init__(self):
+        self.lib = L = C.CDLL(str(build()))
+        L.shimh_sizeof_result.restype = C.c_uint
+        L.shimh_null_checks.restype = C.c_int
+        L.shimh_transform.restype = C.c_long
+        L.shimh_transform.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_int, C.c_uint, C.c_uint,
+                                      C.POINTER(C.c_uint16), C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
+                                      C.POINTER(C.c_int)]
+        L.shimh_vumeter.restype = C.c_long
+        L.shimh_vumeter.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_size_t, C.c_long, C.c_uint,
+                                    C.POINTER(Result), C.c_size_t]
+        L.shimh_chain.restype = C.c_long
+        L.shimh_chain.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_int, C.c_uint, C.c_uint,
+                                  C.POINTER(C.c_uint16), C.c_size_t, C.c_long, C.c_uint, C.POINTER(Result), C.c_size_t]
+
+    def transform(self, pcm, channels, gain=None, rate=48000, src_chunk=0, pull=1024):
+        src = _bytes(pcm)
+        out = np.zeros(src.size + 64, dtype=np.uint8)
+        rc = C.c_int(0)
+        if gain is None:
+            args = (0, 0, 0, None)
+        else:
+            keep, gp = _u16(gain[2])
+            args = (1, gain[0], gain[1], gp)
+        n = self.lib.shimh_transform(src.ctypes.data, src.size, rate, channels, *args, src_chunk, pull,
+                                     out.ctypes.data, out.size, C.byref(rc))
+        if n < 0:
+            raise RuntimeError("shim transform could not be constructed")
+        return out[:n].copy(), int(rc.value)
+
+    def vumeter(self, pcm, channels, rate=48000, src_chunk=0, maxlen=-1, result_every=0, cap=4096):
+        src = _bytes(pcm)
+        res = (Result * cap)()
+        n = self.lib.shimh_vumeter(src.ctypes.data, src.size, rate, channels, src_chunk, maxlen, result_every, res, cap)
+        if n < 0:
+            raise RuntimeError("shim vumeter could not be constructed")
+        return [_res_dict(res[i]) for i in range(n)]
+
+    def chain(self, pcm, channels, gain=None, rate=48000, src_chunk=0, maxlen=-1, result_every=0, cap=4096):
+        src = _bytes(pcm)
+        res = (Result * cap)()
+        if gain is None:
+            args = (0, 0, 0, None)
+        else:
+            keep, gp = _u16(gain[2])
+            args = (1, gain[0], gain[1], gp)
+        n = self.lib.shimh_chain(src.ctypes.data, src.size, rate, channels, *args, src_chunk, maxlen, result_every,
+                                 res, cap)
+        if n < 0:
+            raise RuntimeError("shim chain could not be constructed")
+        return [_res_dict(res[i]) for i in range(n)]
