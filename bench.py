@@ -37,11 +37,21 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 WORKLOADS = {
-    # name: (channels, streams per GPU, seconds, rate, description)
-    "cfg2": (2, 1024, 10, 48000, "1,024 x 48 kHz stereo S16 streams x 10 s per GPU, one device ring, one fused tick per step"),
-    "cfg4a": (8, 4096, 2, 48000, "4,096 x 48 kHz 8-channel S16 streams x 2 s per GPU, per-channel gain + 8-channel meter"),
-    "l2fit": (2, 256, 1, 24000, "DIAGNOSTIC ONLY: 256 stereo streams x 24,000 frames (24.6 MB in + 24.6 MB out, L2 resident)"),
-    "cfg5": (2, 65536, 1, 48000, "65,536 x 48 kHz stereo S16 streams x 1 s in total, sharded by stream across the GPUs"),
+    # device-timed run: `ticks` ticks of `frames` frames over a ring of `ring` slots per step
+    # (graph=True: the ring's ticks replayed as one CUDA graph launch); e2e: `e2e_ticks` ticks of `e2e_frames`
+    "cfg2": dict(channels=2, streams=1024, rate=48000, frames=480000, ticks=1, ring=1, graph=False,
+                 e2e_frames=48000, e2e_ticks=10,
+                 desc="1,024 x 48 kHz stereo S16 streams x 10 s per GPU, one device ring, one fused tick per step"),
+    "cfg3": dict(channels=1, streams=16384, rate=16000, frames=320, ticks=50, ring=50, graph=True,
+                 e2e_frames=320, e2e_ticks=50,
+                 desc="16,384 x 16 kHz mono streams, 20 ms (320-frame, 640-byte) stream-blocks; step = 50 ticks over a "
+                      "50-slot ring (1.05 GB in+out) replayed as one CUDA graph"),
+    "cfg4a": dict(channels=8, streams=4096, rate=48000, frames=96000, ticks=1, ring=1, graph=False,
+                  e2e_frames=9600, e2e_ticks=10,
+                  desc="4,096 x 48 kHz 8-channel S16 streams x 2 s per GPU, per-channel gain + 8-channel meter (parity mode)"),
+    "cfg5": dict(channels=2, streams=65536, rate=48000, frames=48000, ticks=1, ring=1, graph=False,
+                 e2e_frames=4800, e2e_ticks=10, strong=True,
+                 desc="65,536 x 48 kHz stereo S16 streams x 1 s in total, sharded by stream across the GPUs"),
 }
 
 
@@ -133,18 +143,19 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
 
 
-def cpu_reference_run(channels, rate, seconds, budget_s=12.0, threads=None, streams=None):
+def cpu_reference_run(channels, rate, frames, budget_s=12.0, threads=None, streams=None):
     """The reference's own CPU path (oracle/_ref: mem -> transform -> tee -> {consumer, vumeter},
     1,024-byte pulls, result every 20 reads) over `streams` streams of the workload on `threads`
     pthreads, repeated until ~budget_s seconds have been spent. Falls back to the oracle port."""
     from oracle import pyoracle
     threads = threads or os.cpu_count() or 1
-    frames = rate * seconds
     ref = pyoracle.ref()
     streams = streams or max(threads, min(4 * threads, 256))
     # keep the sample's memory bounded (~1 GB of input)
     while streams * frames * channels * 2 > (1 << 30) and frames > rate:
         frames //= 2
+    while streams * frames * channels < 4_000_000:      # tiny blocks: more streams, same shape
+        streams *= 2
     pcm = np.empty((streams, frames * channels), dtype=np.int16)
     synth_block(0, streams, channels, frames, pcm)
     scale, gain = gain_table(0, streams, channels)
@@ -179,7 +190,20 @@ def dist_env():
     return rank, world, local
 
 
+def emit(line: dict):
+    """The ONE JSON line, on the real stdout (libraries such as NCCL print to fd 1 too)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    # keep stdout clean for the JSON line: everything else written to fd 1 goes to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -196,16 +220,20 @@ def main():
         args.warmup = 3
 
     rank, world, local = dist_env()
-    channels, streams_per_gpu, seconds, rate, desc = WORKLOADS[args.workload]
+    wl = WORKLOADS[args.workload]
+    channels, streams_per_gpu, rate, desc = wl["channels"], wl["streams"], wl["rate"], wl["desc"]
+    frames, ticks, ring = wl["frames"], wl["ticks"], wl["ring"]
     scaling = "weak"
-    if args.workload == "cfg5":
+    if wl.get("strong"):
         streams_per_gpu //= max(world, 1)
         scaling = "strong"
-    frames = rate * seconds
-    samples_per_step_rank = streams_per_gpu * frames * channels
+    seconds = frames * ticks / rate
+    samples_per_step_rank = streams_per_gpu * frames * ticks * channels
+    ring_bytes = 2 * ring * streams_per_gpu * frames * channels * 2
     config = {"workload": f"{args.workload}: {desc}", "streams_per_gpu": streams_per_gpu, "channels": channels,
-              "rate_hz": rate, "seconds_per_stream": seconds, "gains": "every stream active, scale 1000+s%9000, gain ~0.75..3.1",
-              "l2": "inputs (>=1.5 GB per GPU) far larger than the 126 MB L2; no flush needed",
+              "rate_hz": rate, "frames_per_tick": frames, "ticks_per_step": ticks, "ring_slots": ring,
+              "cuda_graph": bool(wl["graph"]), "gains": "every stream active, scale 1000+s%9000, gain ~0.75..3.1",
+              "l2": f"in+out rings of {ring_bytes / 1e9:.2f} GB per GPU cycled every step: far larger than the 126 MB L2, no flush needed",
               "sharding": "by stream, one process per GPU, no data-path collective"}
     if args.mode != "fused":
         config["diagnostic_mode"] = args.mode
@@ -216,10 +244,10 @@ def main():
             return 0
         runs = []
         for _ in range(args.warmup if args.warmup < 2 else 1):
-            cpu_reference_run(channels, rate, seconds, budget_s=1.0)
+            cpu_reference_run(channels, rate, frames * ticks, budget_s=1.0)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            runs.append(cpu_reference_run(channels, rate, seconds, budget_s=max(1.0, 60.0 / max(args.steps, 1))))
+            runs.append(cpu_reference_run(channels, rate, frames * ticks, budget_s=max(1.0, 60.0 / max(args.steps, 1))))
         wall = time.perf_counter() - t0
         value = float(np.mean([r["value"] for r in runs]))
         base = dict(runs[-1]); base["value"] = value
@@ -230,7 +258,7 @@ def main():
                 "config": config, "cpu_baseline": base,
                 "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ---------------------------------------------------------------- our arm
@@ -263,27 +291,33 @@ def main():
     first_stream = rank * streams_per_gpu      # == sharding.stream_range(world * streams_per_gpu, world, rank)[0]
     scale, gain = gain_table(first_stream, streams_per_gpu, channels)
 
-    # ---- device-resident run: the whole workload in one ring slot, out of place so that the
-    #      input stays pristine across steps
-    eng = cm.Engine(channels, streams_per_gpu, frames, ring_slots=1, device=local,
+    # ---- device-resident run: the step's ticks live in a ring of `ring` slots, out of place so
+    #      that the input stays pristine across steps
+    eng = cm.Engine(channels, streams_per_gpu, frames, ring_slots=ring, device=local,
                     flags=cm.SEPARATE_OUT | cm.NO_PINNED)
     eng.set_gain_table(scale, gain)
     chunk = max(1, (256 << 20) // (frames * channels * 2))
-    stage = np.empty((streams_per_gpu, eng.stride // 2), dtype=np.int16)
-    for lo in range(0, streams_per_gpu, chunk):
-        hi = min(streams_per_gpu, lo + chunk)
-        synth_block(first_stream + lo, hi - lo, channels, frames, stage[lo:hi])
-    eng.submit(0, stage)
-    eng.sync()
+    stage = np.zeros((streams_per_gpu, eng.stride // 2), dtype=np.int16)
+    for slot in range(ring):
+        for lo in range(0, streams_per_gpu, chunk):
+            hi = min(streams_per_gpu, lo + chunk)
+            synth_block(first_stream + lo, hi - lo, channels, frames, stage[lo:hi], slot * frames)
+        eng.submit(slot, stage)
+        eng.sync()
+
+    def timed(steps):
+        if wl["graph"]:
+            return eng.time_cycles(steps * (ticks // ring), 0, ring, flags=pflags)
+        return eng.time_process(steps * ticks, 0, ring, flags=pflags)
 
     pflags = {"fused": cm.FUSED, "transform": cm.TRANSFORM, "meter": cm.METER, "copy": 0}[args.mode]
     clocks = ClockSampler(local)
-    eng.time_process(args.warmup, flags=pflags)
+    timed(args.warmup)
     eng.reset_meters()
     launches0 = eng.launch_count()
     barrier()
     clocks.start()
-    ms_total = eng.time_process(args.steps, flags=pflags)
+    ms_total = timed(args.steps)
     barrier()
     clk = clocks.stop()
     launches = eng.launch_count() - launches0
@@ -293,14 +327,17 @@ def main():
 
     # meter sanity on what was just measured: K identical ticks -> K * frames frames per stream
     snap = eng.snapshot(0, min(4, streams_per_gpu))
-    assert int(snap[0].frames) == (args.steps * frames if pflags & cm.METER else 0), "meter did not see every timed tick"
+    assert int(snap[0].frames) == (args.steps * ticks * frames if pflags & cm.METER else 0), "meter did not see every timed tick"
     kernel = eng.kernel_name()
     peak, peak_src = measured_peak()
-    alg_bytes = 4.0 * samples_per_step_rank
-    achieved = alg_bytes / (ms_step * 1e-3) / 1e9
+    launches_per_step = max(1, launches // max(args.steps, 1))
+    alg_bytes = 4.0 * samples_per_step_rank / launches_per_step        # per kernel launch
+    ms_launch = ms_step / launches_per_step
+    achieved = alg_bytes / (ms_launch * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": kernel, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_step,
+                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_launch,
+                "launches_per_step": launches_per_step,
                 "frac_of_nominal_8TBps": achieved / 8000.0}
     prof = ROOT / "profiles" / "traffic.json"
     if prof.exists():
@@ -314,8 +351,8 @@ def main():
     # ---- end to end through the C ABI with host buffers: 1 s ticks through a 4-slot ring
     e2e = None
     if not args.no_e2e:
-        tick_frames = rate
-        n_ticks = seconds
+        tick_frames = wl["e2e_frames"]
+        n_ticks = wl["e2e_ticks"]
         e2e_steps = args.e2e_steps or min(args.steps, 5)
         eng = cm.Engine(channels, streams_per_gpu, tick_frames, ring_slots=4, device=local, flags=cm.NO_PINNED)
         eng.set_gain_table(scale, gain)
@@ -347,7 +384,7 @@ def main():
             e2e_step()
         barrier()
         wall = max_over_ranks(time.perf_counter() - t0)
-        assert int(meter_rows[0].frames) == frames
+        assert int(meter_rows[0].frames) == tick_frames * n_ticks
         slot_bytes = streams_per_gpu * eng.stride
         meter_bytes = streams_per_gpu * eng.meter_row_u64() * 8
         e2e = {"value": samples_per_step_rank * world * e2e_steps / wall / 1e6, "unit": "Msamples/s",
@@ -360,7 +397,7 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        cpu = cpu_reference_run(channels, rate, seconds, budget_s=12.0)
+        cpu = cpu_reference_run(channels, rate, frames * ticks, budget_s=12.0)
         cpu.pop("seconds", None)
 
     if rank == 0:
@@ -370,7 +407,7 @@ def main():
                 "dtype": "int32 (S16 in/out, int64 power)", "data": "synthetic", "config": config,
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0

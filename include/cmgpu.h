@@ -130,6 +130,11 @@ int cmgpu_submit(cmgpu_ctx_t *ctx, unsigned slot, const void *host);
 /* One tick: ONE fused kernel launch over all active streams of the slot, on the compute
  * stream, ordered after the slot's last submit. Asynchronous. */
 int cmgpu_process(cmgpu_ctx_t *ctx, unsigned slot, unsigned flags);
+/* Small-buffer regime: `n_slots` consecutive ticks (slots first_slot ..) replayed as ONE cached
+ * CUDA graph launch, so that per-tick launch latency does not dominate 20 ms blocks. Ordered
+ * after the slots' last submits; the graph is rebuilt when gains, frames or the active stream
+ * count change. Asynchronous. */
+int cmgpu_process_cycle(cmgpu_ctx_t *ctx, unsigned first_slot, unsigned n_slots, unsigned flags);
 /* Device -> host copy of the slot's (transformed) PCM on the download stream, ordered after
  * the slot's last tick. `host` NULL = the pinned staging slot. Asynchronous if page-locked. */
 int cmgpu_fetch(cmgpu_ctx_t *ctx, unsigned slot, void *host);
@@ -164,6 +169,9 @@ int      cmgpu_meter_decode(const uint64_t *rows, unsigned count, unsigned chann
  * device time in milliseconds between CUDA events recorded on the compute stream around them. */
 int cmgpu_time_process(cmgpu_ctx_t *ctx, unsigned first_slot, unsigned n_slots, unsigned reps,
                        unsigned flags, float *ms);
+/* The same for `cycles` replays of the cached CUDA graph of n_slots ticks (cmgpu_process_cycle). */
+int cmgpu_time_cycles(cmgpu_ctx_t *ctx, unsigned first_slot, unsigned n_slots, unsigned cycles,
+                      unsigned flags, float *ms);
 /* Number of kernel launches this context has issued so far. */
 uint64_t cmgpu_launch_count(const cmgpu_ctx_t *ctx);
 /* Name of the kernel variant cmgpu_process would pick for the current shape (for logs). */

@@ -82,6 +82,7 @@ SYMBOLS = {
     "cmgpu_slot_set_frames": (C.c_int, [_P, C.c_uint, C.POINTER(C.c_uint32)]),
     "cmgpu_submit": (C.c_int, [_P, C.c_uint, _P]),
     "cmgpu_process": (C.c_int, [_P, C.c_uint, C.c_uint]),
+    "cmgpu_process_cycle": (C.c_int, [_P, C.c_uint, C.c_uint, C.c_uint]),
     "cmgpu_fetch": (C.c_int, [_P, C.c_uint, _P]),
     "cmgpu_sync": (C.c_int, [_P]),
     "cmgpu_slot_wait": (C.c_int, [_P, C.c_uint]),
@@ -93,6 +94,7 @@ SYMBOLS = {
     "cmgpu_meter_row_u64": (C.c_uint, [_P]),
     "cmgpu_meter_decode": (C.c_int, [C.POINTER(C.c_uint64), C.c_uint, C.c_uint, C.POINTER(MeterState)]),
     "cmgpu_time_process": (C.c_int, [_P, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_float)]),
+    "cmgpu_time_cycles": (C.c_int, [_P, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_float)]),
     "cmgpu_launch_count": (C.c_uint64, [_P]),
     "cmgpu_kernel_name": (C.c_char_p, [_P]),
     "cmgpu_recipe_eval": (C.c_int, [C.c_uint16, C.c_uint16, C.c_int16]),
@@ -216,6 +218,9 @@ class Engine:
     def process(self, slot: int, flags: int = FUSED):
         _check(self.L.cmgpu_process(self.ctx, slot, flags), "cmgpu_process")
 
+    def process_cycle(self, first_slot: int, n_slots: int, flags: int = FUSED):
+        _check(self.L.cmgpu_process_cycle(self.ctx, first_slot, n_slots, flags), "cmgpu_process_cycle")
+
     def fetch(self, slot: int, host: np.ndarray | None = None):
         ptr = None if host is None else host.ctypes.data
         if host is not None:
@@ -271,6 +276,12 @@ class Engine:
         ms = C.c_float(0)
         _check(self.L.cmgpu_time_process(self.ctx, first_slot, n_slots, reps, flags, C.byref(ms)),
                "cmgpu_time_process")
+        return float(ms.value)
+
+    def time_cycles(self, cycles: int, first_slot: int = 0, n_slots: int = 1, flags: int = FUSED) -> float:
+        ms = C.c_float(0)
+        _check(self.L.cmgpu_time_cycles(self.ctx, first_slot, n_slots, cycles, flags, C.byref(ms)),
+               "cmgpu_time_cycles")
         return float(ms.value)
 
     def launch_count(self) -> int:

@@ -94,7 +94,6 @@ struct cmgpu_ctx {
     unsigned channels = 0, max_streams = 0, active = 0, slots = 0, block_frames = 0, flags = 0;
     size_t stride = 0, slot_bytes = 0;
     unsigned row_u64 = 0, pbits = 0;
-    uint64_t tick_seq = 0;
     uint64_t launches = 0;
     int num_sms = 0;
 
@@ -105,6 +104,7 @@ struct cmgpu_ctx {
     std::vector<uint16_t> h_scale, h_gain;         // adapted settings, [stream], [stream][channels]
     unsigned dirty_lo = 0, dirty_hi = 0;           // gain rows to upload: [lo, hi)
     unsigned long long *d_meters = nullptr;
+    unsigned long long *d_tick = nullptr;          // [0] tick sequence number, [1] CTA completion ticket
     uint32_t *d_frames = nullptr;                  // [slots][max_streams]
     std::vector<char> has_frames;
     std::vector<uint64_t> scratch;                 // snapshot staging
@@ -114,9 +114,14 @@ struct cmgpu_ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     std::mutex mu;
 
-    // streams grouped by gain mode (GM_IDENTITY / GM_MASKED / GM_ADDALL): one launch per group
-    std::vector<uint32_t> h_ids[3];
-    uint32_t *d_ids = nullptr;                     // [3][max_streams]
+    // cached CUDA graph of a cycle of ticks (launch-bound small-buffer regime)
+    cudaGraphExec_t graph = nullptr;
+    unsigned graph_first = 0, graph_n = 0, graph_flags = 0;
+    uint64_t graph_launches = 0;                   // kernel nodes in the cached graph
+    uint64_t config_gen = 0, graph_gen = ~0ull;    // bumped whenever launch arguments may change
+
+    // how many active streams need which gain mode; the tick runs in the cheapest common one
+    unsigned n_mode[3] = {0, 0, 0};                // GM_IDENTITY / GM_MASKED / GM_ADDALL
     bool classes_dirty = true;
 
     // launch plan (depends on shape only)
@@ -252,6 +257,7 @@ int upload_gains_locked(cmgpu_ctx *c)
 void mark_dirty(cmgpu_ctx *c, unsigned lo, unsigned hi)
 {
     c->classes_dirty = true;
+    c->config_gen++;
     if (lo < c->dirty_lo)
         c->dirty_lo = lo;
     if (hi > c->dirty_hi)
@@ -276,8 +282,14 @@ void set_row(cmgpu_ctx *c, unsigned s, uint16_t scale, const uint16_t *gain)
         }
         identity = unity;     // trunc(x*d/d) == x and x is already inside the clamp range
     }
-    for (unsigned ch = scale ? c->channels : 0; ch < 16; ch++)
-        r.mul[ch] = 1;
+    // rows the identity kernel skips still carry an exact recipe (g == d == 1), so that they can
+    // ride along in a gain-mode launch when other streams of the tick need one
+    const RecipeHost unity = make_recipe(1, 1);
+    for (unsigned ch = scale ? c->channels : 0; ch < 16; ch++) {
+        r.mw[ch] = unity.mw;
+        r.addm[ch] = unity.addm;
+        r.mul[ch] = unity.mul;
+    }
     bool addall = scale != 0;
     for (unsigned ch = 0; ch < c->channels && addall; ch++)
         addall = r.addm[ch] == 0xffffffffu;
@@ -293,17 +305,9 @@ int gain_mode_of(const GainRow &r)
 
 int rebuild_classes_locked(cmgpu_ctx *c)
 {
-    for (auto &v : c->h_ids)
-        v.clear();
+    c->n_mode[0] = c->n_mode[1] = c->n_mode[2] = 0;
     for (unsigned s = 0; s < c->active; s++)
-        c->h_ids[gain_mode_of(c->h_gains[s])].push_back(s);
-    for (int k = 0; k < 3; k++) {
-        // a group that is the whole contiguous range needs no list on the device
-        if (c->h_ids[k].empty() || c->h_ids[k].size() == c->active)
-            continue;
-        CU(cudaMemcpyAsync(c->d_ids + (size_t)k * c->max_streams, c->h_ids[k].data(),
-                           sizeof(uint32_t) * c->h_ids[k].size(), cudaMemcpyHostToDevice, c->s_cmp));
-    }
+        c->n_mode[gain_mode_of(c->h_gains[s])]++;
     c->classes_dirty = false;
     return CMGPU_OK;
 }
@@ -315,6 +319,21 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags)
         return rc;
     const bool meter = (flags & CMGPU_METER) != 0;
     const bool transform = (flags & CMGPU_TRANSFORM) != 0;
+    if (!c->active)
+        return CMGPU_OK;
+    if (c->classes_dirty && (rc = rebuild_classes_locked(c)))
+        return rc;
+    const bool separate = c->d_out != nullptr;
+    // the cheapest mode that is exact for every active stream
+    int gm = cmgpu::GM_IDENTITY;
+    if (transform && c->n_mode[cmgpu::GM_MASKED])
+        gm = cmgpu::GM_MASKED;
+    else if (transform && c->n_mode[cmgpu::GM_ADDALL])
+        gm = (c->plan_g == 0) ? cmgpu::GM_MASKED : cmgpu::GM_ADDALL;   // generic kernel: masked covers it
+    const bool store = gm != cmgpu::GM_IDENTITY || separate;
+    if (!store && !meter)
+        return CMGPU_OK;                 // in-place pass-through without metering: nothing to do
+
     TickArgs a;
     memset(&a, 0, sizeof(a));
     a.in = c->d_in + (size_t)slot * c->slot_bytes;
@@ -322,44 +341,17 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags)
     a.frames = c->has_frames[slot] ? c->d_frames + (size_t)slot * c->max_streams : nullptr;
     a.gains = c->d_gains;
     a.meters = c->d_meters;
-    a.pos_base = (c->tick_seq << c->pbits) & cmgpu::kKeyPosMask;
+    a.tick = c->d_tick;
+    a.pbits = c->pbits;
+    a.n_streams = c->active;
     a.block_frames = c->block_frames;
     a.stride_bytes = (uint32_t)c->stride;
     a.items_per_block = c->plan_items;
     a.per_item = c->plan_per_item;
     a.row_u64 = c->row_u64;
-    c->tick_seq++;
-    if (!c->active)
-        return CMGPU_OK;
-    const bool separate = c->d_out != nullptr;
-
-    if (!transform) {
-        // every stream passes through untouched
-        if (!meter && !separate)
-            return CMGPU_OK;
-        a.stream_ids = nullptr;
-        a.n_streams = c->active;
-        a.store = separate ? 1u : 0u;
-        CU(launch_tick(c, a, cmgpu::GM_IDENTITY, meter));
-        c->launches++;
-        return CMGPU_OK;
-    }
-    if (c->classes_dirty && (rc = rebuild_classes_locked(c)))
-        return rc;
-    for (int gm = 0; gm < 3; gm++) {
-        const size_t n = c->h_ids[gm].size();
-        if (!n)
-            continue;
-        a.store = (gm != cmgpu::GM_IDENTITY || separate) ? 1u : 0u;
-        if (!a.store && !meter)
-            continue;
-        a.stream_ids = (n == c->active) ? nullptr : c->d_ids + (size_t)gm * c->max_streams;
-        a.n_streams = (uint32_t)n;
-        // the generic kernel folds add-all into the masked recipe
-        const int kgm = (c->plan_g == 0 && gm == cmgpu::GM_ADDALL) ? cmgpu::GM_MASKED : gm;
-        CU(launch_tick(c, a, kgm, meter));
-        c->launches++;
-    }
+    a.store = store ? 1u : 0u;
+    CU(launch_tick(c, a, gm, meter));
+    c->launches++;
     return CMGPU_OK;
 }
 
@@ -497,8 +489,9 @@ cmgpu_ctx_t *cmgpu_ctx_create(int device, unsigned channels, unsigned max_stream
         return bail("cudaMalloc(meters)", e);
     if ((e = cudaMemset(c->d_meters, 0, sizeof(uint64_t) * c->row_u64 * max_streams)) != cudaSuccess)
         return bail("cudaMemset(meters)", e);
-    if ((e = cudaMalloc(&c->d_ids, sizeof(uint32_t) * 3 * (size_t)max_streams)) != cudaSuccess)
-        return bail("cudaMalloc(stream lists)", e);
+    if ((e = cudaMalloc(&c->d_tick, 2 * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMemset(c->d_tick, 0, 2 * sizeof(unsigned long long))) != cudaSuccess)
+        return bail("cudaMalloc(tick)", e);
     if ((e = cudaMalloc(&c->d_frames, sizeof(uint32_t) * (size_t)max_streams * ring_slots)) != cudaSuccess)
         return bail("cudaMalloc(frames)", e);
     if ((e = cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -538,6 +531,7 @@ void cmgpu_ctx_destroy(cmgpu_ctx_t *c)
     for (auto ev : c->ev_up) if (ev) cudaEventDestroy(ev);
     for (auto ev : c->ev_cmp) if (ev) cudaEventDestroy(ev);
     for (auto ev : c->ev_down) if (ev) cudaEventDestroy(ev);
+    if (c->graph) cudaGraphExecDestroy(c->graph);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->s_up) cudaStreamDestroy(c->s_up);
@@ -548,7 +542,7 @@ void cmgpu_ctx_destroy(cmgpu_ctx_t *c)
     cudaFree(c->d_gains);
     cudaFree(c->d_meters);
     cudaFree(c->d_frames);
-    cudaFree(c->d_ids);
+    cudaFree(c->d_tick);
     if (c->h_ring)
         cudaFreeHost(c->h_ring);
     cudaGetLastError();
@@ -575,6 +569,7 @@ int cmgpu_set_active_streams(cmgpu_ctx_t *c, unsigned n)
     std::lock_guard<std::mutex> lk(c->mu);
     c->active = n;
     c->classes_dirty = true;
+    c->config_gen++;
     return CMGPU_OK;
 }
 
@@ -650,6 +645,7 @@ int cmgpu_slot_set_frames(cmgpu_ctx_t *c, unsigned slot, const uint32_t *frames)
     if (!slot_ok(c, slot))
         return fail(c ? CMGPU_ERR_INVAL : CMGPU_ERR_FAULT, "bad context or slot");
     std::lock_guard<std::mutex> lk(c->mu);
+    c->config_gen++;
     if (!frames) {
         c->has_frames[slot] = 0;
         return CMGPU_OK;
@@ -843,6 +839,91 @@ int cmgpu_time_process(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, un
         rc = launch_locked(c, first_slot + r % n_slots, flags);
         if (rc)
             return rc;
+    }
+    CU(cudaEventRecord(c->ev_t1, c->s_cmp));
+    CU(cudaEventSynchronize(c->ev_t1));
+    CU(cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
+    return CMGPU_OK;
+}
+
+static int build_cycle_locked(cmgpu_ctx *c, unsigned first_slot, unsigned n_slots, unsigned flags)
+{
+    if (c->graph && c->graph_gen == c->config_gen && c->graph_first == first_slot && c->graph_n == n_slots &&
+        c->graph_flags == flags)
+        return CMGPU_OK;
+    if (c->graph) {
+        cudaGraphExecDestroy(c->graph);
+        c->graph = nullptr;
+    }
+    // everything a launch may have to upload happens before the capture starts
+    int rc = upload_gains_locked(c);
+    if (rc)
+        return rc;
+    CU(cudaStreamSynchronize(c->s_cmp));
+    const uint64_t before = c->launches;
+    CU(cudaStreamBeginCapture(c->s_cmp, cudaStreamCaptureModeThreadLocal));
+    for (unsigned i = 0; i < n_slots && rc == CMGPU_OK; i++)
+        rc = launch_locked(c, first_slot + i, flags);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c->s_cmp, &g);
+    c->graph_launches = c->launches - before;
+    c->launches = before;                           // capturing is not launching
+    if (rc != CMGPU_OK || e != cudaSuccess) {
+        if (g)
+            cudaGraphDestroy(g);
+        return rc != CMGPU_OK ? rc : fail(CMGPU_ERR_GENERIC, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    }
+    e = cudaGraphInstantiate(&c->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess)
+        return fail(CMGPU_ERR_GENERIC, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    c->graph_first = first_slot;
+    c->graph_n = n_slots;
+    c->graph_flags = flags;
+    c->graph_gen = c->config_gen;
+    return CMGPU_OK;
+}
+
+int cmgpu_process_cycle(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, unsigned flags)
+{
+    if (!c)
+        return fail(CMGPU_ERR_FAULT, "NULL context");
+    if (!n_slots || (uint64_t)first_slot + n_slots > c->slots)
+        return fail(CMGPU_ERR_INVAL, "slot range out of bounds");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    int rc = build_cycle_locked(c, first_slot, n_slots, flags);
+    if (rc)
+        return rc;
+    // order the cycle after the uploads of its slots and before their next download
+    for (unsigned i = 0; i < n_slots; i++) {
+        CU(cudaStreamWaitEvent(c->s_cmp, c->ev_up[first_slot + i], 0));
+        CU(cudaStreamWaitEvent(c->s_cmp, c->ev_down[first_slot + i], 0));
+    }
+    CU(cudaGraphLaunch(c->graph, c->s_cmp));
+    c->launches += c->graph_launches;
+    for (unsigned i = 0; i < n_slots; i++)
+        CU(cudaEventRecord(c->ev_cmp[first_slot + i], c->s_cmp));
+    return CMGPU_OK;
+}
+
+int cmgpu_time_cycles(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, unsigned cycles, unsigned flags, float *ms)
+{
+    if (!c || !ms)
+        return fail(CMGPU_ERR_FAULT, "NULL argument");
+    if (!n_slots || (uint64_t)first_slot + n_slots > c->slots)
+        return fail(CMGPU_ERR_INVAL, "slot range out of bounds");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->s_up));
+    CU(cudaStreamSynchronize(c->s_down));
+    int rc = build_cycle_locked(c, first_slot, n_slots, flags);
+    if (rc)
+        return rc;
+    CU(cudaEventRecord(c->ev_t0, c->s_cmp));
+    for (unsigned r = 0; r < cycles; r++) {
+        CU(cudaGraphLaunch(c->graph, c->s_cmp));
+        c->launches += c->graph_launches;
     }
     CU(cudaEventRecord(c->ev_t1, c->s_cmp));
     CU(cudaEventSynchronize(c->ev_t1));

@@ -23,6 +23,13 @@
 #ifndef CMGPU_MIN_CTAS
 #define CMGPU_MIN_CTAS 3    // resident 256-thread CTAs per SM the fast kernels are compiled for
 #endif
+// 8 and 16 channels keep 8 recipes + 8 64-bit power sums per lane: more registers per thread
+#ifndef CMGPU_UNROLL_WIDE
+#define CMGPU_UNROLL_WIDE 4
+#endif
+#ifndef CMGPU_MIN_CTAS_WIDE
+#define CMGPU_MIN_CTAS_WIDE 2
+#endif
 
 namespace cmgpu {
 
@@ -61,10 +68,10 @@ struct TickArgs {
     const uint8_t *in;          // slot base (device)
     uint8_t *out;               // == in when working in place
     const uint32_t *frames;     // valid frames per stream, or nullptr = block_frames each
-    const uint32_t *stream_ids; // streams this launch covers, or nullptr = 0 .. n_streams-1
     const GainRow *gains;
     unsigned long long *meters;
-    uint64_t pos_base;          // tick sequence number << pbits
+    unsigned long long *tick;   // [0] tick sequence number, [1] CTAs of this launch that are done
+    uint32_t pbits;             // position = tick << pbits | frame
     uint32_t n_streams;
     uint32_t block_frames;
     uint32_t stride_bytes;      // bytes between stream-blocks (multiple of 16)
@@ -95,6 +102,28 @@ __device__ __forceinline__ uint64_t shfl_xor64(unsigned mask, uint64_t v, int of
 __device__ __forceinline__ uint64_t make_key(uint32_t mag, uint64_t pos)
 {
     return mag ? (((uint64_t)mag << kKeyMagShift) | (((~pos) & kKeyPosMask) << 1)) : 0ull;
+}
+
+// The tick sequence number lives on the device so that a launch captured in a CUDA graph still
+// sees a fresh position base at every replay. Every thread reads it on entry; the CTA that
+// finishes last (all CTAs of a launch are co-resident, so by then all have read it) advances it.
+__device__ __forceinline__ uint64_t tick_begin(const TickArgs &a)
+{
+    const unsigned long long t = *reinterpret_cast<const volatile unsigned long long *>(a.tick);
+    return ((uint64_t)t << a.pbits) & kKeyPosMask;
+}
+__device__ __forceinline__ void tick_end(const TickArgs &a)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long done = atomicAdd(a.tick + 1, 1ull);
+        if (done == (unsigned long long)gridDim.x - 1ull) {
+            a.tick[1] = 0ull;
+            __threadfence();
+            atomicAdd(a.tick, 1ull);
+        }
+    }
 }
 
 // One sample through the gain recipe (see GainRow).
@@ -138,6 +167,15 @@ struct Shape {
     static constexpr int kFramesPerVec8 = 8 / kPerLane; // frames per vector when C <= 8
 };
 
+// Per-kernel tuning: vectors per load batch and the resident CTAs per SM ptxas must fit.
+// 8-lane groups only ever walk stream-blocks of <= 64 vectors (<= 8 per lane): short batches,
+// and as many resident groups as possible so that one wave covers all streams of a tick.
+template <int C, int G>
+struct Tune {
+    static constexpr int kUnroll = (G == 8) ? 2 : (C >= 8 ? CMGPU_UNROLL_WIDE : CMGPU_UNROLL);
+    static constexpr int kMinCtas = (G == 8) ? (C >= 8 ? 3 : 4) : (C >= 8 ? CMGPU_MIN_CTAS_WIDE : CMGPU_MIN_CTAS);
+};
+
 template <int C, int GM, bool METER, bool MASKED>
 __device__ __forceinline__ uint4 do_vector(uint4 w, const Recipe (&rc)[Shape<C>::kPerLane], uint32_t radd,
                                            uint32_t (&kmax)[8], uint64_t (&pacc)[Shape<C>::kPerLane], int nvalid)
@@ -172,11 +210,11 @@ __device__ __forceinline__ uint4 do_vector(uint4 w, const Recipe (&rc)[Shape<C>:
 }
 
 template <int C, int G, int GM, bool METER>
-__device__ __forceinline__ void run_item(const TickArgs &a, uint32_t s, uint32_t v0, uint32_t v1,
+__device__ __forceinline__ void run_item(const TickArgs &a, uint64_t pos_base, uint32_t s, uint32_t v0, uint32_t v1,
                                          uint32_t valid_bytes, uint32_t gl, unsigned gmask)
 {
     constexpr int P = Shape<C>::kPerLane;
-    constexpr int UNROLL = CMGPU_UNROLL;
+    constexpr int UNROLL = Tune<C, G>::kUnroll;
     const size_t base = (size_t)s * a.stride_bytes;
     const uint8_t *in = a.in + base;
     uint8_t *out = a.out + base;
@@ -282,7 +320,7 @@ __device__ __forceinline__ void run_item(const TickArgs &a, uint32_t s, uint32_t
         // frame index of slot k of vector v inside the stream-block
         const uint32_t frame = (C <= 8) ? (v * (uint32_t)Shape<C>::kFramesPerVec8 + (uint32_t)(k / P))
                                         : (v >> 1);
-        const uint64_t key = make_key(mag, a.pos_base + frame);
+        const uint64_t key = make_key(mag, pos_base + frame);
         kc[k % P] = max(kc[k % P], key);
     }
 #pragma unroll
@@ -311,7 +349,7 @@ __device__ __forceinline__ void run_item(const TickArgs &a, uint32_t s, uint32_t
         if (key) {
             // the sign of the winning sample: re-read it from where it was written
             const uint64_t pos = (~(key >> 1)) & kKeyPosMask;
-            const uint32_t frame = (uint32_t)(pos - a.pos_base);
+            const uint32_t frame = (uint32_t)(pos - pos_base);
             const volatile int16_t *y = reinterpret_cast<const volatile int16_t *>(out);
             const int yv = y[(size_t)frame * C + ch];
             atomicMax(row + ch, (unsigned long long)(key | (yv < 0 ? 1ull : 0ull)));
@@ -322,10 +360,11 @@ __device__ __forceinline__ void run_item(const TickArgs &a, uint32_t s, uint32_t
 }
 
 // One kernel per (channel shape, group width, gain mode, meter on/off): every work item of a
-// launch runs the same straight-line code. A tick whose streams differ in gain mode is issued as
-// one launch per mode present, each over its own stream list.
+// launch runs the same straight-line code. The host picks the cheapest mode that is exact for
+// every active stream (identity rows carry the unity recipe, add-all rows an all-ones mask), so
+// a tick is always exactly ONE launch.
 template <int C, int G, int GM, bool METER>
-__global__ void __launch_bounds__(256, CMGPU_MIN_CTAS) fused_tick(const __grid_constant__ TickArgs a)
+__global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __grid_constant__ TickArgs a)
 {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gl = threadIdx.x & (G - 1);
@@ -333,11 +372,12 @@ __global__ void __launch_bounds__(256, CMGPU_MIN_CTAS) fused_tick(const __grid_c
     const uint32_t groups_per_cta = 256 / G;
     const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block;
     const uint64_t stride = (uint64_t)gridDim.x * groups_per_cta;
+    const uint64_t pos_base = tick_begin(a);
 
     for (uint64_t item = (uint64_t)blockIdx.x * groups_per_cta + threadIdx.x / G; item < n_items; item += stride) {
         const uint32_t si = (uint32_t)(item / a.items_per_block);
         const uint32_t chunk = (uint32_t)(item - (uint64_t)si * a.items_per_block);
-        const uint32_t s = a.stream_ids ? __ldg(a.stream_ids + si) : si;
+        const uint32_t s = si;
         const uint32_t nfr = a.frames ? min(__ldg(a.frames + s), a.block_frames) : a.block_frames;
         const uint32_t valid_bytes = nfr * (uint32_t)(2 * C);
         const uint32_t nvec = (valid_bytes + 15u) >> 4;
@@ -347,8 +387,9 @@ __global__ void __launch_bounds__(256, CMGPU_MIN_CTAS) fused_tick(const __grid_c
         if (METER && chunk == 0 && gl == 0 && nfr)
             atomicAdd(a.meters + (size_t)s * a.row_u64 + 2 * C, (unsigned long long)nfr);
         if (v0 < v1)
-            run_item<C, G, GM, METER>(a, s, v0, v1, valid_bytes, gl, gmask);
+            run_item<C, G, GM, METER>(a, pos_base, s, v0, v1, valid_bytes, gl, gmask);
     }
+    tick_end(a);
 }
 
 // ---- generic kernel: any channel count 1..16 -------------------------------------------------
@@ -359,8 +400,8 @@ __global__ void __launch_bounds__(256, CMGPU_MIN_CTAS) fused_tick(const __grid_c
 // cross-check of the fast kernels (CMGPU_FORCE_GENERIC).
 
 template <int GM, bool METER>
-__device__ __forceinline__ void run_item_generic(const TickArgs &a, int C, uint32_t s, uint32_t f0, uint32_t f1,
-                                                 uint32_t lane)
+__device__ __forceinline__ void run_item_generic(const TickArgs &a, uint64_t pos_base, int C, uint32_t s, uint32_t f0,
+                                                 uint32_t f1, uint32_t lane)
 {
     const size_t base = (size_t)s * a.stride_bytes;
     const int16_t *in = reinterpret_cast<const int16_t *>(a.in + base);
@@ -411,7 +452,7 @@ __device__ __forceinline__ void run_item_generic(const TickArgs &a, int C, uint3
         if (c < C) {
             const uint32_t mag = kmax[c] >> 16;
             const uint32_t it = 0xffffu - (kmax[c] & 0xffffu);
-            uint64_t k = make_key(mag, a.pos_base + (f0 + lane + 32u * it));
+            uint64_t k = make_key(mag, pos_base + (f0 + lane + 32u * it));
             uint64_t p = pacc[c];
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) {
@@ -429,7 +470,7 @@ __device__ __forceinline__ void run_item_generic(const TickArgs &a, int C, uint3
         unsigned long long *row = a.meters + (size_t)s * a.row_u64;
         if (key) {
             const uint64_t pos = (~(key >> 1)) & kKeyPosMask;
-            const uint32_t frame = (uint32_t)(pos - a.pos_base);
+            const uint32_t frame = (uint32_t)(pos - pos_base);
             const volatile int16_t *y = out;
             const int yv = y[(size_t)frame * C + lane];
             atomicMax(row + lane, (unsigned long long)(key | (yv < 0 ? 1ull : 0ull)));
@@ -446,11 +487,12 @@ __global__ void __launch_bounds__(128) generic_tick(const __grid_constant__ Tick
     const uint32_t warps_per_cta = 128 / 32;
     const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block;
     const uint64_t stride = (uint64_t)gridDim.x * warps_per_cta;
+    const uint64_t pos_base = tick_begin(a);
 
     for (uint64_t item = (uint64_t)blockIdx.x * warps_per_cta + threadIdx.x / 32; item < n_items; item += stride) {
         const uint32_t si = (uint32_t)(item / a.items_per_block);
         const uint32_t chunk = (uint32_t)(item - (uint64_t)si * a.items_per_block);
-        const uint32_t s = a.stream_ids ? __ldg(a.stream_ids + si) : si;
+        const uint32_t s = si;
         const uint32_t nfr = a.frames ? min(__ldg(a.frames + s), a.block_frames) : a.block_frames;
         const uint32_t f0 = chunk * a.per_item;
         const uint32_t f1 = min(f0 + a.per_item, nfr);
@@ -458,8 +500,9 @@ __global__ void __launch_bounds__(128) generic_tick(const __grid_constant__ Tick
         if (METER && chunk == 0 && lane == 0 && nfr)
             atomicAdd(a.meters + (size_t)s * a.row_u64 + 2 * C, (unsigned long long)nfr);
         if (f0 < f1)
-            run_item_generic<GM, METER>(a, C, s, f0, f1, lane);
+            run_item_generic<GM, METER>(a, pos_base, C, s, f0, f1, lane);
     }
+    tick_end(a);
 }
 
 }  // namespace cmgpu

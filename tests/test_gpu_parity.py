@@ -358,3 +358,54 @@ def test_full_size_config2_properties(cm, port):
                 assert int(snap[s].power[c]) == int((yc * yc).sum())
                 assert abs(int(snap[s].channel_peak[c])) == int(np.abs(yc).max())
             assert int(snap[s].frames) == block
+
+
+def test_graph_cycle_equals_individual_ticks(cm, port):
+    """cmgpu_process_cycle replays a ring's ticks as one CUDA graph. Every replay must see a fresh
+    tick number (it lives on the device), otherwise an equal magnitude from a later replay could
+    steal the peak. Same result as issuing the ticks one by one, and as the oracle."""
+    rng = np.random.default_rng(77)
+    channels, n_streams, block, ring, cycles = 1, 301, 320, 5, 3
+    data = make_pcm(rng, "ties", (ring, n_streams, block * channels))
+    # slot 0 opens with +100 everywhere, later slots repeat the magnitude with the other sign
+    data[:, :7, :] = 0
+    data[0, :7, 0] = 100
+    data[1:, :7, 3] = -100
+    scale, gain = make_gains(rng, n_streams, channels)
+    scale[:7] = 0
+    results = []
+    for mode in ("cycle", "single"):
+        with cm.Engine(channels, n_streams, block, ring_slots=ring) as eng:
+            eng.set_gain_table(scale, gain)
+            for slot in range(ring):
+                eng.host_slot(slot)[:, : block * channels] = data[slot]
+                eng.submit(slot)
+            for _ in range(cycles):
+                if mode == "cycle":
+                    eng.process_cycle(0, ring)
+                else:
+                    for slot in range(ring):
+                        eng.process(slot)
+            for slot in range(ring):
+                eng.fetch(slot)
+            eng.sync()
+            outs = [eng.host_slot(slot)[:, : block * channels].copy() for slot in range(ring)]
+            snap = eng.snapshot()
+            results.append((outs, [cm.state_dict(snap[s], channels) for s in range(n_streams)]))
+            assert eng.launch_count() >= ring * cycles
+    # oracle: the in-place ring is transformed again on every cycle
+    meters = None
+    work = data.copy()
+    frames = np.full(n_streams, block, np.uint32)
+    for _ in range(cycles):
+        for slot in range(ring):
+            meters, _ = port.batch(work[slot], frames, channels, scale, gain, meters=meters)
+    for outs, states in results:
+        for slot in range(ring):
+            assert np.array_equal(outs[slot], work[slot])
+        for s in range(n_streams):
+            assert states[s]["frames"] == int(meters[s].frames)
+            assert states[s]["power"][0] == int(meters[s].power[0])
+            assert states[s]["channel_peak"][0] == int(meters[s].channel_peak[0]), f"stream {s}"
+            assert states[s]["global_peak"] == int(meters[s].global_peak)
+    assert all(results[0][1][s]["channel_peak"][0] == 100 for s in range(7))
