@@ -114,7 +114,11 @@ struct cmgpu_ctx {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     std::mutex mu;
 
-    // cached CUDA graph of a cycle of ticks (launch-bound small-buffer regime)
+    // cached CUDA graph of a cycle of ticks (launch-bound small-buffer regime): the ticks are
+    // independent nodes spread over a few side streams, so their latencies overlap
+    std::vector<cudaStream_t> s_fork;
+    cudaEvent_t ev_fork = nullptr;
+    std::vector<cudaEvent_t> ev_join;
     cudaGraphExec_t graph = nullptr;
     unsigned graph_first = 0, graph_n = 0, graph_flags = 0;
     uint64_t graph_launches = 0;                   // kernel nodes in the cached graph
@@ -191,7 +195,7 @@ int resident_ctas(cmgpu_ctx *c, int gm, bool meter)
     return cap;
 }
 
-cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter)
+cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter, cudaStream_t st)
 {
     const uint64_t items = (uint64_t)a.n_streams * a.items_per_block;
     const uint64_t per_cta = c->plan_g ? 256u / (unsigned)c->plan_g : 4u;
@@ -200,9 +204,9 @@ cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter)
     if (grid > cap)
         grid = cap;
     if (c->plan_g == 0)
-        generic_kernel(gm, meter)<<<(unsigned)grid, 128, 0, c->s_cmp>>>(a, (int)c->channels);
+        generic_kernel(gm, meter)<<<(unsigned)grid, 128, 0, st>>>(a, (int)c->channels);
     else
-        pick_fast(c, gm, meter)<<<(unsigned)grid, 256, 0, c->s_cmp>>>(a);
+        pick_fast(c, gm, meter)<<<(unsigned)grid, 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -312,8 +316,13 @@ int rebuild_classes_locked(cmgpu_ctx *c)
     return CMGPU_OK;
 }
 
-int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags)
+// One tick on stream `st`. In a cycle (cmgpu_process_cycle) the ticks run concurrently: each gets
+// its place in the sequence as `tick_offset` and leaves advancing the counter to the cycle's end.
+int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st = nullptr, unsigned tick_offset = 0,
+                  unsigned tick_bump = 1)
 {
+    if (!st)
+        st = c->s_cmp;
     int rc = upload_gains_locked(c);
     if (rc)
         return rc;
@@ -343,6 +352,8 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags)
     a.meters = c->d_meters;
     a.tick = c->d_tick;
     a.pbits = c->pbits;
+    a.tick_offset = tick_offset;
+    a.tick_bump = tick_bump;
     a.n_streams = c->active;
     a.block_frames = c->block_frames;
     a.stride_bytes = (uint32_t)c->stride;
@@ -350,7 +361,7 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags)
     a.per_item = c->plan_per_item;
     a.row_u64 = c->row_u64;
     a.store = store ? 1u : 0u;
-    CU(launch_tick(c, a, gm, meter));
+    CU(launch_tick(c, a, gm, meter, st));
     c->launches++;
     return CMGPU_OK;
 }
@@ -532,6 +543,9 @@ void cmgpu_ctx_destroy(cmgpu_ctx_t *c)
     for (auto ev : c->ev_cmp) if (ev) cudaEventDestroy(ev);
     for (auto ev : c->ev_down) if (ev) cudaEventDestroy(ev);
     if (c->graph) cudaGraphExecDestroy(c->graph);
+    for (auto st : c->s_fork) if (st) cudaStreamDestroy(st);
+    for (auto ev : c->ev_join) if (ev) cudaEventDestroy(ev);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->s_up) cudaStreamDestroy(c->s_up);
@@ -860,18 +874,43 @@ static int build_cycle_locked(cmgpu_ctx *c, unsigned first_slot, unsigned n_slot
     if (rc)
         return rc;
     CU(cudaStreamSynchronize(c->s_cmp));
+    const unsigned kFork = 8;
+    if (c->s_fork.empty()) {
+        c->s_fork.assign(kFork, nullptr);
+        c->ev_join.assign(kFork, nullptr);
+        for (unsigned i = 0; i < kFork; i++) {
+            CU(cudaStreamCreateWithFlags(&c->s_fork[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    }
     const uint64_t before = c->launches;
     CU(cudaStreamBeginCapture(c->s_cmp, cudaStreamCaptureModeThreadLocal));
-    for (unsigned i = 0; i < n_slots && rc == CMGPU_OK; i++)
-        rc = launch_locked(c, first_slot + i, flags);
+    const unsigned lanes = n_slots < kFork ? n_slots : kFork;
+    cudaError_t ce = cudaEventRecord(c->ev_fork, c->s_cmp);
+    for (unsigned i = 0; i < lanes && ce == cudaSuccess; i++)
+        ce = cudaStreamWaitEvent(c->s_fork[i], c->ev_fork, 0);
+    for (unsigned i = 0; i < n_slots && rc == CMGPU_OK && ce == cudaSuccess; i++)
+        rc = launch_locked(c, first_slot + i, flags, c->s_fork[i % lanes], i, 0);
+    for (unsigned i = 0; i < lanes && ce == cudaSuccess; i++) {
+        ce = cudaEventRecord(c->ev_join[i], c->s_fork[i]);
+        if (ce == cudaSuccess)
+            ce = cudaStreamWaitEvent(c->s_cmp, c->ev_join[i], 0);
+    }
+    if (ce == cudaSuccess) {
+        cmgpu::bump_tick<<<1, 32, 0, c->s_cmp>>>(c->d_tick, n_slots);
+        ce = cudaGetLastError();             // (the one-thread bump is not counted as a tick launch)
+    }
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(c->s_cmp, &g);
     c->graph_launches = c->launches - before;
     c->launches = before;                           // capturing is not launching
-    if (rc != CMGPU_OK || e != cudaSuccess) {
+    if (rc != CMGPU_OK || e != cudaSuccess || ce != cudaSuccess) {
         if (g)
             cudaGraphDestroy(g);
-        return rc != CMGPU_OK ? rc : fail(CMGPU_ERR_GENERIC, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        return rc != CMGPU_OK ? rc
+                              : fail(CMGPU_ERR_GENERIC, "capturing the cycle failed: %s",
+                                     cudaGetErrorString(e != cudaSuccess ? e : ce));
     }
     e = cudaGraphInstantiate(&c->graph, g, 0);
     cudaGraphDestroy(g);

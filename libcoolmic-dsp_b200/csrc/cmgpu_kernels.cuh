@@ -23,7 +23,7 @@
 #ifndef CMGPU_MIN_CTAS
 #define CMGPU_MIN_CTAS 3    // resident 256-thread CTAs per SM the fast kernels are compiled for
 #endif
-// 8 and 16 channels keep 8 recipes + 8 64-bit power sums per lane: more registers per thread
+// 4, 8 and 16 channels keep 4-8 recipes + 4-8 64-bit power sums per lane: more registers per thread
 #ifndef CMGPU_UNROLL_WIDE
 #define CMGPU_UNROLL_WIDE 4
 #endif
@@ -71,7 +71,9 @@ struct TickArgs {
     const GainRow *gains;
     unsigned long long *meters;
     unsigned long long *tick;   // [0] tick sequence number, [1] CTAs of this launch that are done
-    uint32_t pbits;             // position = tick << pbits | frame
+    uint32_t pbits;             // position = (tick[0] + tick_offset) << pbits | frame
+    uint32_t tick_offset;       // which tick of a concurrently running cycle this launch is
+    uint32_t tick_bump;         // what the last CTA adds to tick[0] (0: a later launch does it)
     uint32_t n_streams;
     uint32_t block_frames;
     uint32_t stride_bytes;      // bytes between stream-blocks (multiple of 16)
@@ -109,11 +111,14 @@ __device__ __forceinline__ uint64_t make_key(uint32_t mag, uint64_t pos)
 // finishes last (all CTAs of a launch are co-resident, so by then all have read it) advances it.
 __device__ __forceinline__ uint64_t tick_begin(const TickArgs &a)
 {
-    const unsigned long long t = *reinterpret_cast<const volatile unsigned long long *>(a.tick);
+
+    const unsigned long long t = *reinterpret_cast<const volatile unsigned long long *>(a.tick) + a.tick_offset;
     return ((uint64_t)t << a.pbits) & kKeyPosMask;
 }
 __device__ __forceinline__ void tick_end(const TickArgs &a)
 {
+    if (!a.tick_bump)
+        return;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -121,7 +126,7 @@ __device__ __forceinline__ void tick_end(const TickArgs &a)
         if (done == (unsigned long long)gridDim.x - 1ull) {
             a.tick[1] = 0ull;
             __threadfence();
-            atomicAdd(a.tick, 1ull);
+            atomicAdd(a.tick, (unsigned long long)a.tick_bump);
         }
     }
 }
@@ -172,8 +177,8 @@ struct Shape {
 // and as many resident groups as possible so that one wave covers all streams of a tick.
 template <int C, int G>
 struct Tune {
-    static constexpr int kUnroll = (G == 8) ? 2 : (C >= 8 ? CMGPU_UNROLL_WIDE : CMGPU_UNROLL);
-    static constexpr int kMinCtas = (G == 8) ? (C >= 8 ? 3 : 4) : (C >= 8 ? CMGPU_MIN_CTAS_WIDE : CMGPU_MIN_CTAS);
+    static constexpr int kUnroll = (G == 8) ? 2 : (C >= 4 ? CMGPU_UNROLL_WIDE : CMGPU_UNROLL);
+    static constexpr int kMinCtas = (G == 8) ? (C >= 4 ? 3 : 4) : (C >= 4 ? CMGPU_MIN_CTAS_WIDE : CMGPU_MIN_CTAS);
 };
 
 template <int C, int GM, bool METER, bool MASKED>
@@ -209,17 +214,62 @@ __device__ __forceinline__ uint4 do_vector(uint4 w, const Recipe (&rc)[Shape<C>:
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-template <int C, int G, int GM, bool METER>
-__device__ __forceinline__ void run_item(const TickArgs &a, uint64_t pos_base, uint32_t s, uint32_t v0, uint32_t v1,
-                                         uint32_t valid_bytes, uint32_t gl, unsigned gmask)
+// What a lane needs to know about one work item.
+struct Item {
+    const uint8_t *src;      // the lane's first vector of the item
+    uint8_t *dst;
+    uint32_t s;              // stream
+    uint32_t first;          // index of that vector in the stream-block
+    uint32_t n_i;            // how many entirely valid vectors the lane visits
+    uint32_t tail_vec;       // vector straddling the end of the valid frames, if this lane owns it
+    uint32_t tail_step;      // ... its step number in the item
+    int tail_valid;          // ... its number of valid samples (0: the lane owns no such vector)
+    uint32_t count_frames;   // frames to add to the stream's counter (first chunk, lane 0 only)
+};
+
+template <int C, int G>
+__device__ __forceinline__ bool item_setup(const TickArgs &a, uint64_t item, uint64_t n_items, uint32_t gl, Item &it)
+{
+    it.n_i = 0;
+    it.tail_valid = 0;
+    it.count_frames = 0;
+    it.s = 0;
+    it.first = 0;
+    it.tail_vec = it.tail_step = 0;
+    it.src = a.in;
+    it.dst = a.out;
+    if (item >= n_items)
+        return false;
+    const uint32_t s = (uint32_t)(item / a.items_per_block);
+    const uint32_t chunk = (uint32_t)(item - (uint64_t)s * a.items_per_block);
+    const uint32_t nfr = a.frames ? min(__ldg(a.frames + s), a.block_frames) : a.block_frames;
+    const uint32_t valid_bytes = nfr * (uint32_t)(2 * C);
+    const uint32_t nvec = (valid_bytes + 15u) >> 4;
+    const uint32_t v0 = chunk * a.per_item;
+    const uint32_t v1 = min(v0 + a.per_item, nvec);
+    const size_t base = (size_t)s * a.stride_bytes;
+    it.s = s;
+    it.first = v0 + gl;
+    it.src = a.in + base + (size_t)it.first * 16;
+    it.dst = a.out + base + (size_t)it.first * 16;
+    it.count_frames = (chunk == 0 && gl == 0) ? nfr : 0;
+    if (v0 < v1) {
+        const uint32_t vfull = min(v1, valid_bytes >> 4);        // vectors [v0, vfull) are entirely valid
+        it.n_i = it.first < vfull ? (vfull - it.first + (G - 1)) / G : 0;
+        if (vfull < v1 && (vfull << 4) < valid_bytes && ((vfull - v0) % G) == gl) {
+            it.tail_vec = vfull;
+            it.tail_step = (vfull - v0) / G;
+            it.tail_valid = (int)((valid_bytes - (vfull << 4)) >> 1);
+        }
+    }
+    return true;
+}
+
+template <int C, int GM>
+__device__ __forceinline__ void load_recipes(const TickArgs &a, uint32_t s, uint32_t gl,
+                                             Recipe (&rc)[Shape<C>::kPerLane])
 {
     constexpr int P = Shape<C>::kPerLane;
-    constexpr int UNROLL = Tune<C, G>::kUnroll;
-    const size_t base = (size_t)s * a.stride_bytes;
-    const uint8_t *in = a.in + base;
-    uint8_t *out = a.out + base;
-
-    Recipe rc[P];
 #pragma unroll
     for (int c = 0; c < P; c++) {
         rc[c].mw = rc[c].addm = 0;
@@ -237,77 +287,16 @@ __device__ __forceinline__ void run_item(const TickArgs &a, uint64_t pos_base, u
                 rc[c].addm = (int)__ldg(&g->addm[cbase + c]);
         }
     }
+}
 
-    uint32_t kmax[8];
-    uint64_t pacc[P];
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-        kmax[k] = 0;
-#pragma unroll
-    for (int c = 0; c < P; c++)
-        pacc[c] = 0;
-
-    const uint32_t vfull = min(v1, valid_bytes >> 4);     // vectors [v0, vfull) are entirely valid
-    const uint32_t first = v0 + gl;
-    // number of this lane's vectors below vfull
-    const uint32_t n_i = first < vfull ? (vfull - first + (G - 1)) / G : 0;
-    const uint8_t *src = in + (size_t)first * 16;
-    uint8_t *dst = out + (size_t)first * 16;
-    constexpr size_t kStep = (size_t)G * 16;              // bytes between a lane's consecutive vectors
-
-    // Double-buffered batches: a lane requests UNROLL consecutive vectors of its stride
-    // back-to-back (the warp's requests then cover UNROLL*G*16 contiguous bytes at once, which
-    // is what HBM rows like), one whole batch ahead of the batch it is computing on. Two
-    // register sets alternate roles, so nothing is ever copied.
-    uint4 bufA[UNROLL], bufB[UNROLL];
-    const uint32_t nb = n_i / UNROLL;                     // full batches of this lane
-#define CMGPU_LOAD_BATCH(buf, b)                                                        \
-    _Pragma("unroll") for (int u = 0; u < UNROLL; u++)                                  \
-        buf[u] = ld_stream(src + (size_t)((b) * UNROLL + u) * kStep);
-#define CMGPU_DO_BATCH(buf, b)                                                          \
-    _Pragma("unroll") for (int u = 0; u < UNROLL; u++) {                                \
-        const uint32_t iu = (b) * UNROLL + u;                                           \
-        const uint4 o = do_vector<C, GM, METER, false>(buf[u], rc, 0xffffu - iu, kmax, pacc, 8); \
-        if (a.store)                                                                    \
-            st_stream(dst + (size_t)iu * kStep, o);                                     \
-    }
-    if (nb > 0) {
-        CMGPU_LOAD_BATCH(bufA, 0u)
-    }
-    for (uint32_t b = 0; b < nb; b += 2) {
-        if (b + 1 < nb) {
-            CMGPU_LOAD_BATCH(bufB, b + 1)
-        }
-        CMGPU_DO_BATCH(bufA, b)
-        if (b + 2 < nb) {
-            CMGPU_LOAD_BATCH(bufA, b + 2)
-        }
-        if (b + 1 < nb) {
-            CMGPU_DO_BATCH(bufB, b + 1)
-        }
-    }
-#undef CMGPU_LOAD_BATCH
-#undef CMGPU_DO_BATCH
-    for (uint32_t i = nb * UNROLL; i < n_i; i++) {
-        const uint4 w = ld_stream(src + (size_t)i * kStep);
-        const uint4 o = do_vector<C, GM, METER, false>(w, rc, 0xffffu - i, kmax, pacc, 8);
-        if (a.store)
-            st_stream(dst + (size_t)i * kStep, o);
-    }
-    // the one vector that straddles the end of the valid frames, if it lies in this item
-    if (vfull < v1 && (vfull << 4) < valid_bytes && ((vfull - v0) % G) == gl) {
-        const uint32_t it = (vfull - v0) / G;
-        const int nvalid = (int)((valid_bytes - (vfull << 4)) >> 1);
-        uint4 w = ld_stream(in + (size_t)vfull * 16);
-        uint4 o = do_vector<C, GM, METER, true>(w, rc, 0xffffu - it, kmax, pacc, nvalid);
-        if (a.store)
-            st_stream(out + (size_t)vfull * 16, o);
-    }
-
-    if (!METER)
-        return;
-
-    // ---- widen to position keys, fold slots of the same channel, combine lanes -------------
+// Meter epilogue of one item: widen the lane's in-loop keys to position keys, fold slots of the
+// same channel, combine the group's lanes with shuffles, publish one channel per lane.
+template <int C, int G>
+__device__ __forceinline__ void item_publish(const TickArgs &a, const Item &it, uint32_t gl, unsigned gmask,
+                                             const uint32_t (&kmax)[8], uint64_t (&pacc)[Shape<C>::kPerLane])
+{
+    constexpr int P = Shape<C>::kPerLane;
+    const uint64_t pos_base = tick_begin(a);
     uint64_t kc[P];
 #pragma unroll
     for (int c = 0; c < P; c++)
@@ -315,8 +304,8 @@ __device__ __forceinline__ void run_item(const TickArgs &a, uint64_t pos_base, u
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const uint32_t mag = kmax[k] >> 16;
-        const uint32_t it = 0xffffu - (kmax[k] & 0xffffu);
-        const uint32_t v = first + it * G;
+        const uint32_t step = 0xffffu - (kmax[k] & 0xffffu);
+        const uint32_t v = it.first + step * G;
         // frame index of slot k of vector v inside the stream-block
         const uint32_t frame = (C <= 8) ? (v * (uint32_t)Shape<C>::kFramesPerVec8 + (uint32_t)(k / P))
                                         : (v >> 1);
@@ -331,7 +320,6 @@ __device__ __forceinline__ void run_item(const TickArgs &a, uint64_t pos_base, u
             pacc[c] += shfl_xor64(gmask, pacc[c], off);
         }
     }
-
     // lane L publishes one channel: C <= 8 -> channel L; C == 16 -> channel 8*(L&1) + (L>>1)
     uint64_t key = 0, pw = 0;
     const int sel = (C == 16) ? (int)(gl >> 1) : (int)gl;
@@ -345,51 +333,144 @@ __device__ __forceinline__ void run_item(const TickArgs &a, uint64_t pos_base, u
     const int ch = (C == 16) ? (int)((gl & 1u) * 8u + (gl >> 1)) : (int)gl;
     __syncwarp(gmask);       // make the item's stores visible to the lane that re-reads a sample
     if ((int)gl < C) {
-        unsigned long long *row = a.meters + (size_t)s * a.row_u64;
+        unsigned long long *row = a.meters + (size_t)it.s * a.row_u64;
         if (key) {
             // the sign of the winning sample: re-read it from where it was written
             const uint64_t pos = (~(key >> 1)) & kKeyPosMask;
             const uint32_t frame = (uint32_t)(pos - pos_base);
-            const volatile int16_t *y = reinterpret_cast<const volatile int16_t *>(out);
+            const volatile int16_t *y =
+                reinterpret_cast<const volatile int16_t *>(a.out + (size_t)it.s * a.stride_bytes);
             const int yv = y[(size_t)frame * C + ch];
             atomicMax(row + ch, (unsigned long long)(key | (yv < 0 ? 1ull : 0ull)));
         }
         if (pw)
             atomicAdd(row + C + ch, (unsigned long long)pw);
     }
+    if (it.count_frames)
+        atomicAdd(a.meters + (size_t)it.s * a.row_u64 + 2 * C, (unsigned long long)it.count_frames);
 }
 
 // One kernel per (channel shape, group width, gain mode, meter on/off): every work item of a
 // launch runs the same straight-line code. The host picks the cheapest mode that is exact for
 // every active stream (identity rows carry the unity recipe, add-all rows an all-ones mask), so
 // a tick is always exactly ONE launch.
+//
+// Each group walks its items (grid-stride) as a software pipeline:
+//   * inside an item, double-buffered batches: a lane requests UNROLL consecutive vectors of its
+//     stride back-to-back (the warp's requests then cover UNROLL*G*16 contiguous bytes at once,
+//     which is what HBM rows like), one whole batch ahead of the batch it computes on; two
+//     register sets alternate roles, nothing is copied;
+//   * across items, the next item's recipes and first batch are requested BEFORE the current
+//     item's meter epilogue (shuffles, one dependent re-read, atomics), whose latency they hide.
 template <int C, int G, int GM, bool METER>
 __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __grid_constant__ TickArgs a)
 {
+    constexpr int P = Shape<C>::kPerLane;
+    constexpr int UNROLL = Tune<C, G>::kUnroll;
+    constexpr size_t kStep = (size_t)G * 16;              // bytes between a lane's consecutive vectors
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gl = threadIdx.x & (G - 1);
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(uint32_t)(G - 1)));
     const uint32_t groups_per_cta = 256 / G;
     const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block;
     const uint64_t stride = (uint64_t)gridDim.x * groups_per_cta;
-    const uint64_t pos_base = tick_begin(a);
 
-    for (uint64_t item = (uint64_t)blockIdx.x * groups_per_cta + threadIdx.x / G; item < n_items; item += stride) {
-        const uint32_t si = (uint32_t)(item / a.items_per_block);
-        const uint32_t chunk = (uint32_t)(item - (uint64_t)si * a.items_per_block);
-        const uint32_t s = si;
-        const uint32_t nfr = a.frames ? min(__ldg(a.frames + s), a.block_frames) : a.block_frames;
-        const uint32_t valid_bytes = nfr * (uint32_t)(2 * C);
-        const uint32_t nvec = (valid_bytes + 15u) >> 4;
-        const uint32_t v0 = chunk * a.per_item;
-        const uint32_t v1 = min(v0 + a.per_item, nvec);
+    uint32_t kmax[8];
+    uint64_t pacc[P];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        kmax[k] = 0;
+#pragma unroll
+    for (int c = 0; c < P; c++)
+        pacc[c] = 0;
 
-        if (METER && chunk == 0 && gl == 0 && nfr)
-            atomicAdd(a.meters + (size_t)s * a.row_u64 + 2 * C, (unsigned long long)nfr);
-        if (v0 < v1)
-            run_item<C, G, GM, METER>(a, pos_base, s, v0, v1, valid_bytes, gl, gmask);
+    uint4 bufA[UNROLL], bufB[UNROLL];
+#define CMGPU_LOAD_BATCH(buf, it, b)                                                    \
+    _Pragma("unroll") for (int u = 0; u < UNROLL; u++)                                  \
+        buf[u] = ld_stream((it).src + (size_t)((b) * UNROLL + u) * kStep);
+#define CMGPU_DO_BATCH(buf, it, b)                                                      \
+    _Pragma("unroll") for (int u = 0; u < UNROLL; u++) {                                \
+        const uint32_t iu = (b) * UNROLL + u;                                           \
+        const uint4 o = do_vector<C, GM, METER, false>(buf[u], rc, 0xffffu - iu, kmax, pacc, 8); \
+        if (a.store)                                                                    \
+            st_stream((it).dst + (size_t)iu * kStep, o);                                \
     }
+
+    uint64_t item = (uint64_t)blockIdx.x * groups_per_cta + threadIdx.x / G;
+    Item cur;
+    Recipe rc[P];
+    bool have = item_setup<C, G>(a, item, n_items, gl, cur);
+    if (have) {
+        load_recipes<C, GM>(a, cur.s, gl, rc);
+        if (cur.n_i >= (uint32_t)UNROLL) {
+            CMGPU_LOAD_BATCH(bufA, cur, 0u)
+        }
+    }
+    while (have) {
+        const uint32_t nb = cur.n_i / UNROLL;             // full batches of this lane; batch 0 is in flight
+        for (uint32_t b = 0; b < nb; b += 2) {
+            if (b + 1 < nb) {
+                CMGPU_LOAD_BATCH(bufB, cur, b + 1)
+            }
+            CMGPU_DO_BATCH(bufA, cur, b)
+            if (b + 2 < nb) {
+                CMGPU_LOAD_BATCH(bufA, cur, b + 2)
+            }
+            if (b + 1 < nb) {
+                CMGPU_DO_BATCH(bufB, cur, b + 1)
+            }
+        }
+        for (uint32_t i = nb * UNROLL; i < cur.n_i; i++) {
+            const uint4 w = ld_stream(cur.src + (size_t)i * kStep);
+            const uint4 o = do_vector<C, GM, METER, false>(w, rc, 0xffffu - i, kmax, pacc, 8);
+            if (a.store)
+                st_stream(cur.dst + (size_t)i * kStep, o);
+        }
+        if (cur.tail_valid) {
+            // the one vector that straddles the end of the valid frames
+            const size_t off = (size_t)cur.s * a.stride_bytes + (size_t)cur.tail_vec * 16;
+            const uint4 w = ld_stream(a.in + off);
+            const uint4 o = do_vector<C, GM, METER, true>(w, rc, 0xffffu - cur.tail_step, kmax, pacc, cur.tail_valid);
+            if (a.store)
+                st_stream(a.out + off, o);
+        }
+
+        // next item: recipes and first batch go out before this item's epilogue
+        item += stride;
+        Item nxt;
+        Recipe rcn[P];
+        have = item_setup<C, G>(a, item, n_items, gl, nxt);
+        if (have) {
+            load_recipes<C, GM>(a, nxt.s, gl, rcn);
+            if (nxt.n_i >= (uint32_t)UNROLL) {
+                CMGPU_LOAD_BATCH(bufA, nxt, 0u)
+            }
+        }
+        if (METER) {
+            item_publish<C, G>(a, cur, gl, gmask, kmax, pacc);
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                kmax[k] = 0;
+#pragma unroll
+            for (int c = 0; c < P; c++)
+                pacc[c] = 0;
+        }
+        cur = nxt;
+#pragma unroll
+        for (int c = 0; c < P; c++)
+            rc[c] = rcn[c];
+    }
+#undef CMGPU_LOAD_BATCH
+#undef CMGPU_DO_BATCH
     tick_end(a);
+}
+
+// Closes a cycle of concurrently running ticks: advances the tick sequence number once all of
+// them are done (the graph orders it after every tick node).
+__global__ void bump_tick(unsigned long long *tick, unsigned n)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        atomicAdd(tick, (unsigned long long)n);
 }
 
 // ---- generic kernel: any channel count 1..16 -------------------------------------------------
@@ -400,8 +481,8 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
 // cross-check of the fast kernels (CMGPU_FORCE_GENERIC).
 
 template <int GM, bool METER>
-__device__ __forceinline__ void run_item_generic(const TickArgs &a, uint64_t pos_base, int C, uint32_t s, uint32_t f0,
-                                                 uint32_t f1, uint32_t lane)
+__device__ __forceinline__ void run_item_generic(const TickArgs &a, int C, uint32_t s, uint32_t f0, uint32_t f1,
+                                                 uint32_t lane)
 {
     const size_t base = (size_t)s * a.stride_bytes;
     const int16_t *in = reinterpret_cast<const int16_t *>(a.in + base);
@@ -446,6 +527,7 @@ __device__ __forceinline__ void run_item_generic(const TickArgs &a, uint64_t pos
     if (!METER)
         return;
 
+    const uint64_t pos_base = tick_begin(a);
     uint64_t key = 0, pw = 0;
 #pragma unroll
     for (int c = 0; c < 16; c++) {
@@ -487,7 +569,6 @@ __global__ void __launch_bounds__(128) generic_tick(const __grid_constant__ Tick
     const uint32_t warps_per_cta = 128 / 32;
     const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block;
     const uint64_t stride = (uint64_t)gridDim.x * warps_per_cta;
-    const uint64_t pos_base = tick_begin(a);
 
     for (uint64_t item = (uint64_t)blockIdx.x * warps_per_cta + threadIdx.x / 32; item < n_items; item += stride) {
         const uint32_t si = (uint32_t)(item / a.items_per_block);
@@ -500,7 +581,7 @@ __global__ void __launch_bounds__(128) generic_tick(const __grid_constant__ Tick
         if (METER && chunk == 0 && lane == 0 && nfr)
             atomicAdd(a.meters + (size_t)s * a.row_u64 + 2 * C, (unsigned long long)nfr);
         if (f0 < f1)
-            run_item_generic<GM, METER>(a, pos_base, C, s, f0, f1, lane);
+            run_item_generic<GM, METER>(a, C, s, f0, f1, lane);
     }
     tick_end(a);
 }
