@@ -420,11 +420,21 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
                 CMGPU_DO_BATCH(bufB, cur, b + 1)
             }
         }
-        for (uint32_t i = nb * UNROLL; i < cur.n_i; i++) {
-            const uint4 w = ld_stream(cur.src + (size_t)i * kStep);
-            const uint4 o = do_vector<C, GM, METER, false>(w, rc, 0xffffu - i, kmax, pacc, 8);
-            if (a.store)
-                st_stream(cur.dst + (size_t)i * kStep, o);
+        // what is left of the lane's vectors (< UNROLL): requested together, then worked on
+        const uint32_t rem0 = nb * UNROLL;
+        if (rem0 < cur.n_i) {
+#pragma unroll
+            for (int u = 0; u < UNROLL - 1; u++)
+                if (rem0 + u < cur.n_i)
+                    bufB[u] = ld_stream(cur.src + (size_t)(rem0 + u) * kStep);
+#pragma unroll
+            for (int u = 0; u < UNROLL - 1; u++) {
+                if (rem0 + u < cur.n_i) {
+                    const uint4 o = do_vector<C, GM, METER, false>(bufB[u], rc, 0xffffu - (rem0 + u), kmax, pacc, 8);
+                    if (a.store)
+                        st_stream(cur.dst + (size_t)(rem0 + u) * kStep, o);
+                }
+            }
         }
         if (cur.tail_valid) {
             // the one vector that straddles the end of the valid frames
