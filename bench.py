@@ -90,13 +90,20 @@ class ClockSampler:
 
     def __init__(self, device: int):
         self.device = device
-        self.rows = []
+        self.rows = []          # (arrival time, fields)
         self.proc = None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -105,7 +112,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self) -> dict:
         if not self.proc:
@@ -117,7 +124,11 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
-        for r in self.rows:
+        inside = [r for t, r in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.03)]
+        # a timed region shorter than the sampling period: fall back to the samples nearest to it
+        if not inside and self.rows and self.t0 is not None:
+            inside = [r for t, r in sorted(self.rows, key=lambda tr: abs(tr[0] - self.t0))[:2]]
+        for r in inside:
             if len(r) < 9:
                 continue
             try:
@@ -312,12 +323,14 @@ def main():
 
     pflags = {"fused": cm.FUSED, "transform": cm.TRANSFORM, "meter": cm.METER, "copy": 0}[args.mode]
     clocks = ClockSampler(local)
+    clocks.start()
     timed(args.warmup)
     eng.reset_meters()
     launches0 = eng.launch_count()
     barrier()
-    clocks.start()
+    clocks.mark_begin()
     ms_total = timed(args.steps)
+    clocks.mark_end()
     barrier()
     clk = clocks.stop()
     launches = eng.launch_count() - launches0
