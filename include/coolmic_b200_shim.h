@@ -86,6 +86,25 @@ int                coolmic_vumeter_attach_iohandle(coolmic_vumeter_t *self, cool
 ssize_t            coolmic_vumeter_read(coolmic_vumeter_t *self, ssize_t maxlen);
 int                coolmic_vumeter_result(coolmic_vumeter_t *self, coolmic_vumeter_result_t *result);
 
+/* ---- batch mode: the same objects, many streams per GPU tick ---------------
+ * A batch owns one cmgpu context for `channels`-channel streams. Its member transforms are
+ * ordinary coolmic_transform_t objects (attach_iohandle / get_iohandle / set_master_gain work as
+ * usual); coolmic_b200_batch_tick() pulls up to block_frames from every member's input, runs ONE
+ * fused transform+vumeter launch for all members and makes the transformed PCM readable through
+ * the members' handles -- every handle has its own read position, so several consumers can read
+ * one transform without a tee. A batch vumeter is fused with its transform: no handle, no copy.
+ * tick() returns the frames processed (>= 0), COOLMIC_ERROR_BUSY (-12) while some reader has not
+ * consumed the previous tick's output, or another negative COOLMIC_ERROR_* code. */
+typedef struct coolmic_b200_batch coolmic_b200_batch_t;
+coolmic_b200_batch_t *coolmic_b200_batch_new(int device, unsigned int channels, unsigned int max_streams,
+                                             unsigned int block_frames);
+coolmic_transform_t  *coolmic_b200_batch_transform_new(coolmic_b200_batch_t *batch, const char *name,
+                                                       coolmic_b200_ro_t associated, uint_least32_t rate);
+coolmic_vumeter_t    *coolmic_b200_batch_vumeter_new(coolmic_b200_batch_t *batch, coolmic_transform_t *of,
+                                                     const char *name, coolmic_b200_ro_t associated);
+int                   coolmic_b200_batch_tick(coolmic_b200_batch_t *batch);
+size_t                coolmic_b200_batch_pending(coolmic_b200_batch_t *batch);
+
 /* Which CUDA device the objects created from now on use (default 0, or $COOLMIC_B200_DEVICE). */
 int coolmic_b200_set_device(int device);
 /* Kernel launches issued on behalf of shim objects so far (evidence that reads run on the GPU). */

@@ -8,25 +8,8 @@
  */
 #include "shim_internal.h"
 
+#include <stdlib.h>
 #include <string.h>
-
-#define SHIM_BLOCK_BYTES 8192u        /* the most the chain ever asks for at once (tee.c:91-97) */
-
-struct coolmic_transform {
-    shim_base_t base;
-    coolmic_iohandle_t *io;
-    unsigned char carry[2 * COOLMIC_B200_MAX_CHANNELS - 1];
-    size_t carry_fill;
-    uint_least32_t rate;
-    unsigned int channels;
-    /* setting kept on the host so that it survives until the context exists */
-    unsigned int gain_n;
-    uint16_t gain_scale;
-    uint16_t gain[COOLMIC_B200_MAX_CHANNELS];
-    int gain_dirty;
-    cmgpu_ctx_t *ctx;
-    unsigned int block_frames;
-};
 
 static void transform_destroy(void *self)
 {
@@ -34,6 +17,8 @@ static void transform_destroy(void *self)
     shim_unref(t->io);
     if (t->ctx)
         cmgpu_ctx_destroy(t->ctx);
+    if (t->batch)
+        shim_batch_release(t->batch, t->stream);
 }
 
 coolmic_transform_t *coolmic_transform_new(const char *name, coolmic_b200_ro_t associated,
@@ -84,8 +69,10 @@ int coolmic_transform_set_master_gain(coolmic_transform_t *self, unsigned int ch
     } else {
         return COOLMIC_ERROR_INVAL;     /* previous setting stays in force */
     }
-    self->gain_n = self->channels;
     self->gain_dirty = 1;
+    if (self->batch)
+        return shim_batch_set_gain(self->batch, self->stream, self->gain_scale, self->gain) == 0
+                   ? COOLMIC_ERROR_NONE : COOLMIC_ERROR_GENERIC;
     return COOLMIC_ERROR_NONE;
 }
 
@@ -130,9 +117,17 @@ static int transform_process(coolmic_transform_t *t, void *buffer, size_t frames
     return 0;
 }
 
+/* One handle = one reader. In a batch every reader has its own cursor into the stream's output,
+ * which is what makes the handles tee-compatible (tee.c:167-206 keeps one offset per reader). */
+typedef struct transform_reader {
+    coolmic_transform_t *t;
+    void *cursor;
+} transform_reader_t;
+
 static ssize_t transform_read(void *userdata, void *buffer, size_t len)
 {
-    coolmic_transform_t *t = userdata;
+    transform_reader_t *rd = userdata;
+    coolmic_transform_t *t = rd->t;
     const size_t framesize = 2u * t->channels;
     size_t have = 0, rest;
     ssize_t r;
@@ -140,6 +135,8 @@ static ssize_t transform_read(void *userdata, void *buffer, size_t len)
     len -= len % framesize;
     if (!len)
         return 0;
+    if (t->batch)                       /* whole frames the last ticks left for this reader */
+        return shim_batch_read(t->batch, t->stream, rd->cursor, buffer, len);
     if (t->carry_fill) {                /* an unfinished frame from last time goes first */
         memcpy(buffer, t->carry, t->carry_fill);
         have = t->carry_fill;
@@ -161,7 +158,11 @@ static ssize_t transform_read(void *userdata, void *buffer, size_t len)
 
 static int transform_eof(void *userdata)
 {
-    coolmic_transform_t *t = userdata;
+    transform_reader_t *rd = userdata;
+    coolmic_transform_t *t = rd->t;
+    /* like tee.c:208-217: data still waiting for this reader is not EOF */
+    if (t->batch && shim_batch_cursor_unread(t->batch, rd->cursor))
+        return 0;
     if (!t->io)
         return 1;
     return coolmic_iohandle_eof(t->io);
@@ -169,16 +170,32 @@ static int transform_eof(void *userdata)
 
 static int transform_release(void *userdata)
 {
-    return shim_unref(userdata);
+    transform_reader_t *rd = userdata;
+    coolmic_transform_t *t = rd->t;
+    if (t->batch && rd->cursor)
+        shim_batch_cursor_free(t->batch, rd->cursor);
+    free(rd);
+    return shim_unref(t);
 }
 
 coolmic_iohandle_t *coolmic_transform_get_iohandle(coolmic_transform_t *self)
 {
     coolmic_iohandle_t *h;
+    transform_reader_t *rd;
     if (shim_ref(self) != COOLMIC_ERROR_NONE)
         return NULL;
-    h = coolmic_iohandle_new(NULL, NULL, self, transform_release, transform_read, transform_eof);
-    if (!h)
+    rd = calloc(1, sizeof(*rd));
+    if (rd) {
+        rd->t = self;
+        rd->cursor = self->batch ? shim_batch_cursor_new(self->batch, self->stream) : NULL;
+    }
+    h = rd && (!self->batch || rd->cursor)
+            ? coolmic_iohandle_new(NULL, NULL, rd, transform_release, transform_read, transform_eof) : NULL;
+    if (!h) {
+        if (rd && rd->cursor)
+            shim_batch_cursor_free(self->batch, rd->cursor);
+        free(rd);
         shim_unref(self);
+    }
     return h;
 }

@@ -12,24 +12,14 @@
 
 #include <string.h>
 
-#define SHIM_VU_BUFFER (2u * COOLMIC_B200_MAX_CHANNELS * 32u)      /* 1024, vumeter.c:48 */
-
-struct coolmic_vumeter {
-    shim_base_t base;
-    coolmic_iohandle_t *in;
-    uint_least32_t rate;
-    unsigned int channels;
-    unsigned char buffer[SHIM_VU_BUFFER];
-    size_t fill;
-    cmgpu_ctx_t *ctx;
-};
-
 static void vumeter_destroy(void *self)
 {
     coolmic_vumeter_t *v = self;
     shim_unref(v->in);
     if (v->ctx)
         cmgpu_ctx_destroy(v->ctx);
+    if (v->batch)
+        shim_unref(v->batch);
 }
 
 coolmic_vumeter_t *coolmic_vumeter_new(const char *name, coolmic_b200_ro_t associated,
@@ -51,6 +41,8 @@ int coolmic_vumeter_reset(coolmic_vumeter_t *self)
 {
     if (!self)
         return COOLMIC_ERROR_FAULT;
+    if (self->batch)
+        return shim_batch_vumeter_reset(self->batch, self);
     if (self->ctx && cmgpu_meter_reset(self->ctx, 0, 1) != CMGPU_OK)
         return COOLMIC_ERROR_GENERIC;
     return COOLMIC_ERROR_NONE;
@@ -92,6 +84,8 @@ ssize_t coolmic_vumeter_read(coolmic_vumeter_t *self, ssize_t maxlen)
 
     if (!self)
         return -1;
+    if (self->batch)
+        return shim_batch_vumeter_read(self->batch, self, maxlen);
     want = sizeof(self->buffer) - self->fill;
     if (maxlen >= 0 && want > (size_t)maxlen)
         want = (size_t)maxlen;
@@ -127,6 +121,8 @@ int coolmic_vumeter_result(coolmic_vumeter_t *self, coolmic_vumeter_result_t *re
 
     if (!self || !result)
         return COOLMIC_ERROR_FAULT;
+    if (self->batch)
+        return shim_batch_vumeter_result(self->batch, self, result);
     if (!self->ctx)
         return COOLMIC_ERROR_INVAL;     /* nothing metered yet: frames == 0 (vumeter.c:198-199) */
     rc = cmgpu_meter_result(self->ctx, 0, (uint32_t)self->rate, &res);

@@ -2,6 +2,7 @@
  * exactly the way oracle/ref_harness.c drives the reference's objects, so that the same Python
  * test code can run both and compare. Test code only. */
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/types.h>
 
@@ -222,4 +223,94 @@ int shimh_null_checks(void)
         coolmic_b200_unref(v);
     }
     return bad;
+}
+
+/* ---- batch mode: n_streams member transforms with fused meters on one engine --------------- */
+long shimh_batch(const void *in, size_t n_streams, size_t bytes_per_stream, unsigned rate, unsigned channels,
+                 const uint16_t *scale, const uint16_t *gain, size_t src_chunk, unsigned block_frames,
+                 unsigned result_every_ticks, size_t pull, void *out, size_t *out_bytes,
+                 shimh_result_t *results, size_t cap, size_t *n_results, int *fanout_mismatch)
+{
+    coolmic_b200_batch_t *batch = coolmic_b200_batch_new(-1, channels, (unsigned)n_streams, block_frames);
+    memsrc_t *mem = calloc(n_streams, sizeof(*mem));
+    coolmic_transform_t **tr = calloc(n_streams, sizeof(*tr));
+    coolmic_vumeter_t **vu = calloc(n_streams, sizeof(*vu));
+    coolmic_iohandle_t **rd0 = calloc(n_streams, sizeof(*rd0)), **rd1 = calloc(n_streams, sizeof(*rd1));
+    char *scratch = malloc(pull ? pull : 1024), *scratch2 = malloc(pull ? pull : 1024);
+    long ticks = 0;
+    size_t s;
+
+    if (!batch || !mem || !tr || !vu || !rd0 || !rd1)
+        return -1;
+    if (!pull)
+        pull = 1024;
+    *fanout_mismatch = 0;
+    for (s = 0; s < n_streams; s++) {
+        coolmic_iohandle_t *src;
+        mem[s].data = (const char *)in + s * bytes_per_stream;
+        mem[s].len = bytes_per_stream;
+        mem[s].chunk = src_chunk;
+        tr[s] = coolmic_b200_batch_transform_new(batch, "tr", NULL, rate);
+        if (!tr[s])
+            return -2;
+        coolmic_transform_set_master_gain(tr[s], channels, scale[s], gain + s * channels);
+        src = coolmic_iohandle_new("memsrc", NULL, &mem[s], NULL, memsrc_read, memsrc_eof);
+        coolmic_transform_attach_iohandle(tr[s], src);
+        coolmic_b200_unref(src);
+        rd0[s] = coolmic_transform_get_iohandle(tr[s]);       /* "the encoder" */
+        rd1[s] = coolmic_transform_get_iohandle(tr[s]);       /* a second consumer of the same stream */
+        vu[s] = coolmic_b200_batch_vumeter_new(batch, tr[s], "vu", NULL);
+        out_bytes[s] = 0;
+        n_results[s] = 0;
+    }
+    if (coolmic_b200_batch_new(-1, 0, 1, 1) != NULL)
+        return -3;
+    for (;;) {
+        int frames = coolmic_b200_batch_tick(batch);
+        if (frames < 0)
+            return -10 + frames;
+        if (frames == 0)
+            break;
+        ticks++;
+        /* a second tick before the readers caught up must be refused */
+        if (coolmic_b200_batch_tick(batch) != -12)
+            return -4;
+        for (s = 0; s < n_streams; s++) {
+            coolmic_vumeter_result_t res;
+            for (;;) {
+                ssize_t r = coolmic_iohandle_read(rd0[s], scratch, pull);
+                ssize_t r2;
+                if (r <= 0)
+                    break;
+                r2 = coolmic_iohandle_read(rd1[s], scratch2, (size_t)r);
+                if (r2 != r || memcmp(scratch, scratch2, (size_t)r) != 0)
+                    *fanout_mismatch = 1;
+                memcpy((char *)out + s * bytes_per_stream + out_bytes[s], scratch, (size_t)r);
+                out_bytes[s] += (size_t)r;
+            }
+            coolmic_vumeter_read(vu[s], -1);
+            if (result_every_ticks && ticks % result_every_ticks == 0) {
+                int rc = coolmic_vumeter_result(vu[s], &res);
+                if (n_results[s] < cap)
+                    flatten(&results[s * cap + n_results[s]], rc, &res);
+                n_results[s]++;
+            }
+        }
+    }
+    for (s = 0; s < n_streams; s++) {
+        coolmic_vumeter_result_t res;
+        int rc = coolmic_vumeter_result(vu[s], &res);
+        if (n_results[s] < cap)
+            flatten(&results[s * cap + n_results[s]], rc, &res);
+        n_results[s]++;
+        if (coolmic_iohandle_eof(rd0[s]) != 1)
+            *fanout_mismatch |= 2;
+        coolmic_b200_unref(rd0[s]);
+        coolmic_b200_unref(rd1[s]);
+        coolmic_b200_unref(vu[s]);
+        coolmic_b200_unref(tr[s]);
+    }
+    coolmic_b200_unref(batch);
+    free(mem); free(tr); free(vu); free(rd0); free(rd1); free(scratch); free(scratch2);
+    return ticks;
 }

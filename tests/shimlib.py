@@ -41,6 +41,32 @@ class ShimLib:
         L.shimh_chain.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_int, C.c_uint, C.c_uint,
                                   C.POINTER(C.c_uint16), C.c_size_t, C.c_long, C.c_uint, C.POINTER(Result), C.c_size_t]
 
+    def batch(self, pcm2d, channels, scale, gain, rate=48000, src_chunk=0, block_frames=256, result_every_ticks=0,
+              pull=1024, cap=256):
+        """n member transforms + fused meters on one batch engine. Returns (ticks, [out bytes per
+        stream], [[results] per stream], fanout_flags)."""
+        assert pcm2d.dtype == np.uint8 and pcm2d.ndim == 2 and pcm2d.flags.c_contiguous
+        n, nbytes = pcm2d.shape
+        out = np.zeros((n, nbytes), dtype=np.uint8)
+        out_bytes = (C.c_size_t * n)()
+        n_results = (C.c_size_t * n)()
+        res = (Result * (n * cap))()
+        mism = C.c_int(0)
+        keep_s, sp = _u16(scale)
+        keep_g, gp = _u16(gain)
+        fn = self.lib.shimh_batch
+        fn.restype = C.c_long
+        fn.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint, C.c_uint, C.POINTER(C.c_uint16),
+                       C.POINTER(C.c_uint16), C.c_size_t, C.c_uint, C.c_uint, C.c_size_t, C.c_void_p,
+                       C.POINTER(C.c_size_t), C.POINTER(Result), C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
+        ticks = fn(pcm2d.ctypes.data, n, nbytes, rate, channels, sp, gp, src_chunk, block_frames, result_every_ticks,
+                   pull, out.ctypes.data, out_bytes, res, cap, n_results, C.byref(mism))
+        if ticks < 0:
+            raise RuntimeError(f"shim batch harness failed: {ticks}")
+        outs = [out[s, : out_bytes[s]].copy() for s in range(n)]
+        results = [[_res_dict(res[s * cap + i]) for i in range(min(n_results[s], cap))] for s in range(n)]
+        return int(ticks), outs, results, int(mism.value)
+
     def transform(self, pcm, channels, gain=None, rate=48000, src_chunk=0, pull=1024):
         src = _bytes(pcm)
         out = np.zeros(src.size + 64, dtype=np.uint8)

@@ -93,3 +93,37 @@ def test_shim_reads_ran_on_the_gpu(shim, cm):
     before = cm.lib().coolmic_b200_shim_launches()
     shim.chain(np.arange(4000, dtype=np.int16), 2, (1, 3, [2]))
     assert cm.lib().coolmic_b200_shim_launches() > before
+
+
+@pytest.mark.parametrize("channels,block_frames,every,chunk", [(2, 256, 3, 0), (1, 1000, 1, 7), (8, 64, 0, 100),
+                                                             (3, 333, 2, 0), (16, 50, 5, 3)])
+def test_batch_mode_objects(shim, port, channels, block_frames, every, chunk):
+    """member transforms + fused meters of one batch, two readers per stream.
+    PCM must equal the reference transform's output; every result must equal the reference meter
+    run over exactly the frames of its window of ticks."""
+    rng = np.random.default_rng(channels * 1000 + block_frames)
+    n = 13
+    nbytes = 2 * channels * 1500 + 6            # ends inside a frame: the tail is withheld (Appendix B row 16)
+    pcm = rng.integers(0, 256, size=(n, nbytes), dtype=np.uint8)
+    scale = rng.integers(0, 65536, size=n).astype(np.uint16)
+    scale[0] = 0
+    gain = rng.integers(0, 65536, size=(n, channels)).astype(np.uint16)
+    gain[1] = scale[1]
+    ticks, outs, results, flags = shim.batch(pcm, channels, scale, gain, src_chunk=chunk, block_frames=block_frames,
+                                             result_every_ticks=every, pull=1024)
+    assert flags == 0, "second reader saw different bytes, or EOF was not reported"
+    whole = (nbytes // (2 * channels)) * 2 * channels
+    frames_total = whole // (2 * channels)
+    assert ticks == -(-frames_total // block_frames)
+    for s in range(n):
+        want, rc = port.transform(pcm[s], channels, (channels, int(scale[s]), gain[s].tolist()))
+        assert rc == 0 and np.array_equal(outs[s], want), f"stream {s}"
+        # windows: `every` ticks of block_frames frames each (the last one shorter)
+        step = (every or ticks) * block_frames * 2 * channels
+        want_res = []
+        for lo in range(0, whole, step):
+            want_res.append(port.vumeter(want[lo: lo + step], channels)[-1])
+        got = [r for r in results[s] if r.get("rc", 0) == 0]
+        assert len(got) == len(want_res), (len(got), len(want_res))
+        for a, b in zip(got, want_res):
+            assert same_result(a, b), f"stream {s}: {a} != {b}"
