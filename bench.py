@@ -376,9 +376,10 @@ def main():
                 hi = min(streams_per_gpu, lo + 256)
                 synth_block(first_stream + lo, hi - lo, channels, tick_frames, pin_in.array[t, lo:hi], t * tick_frames)
         meter_rows = None
+        gathered = None
 
         def e2e_step():
-            nonlocal meter_rows
+            nonlocal meter_rows, gathered
             for t in range(n_ticks):
                 slot = t % 4
                 eng.submit(slot, pin_in.array[t])
@@ -386,7 +387,7 @@ def main():
                 eng.fetch(slot, pin_out.array[t])
             eng.sync()
             if dist is not None:
-                gather_meters(cm, eng, dist, rank, world)
+                gathered = gather_meters(cm, eng, dist, rank, world)
             meter_rows = eng.snapshot(reset=True)      # D2H of the integer meter state, then reset
 
         for _ in range(2):
@@ -398,9 +399,14 @@ def main():
         barrier()
         wall = max_over_ranks(time.perf_counter() - t0)
         assert int(meter_rows[0].frames) == tick_frames * n_ticks
+        spot = None
+        if rank == 0:
+            spot = spot_check(cm, wl, streams_per_gpu, world, channels, tick_frames, n_ticks, rate, pin_out.array,
+                              meter_rows, gathered)
         slot_bytes = streams_per_gpu * eng.stride
         meter_bytes = streams_per_gpu * eng.meter_row_u64() * 8
-        e2e = {"value": samples_per_step_rank * world * e2e_steps / wall / 1e6, "unit": "Msamples/s",
+        e2e = {"parity_spot_check": spot,
+               "value": samples_per_step_rank * world * e2e_steps / wall / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": n_ticks * slot_bytes, "d2h_bytes_per_step": n_ticks * slot_bytes + meter_bytes,
                "steps": e2e_steps, "ms_per_step": 1e3 * wall / e2e_steps,
                "how": f"{n_ticks} ticks of {tick_frames} frames per step through a 4-slot ring, pinned host buffers, "
@@ -424,6 +430,42 @@ def main():
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def spot_check(cm, wl, streams_per_gpu, world, channels, tick_frames, n_ticks, rate, out0, meter_rows, gathered):
+    """Rank 0 re-derives, with the oracle port, what a few streams of EVERY rank must have produced
+    in the last end-to-end step: transformed PCM (rank 0's own streams) and the integer meter state
+    (all ranks, from the rows that came over NCCL). The oracle is the checker here, nothing it
+    computes is measured or shipped."""
+    from oracle import pyoracle
+    port = pyoracle.port()
+    frames = tick_frames * n_ticks
+    checked = 0
+    for r in range(world):
+        if r == 0:
+            states = meter_rows
+        else:
+            rows = gathered[r].cpu().numpy()
+            states = cm.sharding.decode_rows(cm.lib(), rows, channels)
+        for s in sorted({0, 5, streams_per_gpu // 2, streams_per_gpu - 1}):
+            g = r * streams_per_gpu + s
+            pcm = np.empty((1, frames * channels), dtype=np.int16)
+            for t in range(n_ticks):
+                synth_block(g, 1, channels, tick_frames, pcm[:, t * tick_frames * channels:], t * tick_frames)
+            scale, gain = gain_table(g, 1, channels)
+            meters, _ = port.batch(pcm, np.array([frames], np.uint32), channels, scale, gain)
+            st = states[s]
+            ok = int(st.frames) == frames and int(st.global_peak) == int(meters[0].global_peak)
+            for c in range(channels):
+                ok = ok and int(st.power[c]) == int(meters[0].power[c])
+                ok = ok and int(st.channel_peak[c]) == int(meters[0].channel_peak[c])
+            if r == 0:
+                got = np.concatenate([out0[t, s, : tick_frames * channels] for t in range(n_ticks)])
+                ok = ok and np.array_equal(got, pcm[0])
+            if not ok:
+                return f"MISMATCH rank {r} stream {s}"
+            checked += 1
+    return f"ok: {checked} streams over {world} rank(s) bit-exact vs oracle (PCM on rank 0, meter state on all)"
 
 
 def gather_meters(cm, eng, dist, rank, world):
