@@ -49,6 +49,11 @@ WORKLOADS = {
     "cfg4a": dict(channels=8, streams=4096, rate=48000, frames=96000, ticks=1, ring=1, graph=False,
                   e2e_frames=9600, e2e_ticks=10,
                   desc="4,096 x 48 kHz 8-channel S16 streams x 2 s per GPU, per-channel gain + 8-channel meter (parity mode)"),
+    "cfg4b": dict(channels=8, streams=4096, rate=48000, frames=96000, ticks=1, ring=1, graph=False,
+                  e2e_frames=9600, e2e_ticks=10, mix_out=2, bytes_per_sample=2.5,
+                  desc="EXTENSION, PARITY UNPINNED (the reference has no downmix): 4,096 x 48 kHz 8-channel streams x 2 s "
+                       "per GPU, 8->2 integer downmix + metering of the 8 input and 2 output channels; 16 B read + 4 B "
+                       "written per frame; checked against our own CPU restatement only"),
     "cfg5": dict(channels=2, streams=65536, rate=48000, frames=48000, ticks=1, ring=1, graph=False,
                  e2e_frames=4800, e2e_ticks=10, strong=True,
                  desc="65,536 x 48 kHz stereo S16 streams x 1 s in total, sharded by stream across the GPUs"),
@@ -62,6 +67,17 @@ def gain_table(first_stream: int, n: int, channels: int):
     scale = (1000 + s % 9000).astype(np.uint16)
     gain = (scale[:, None].astype(np.int64) * 3 // 4 + 37 * ((s[:, None] + np.arange(channels)) % 64)).astype(np.uint16)
     return scale, gain
+
+
+def mix_table(first_stream: int, n: int, cin: int, cout: int):
+    """Extension workload: scale as in gain_table, weights around scale/cin (a roughly unity-sum mix
+    with some streams summing above 1.0, i.e. clipping)."""
+    s = np.arange(first_stream, first_stream + n)
+    scale = (1000 + s % 9000).astype(np.uint16)
+    m = np.arange(cout)[None, :, None]
+    c = np.arange(cin)[None, None, :]
+    w = (scale[:, None, None].astype(np.int64) // cin + 11 * ((s[:, None, None] + c + 3 * m) % 32)).astype(np.uint16)
+    return scale, w
 
 
 def synth_block(first_stream: int, n: int, channels: int, frames: int, out: np.ndarray, first_frame: int = 0):
@@ -304,9 +320,20 @@ def main():
 
     # ---- device-resident run: the step's ticks live in a ring of `ring` slots, out of place so
     #      that the input stays pristine across steps
+    mix_out = wl.get("mix_out", 0)
+    bytes_per_sample = wl.get("bytes_per_sample", 4.0)
+
+    def configure(e):
+        if mix_out:
+            mscale, mw = mix_table(first_stream, streams_per_gpu, channels, mix_out)
+            for i in range(streams_per_gpu):
+                assert e.set_mix(i, int(mscale[i]), mw[i]) == 0
+        else:
+            e.set_gain_table(scale, gain)
+
     eng = cm.Engine(channels, streams_per_gpu, frames, ring_slots=ring, device=local,
-                    flags=cm.SEPARATE_OUT | cm.NO_PINNED)
-    eng.set_gain_table(scale, gain)
+                    flags=cm.NO_PINNED | (0 if mix_out else cm.SEPARATE_OUT), out_channels=mix_out)
+    configure(eng)
     chunk = max(1, (256 << 20) // (frames * channels * 2))
     stage = np.zeros((streams_per_gpu, eng.stride // 2), dtype=np.int16)
     for slot in range(ring):
@@ -344,7 +371,7 @@ def main():
     kernel = eng.kernel_name()
     peak, peak_src = measured_peak()
     launches_per_step = max(1, launches // max(args.steps, 1))
-    alg_bytes = 4.0 * samples_per_step_rank / launches_per_step        # per kernel launch
+    alg_bytes = bytes_per_sample * samples_per_step_rank / launches_per_step        # per kernel launch
     ms_launch = ms_step / launches_per_step
     achieved = alg_bytes / (ms_launch * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -367,10 +394,12 @@ def main():
         tick_frames = wl["e2e_frames"]
         n_ticks = wl["e2e_ticks"]
         e2e_steps = args.e2e_steps or min(args.steps, 5)
-        eng = cm.Engine(channels, streams_per_gpu, tick_frames, ring_slots=4, device=local, flags=cm.NO_PINNED)
-        eng.set_gain_table(scale, gain)
+        eng = cm.Engine(channels, streams_per_gpu, tick_frames, ring_slots=4, device=local, flags=cm.NO_PINNED,
+                        out_channels=mix_out)
+        configure(eng)
         shape = (n_ticks, streams_per_gpu, eng.stride // 2)
-        pin_in, pin_out = cm.PinnedArray(shape), cm.PinnedArray(shape)
+        pin_in = cm.PinnedArray(shape)
+        pin_out = cm.PinnedArray((n_ticks, streams_per_gpu, eng.out_stride // 2))
         for t in range(n_ticks):
             for lo in range(0, streams_per_gpu, 256):
                 hi = min(streams_per_gpu, lo + 256)
@@ -404,10 +433,11 @@ def main():
             spot = spot_check(cm, wl, streams_per_gpu, world, channels, tick_frames, n_ticks, rate, pin_out.array,
                               meter_rows, gathered)
         slot_bytes = streams_per_gpu * eng.stride
+        out_slot_bytes = streams_per_gpu * eng.out_stride
         meter_bytes = streams_per_gpu * eng.meter_row_u64() * 8
         e2e = {"parity_spot_check": spot,
                "value": samples_per_step_rank * world * e2e_steps / wall / 1e6, "unit": "Msamples/s",
-               "h2d_bytes_per_step": n_ticks * slot_bytes, "d2h_bytes_per_step": n_ticks * slot_bytes + meter_bytes,
+               "h2d_bytes_per_step": n_ticks * slot_bytes, "d2h_bytes_per_step": n_ticks * out_slot_bytes + meter_bytes,
                "steps": e2e_steps, "ms_per_step": 1e3 * wall / e2e_steps,
                "how": f"{n_ticks} ticks of {tick_frames} frames per step through a 4-slot ring, pinned host buffers, "
                       "upload/compute/download on three CUDA streams, meter snapshot (+ NCCL gather to rank 0 when N>1) per step"}
@@ -415,7 +445,21 @@ def main():
         pin_in.free(); pin_out.free()
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline and mix_out:
+        # no reference implementation exists for the extension: time our own restatement, one thread
+        from oracle import pyoracle
+        port = pyoracle.port()
+        n = min(frames, 96000)
+        pcm = np.empty((1, n * channels), dtype=np.int16)
+        synth_block(0, 1, channels, n, pcm)
+        mscale, mw = mix_table(0, 1, channels, mix_out)
+        t0 = time.perf_counter(); reps = 0
+        while time.perf_counter() - t0 < 5.0:
+            port.mix(pcm[0], n, channels, mix_out, int(mscale[0]), mw[0], pyoracle.Meter(), pyoracle.Meter())
+            reps += 1
+        cpu = {"value": reps * n * channels / (time.perf_counter() - t0) / 1e6, "unit": "Msamples/s", "cores": 1,
+               "kind": "port", "sample": f"1 stream x {n} frames x {reps} passes, our own restatement (no reference exists)"}
+    elif rank == 0 and not args.no_cpu_baseline:
         cpu = cpu_reference_run(channels, rate, frames * ticks, budget_s=12.0)
         cpu.pop("seconds", None)
 
@@ -441,6 +485,25 @@ def spot_check(cm, wl, streams_per_gpu, world, channels, tick_frames, n_ticks, r
     port = pyoracle.port()
     frames = tick_frames * n_ticks
     checked = 0
+    if wl.get("mix_out"):
+        # extension: our own restatement is the only checker there is (parity unpinned)
+        cout = wl["mix_out"]
+        for s in sorted({0, 5, streams_per_gpu // 2, streams_per_gpu - 1}):
+            pcm = np.empty((1, frames * channels), dtype=np.int16)
+            for t in range(n_ticks):
+                synth_block(s, 1, channels, tick_frames, pcm[:, t * tick_frames * channels:], t * tick_frames)
+            mscale, mw = mix_table(s, 1, channels, cout)
+            m_out = pyoracle.Meter()
+            want = port.mix(pcm[0], frames, channels, cout, int(mscale[0]), mw[0], None, m_out)
+            got = np.concatenate([out0[t, s, : tick_frames * cout] for t in range(n_ticks)])
+            st = meter_rows[s]
+            ok = np.array_equal(got, want) and int(st.frames) == frames
+            for c in range(cout):
+                ok = ok and int(st.power[c]) == int(m_out.power[c]) and int(st.channel_peak[c]) == int(m_out.channel_peak[c])
+            if not ok:
+                return f"MISMATCH (extension) stream {s}"
+            checked += 1
+        return f"ok: {checked} streams bit-exact vs our own CPU restatement (extension, parity unpinned)"
     for r in range(world):
         if r == 0:
             states = meter_rows

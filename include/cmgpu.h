@@ -164,6 +164,25 @@ unsigned cmgpu_meter_row_u64(const cmgpu_ctx_t *ctx);
 int      cmgpu_meter_decode(const uint64_t *rows, unsigned count, unsigned channels,
                             cmgpu_meter_state_t *out);
 
+/* ---- EXTENSION: N -> M integer downmix (no counterpart in libcoolmic-dsp; PARITY UNPINNED) ------
+ * BASELINE.json's config 4 names a downmix the reference does not implement.
+ * Specified here in the reference's arithmetic style (transform.c:110-123):
+ *     out[m] = clamp16(trunc(sum_c (int64)x[c] * weights[m][c] / scale))
+ * with the vumeter rules applied to the in_channels input channels AND the out_channels outputs.
+ * Checked only against our own CPU restatement (oracle_mix_process); reported separately. A mix
+ * context is used like any other: cmgpu_submit (input geometry), cmgpu_process (flags ignored),
+ * cmgpu_fetch (output geometry: cmgpu_out_block_stride), cmgpu_meter_* (OUTPUT channels). */
+cmgpu_ctx_t *cmgpu_mix_ctx_create(int device, unsigned in_channels, unsigned out_channels,
+                                  unsigned max_streams, unsigned ring_slots, unsigned block_frames,
+                                  unsigned flags);
+/* weights[out_channels][in_channels], scale 1..65535. */
+int      cmgpu_stream_set_mix(cmgpu_ctx_t *ctx, unsigned stream, uint16_t scale, const uint16_t *weights);
+int      cmgpu_mix_input_snapshot(cmgpu_ctx_t *ctx, unsigned first, unsigned count,
+                                  cmgpu_meter_state_t *out, int reset);   /* INPUT-side meters */
+unsigned cmgpu_out_channels(const cmgpu_ctx_t *ctx);        /* == cmgpu_channels for gain contexts */
+size_t   cmgpu_out_block_stride(const cmgpu_ctx_t *ctx);    /* == cmgpu_block_stride for gain contexts */
+void    *cmgpu_host_out_slot(cmgpu_ctx_t *ctx, unsigned slot); /* == cmgpu_host_slot for gain contexts */
+
 /* ---- measurement ---------------------------------------------------------------- */
 /* Runs `reps` ticks over slots first_slot .. first_slot+n_slots-1 (cyclically) and returns the
  * device time in milliseconds between CUDA events recorded on the compute stream around them. */

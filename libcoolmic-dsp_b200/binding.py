@@ -93,6 +93,12 @@ SYMBOLS = {
     "cmgpu_device_meters": (_P, [_P]),
     "cmgpu_meter_row_u64": (C.c_uint, [_P]),
     "cmgpu_meter_decode": (C.c_int, [C.POINTER(C.c_uint64), C.c_uint, C.c_uint, C.POINTER(MeterState)]),
+    "cmgpu_mix_ctx_create": (_P, [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint]),
+    "cmgpu_stream_set_mix": (C.c_int, [_P, C.c_uint, C.c_uint16, _U16P]),
+    "cmgpu_mix_input_snapshot": (C.c_int, [_P, C.c_uint, C.c_uint, C.POINTER(MeterState), C.c_int]),
+    "cmgpu_out_channels": (C.c_uint, [_P]),
+    "cmgpu_out_block_stride": (C.c_size_t, [_P]),
+    "cmgpu_host_out_slot": (_P, [_P, C.c_uint]),
     "cmgpu_time_process": (C.c_int, [_P, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_float)]),
     "cmgpu_time_cycles": (C.c_int, [_P, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_float)]),
     "cmgpu_launch_count": (C.c_uint64, [_P]),
@@ -137,12 +143,18 @@ class Engine:
     """One cmgpu context: a device ring of [slots][streams][block_frames*channels] S16."""
 
     def __init__(self, channels: int, max_streams: int, block_frames: int, ring_slots: int = 1,
-                 device: int = 0, flags: int = 0):
+                 device: int = 0, flags: int = 0, out_channels: int = 0):
         self.L = lib()
-        self.ctx = self.L.cmgpu_ctx_create(device, channels, max_streams, ring_slots, block_frames, flags)
+        if out_channels:      # EXTENSION: downmix context (parity unpinned)
+            self.ctx = self.L.cmgpu_mix_ctx_create(device, channels, out_channels, max_streams, ring_slots,
+                                                   block_frames, flags)
+        else:
+            self.ctx = self.L.cmgpu_ctx_create(device, channels, max_streams, ring_slots, block_frames, flags)
         if not self.ctx:
             raise CmgpuError(-1, "cmgpu_ctx_create")
         self.channels = channels
+        self.out_channels = out_channels or channels
+        self.out_stride = int(self.L.cmgpu_out_block_stride(self.ctx))
         self.max_streams = max_streams
         self.block_frames = block_frames
         self.ring_slots = ring_slots
@@ -209,6 +221,24 @@ class Engine:
         buf = (C.c_int16 * (self.slot_bytes // 2)).from_address(p)
         return np.frombuffer(buf, dtype=np.int16).reshape(self.max_streams, self.stride // 2)
 
+    def host_out_slot(self, slot: int) -> np.ndarray:
+        p = self.L.cmgpu_host_out_slot(self.ctx, slot)
+        if not p:
+            raise CmgpuError(-9, "cmgpu_host_out_slot")
+        n = self.max_streams * self.out_stride // 2
+        buf = (C.c_int16 * n).from_address(p)
+        return np.frombuffer(buf, dtype=np.int16).reshape(self.max_streams, self.out_stride // 2)
+
+    def set_mix(self, stream: int, scale: int, weights) -> int:
+        w = np.ascontiguousarray(weights, dtype=np.uint16).reshape(self.out_channels, self.channels)
+        return self.L.cmgpu_stream_set_mix(self.ctx, stream, scale, w.ctypes.data_as(_U16P))
+
+    def input_snapshot(self, first: int = 0, count: int | None = None, reset: bool = False):
+        count = self.active - first if count is None else count
+        arr = (MeterState * count)()
+        _check(self.L.cmgpu_mix_input_snapshot(self.ctx, first, count, arr, int(reset)), "cmgpu_mix_input_snapshot")
+        return arr
+
     def submit(self, slot: int, host: np.ndarray | None = None):
         ptr = None if host is None else host.ctypes.data
         if host is not None:
@@ -224,7 +254,7 @@ class Engine:
     def fetch(self, slot: int, host: np.ndarray | None = None):
         ptr = None if host is None else host.ctypes.data
         if host is not None:
-            assert host.nbytes >= self.stride * self.active and host.flags.c_contiguous
+            assert host.nbytes >= self.out_stride * self.active and host.flags.c_contiguous
         _check(self.L.cmgpu_fetch(self.ctx, slot, ptr), "cmgpu_fetch")
 
     def sync(self):
@@ -258,9 +288,9 @@ class Engine:
             return {"rc": rc}
         return res.as_dict()
 
-    def finalise(self, state: MeterState, rate: int) -> dict:
+    def finalise(self, state: MeterState, rate: int, channels: int = 0) -> dict:
         res = Result()
-        rc = self.L.cmgpu_finalise(C.byref(state), rate, self.channels, C.byref(res))
+        rc = self.L.cmgpu_finalise(C.byref(state), rate, channels or self.out_channels, C.byref(res))
         if rc != 0:
             return {"rc": rc}
         return res.as_dict()

@@ -5,6 +5,7 @@
 // that order a slot's submit -> tick -> fetch. No PyTorch, no CPU fallback: every data-path
 // entry point ends in a CUDA call and fails with CMGPU_ERR_GENERIC if that call fails.
 #include "cmgpu_kernels.cuh"
+#include "cmgpu_mix.cuh"
 
 #include "../../include/cmgpu.h"
 
@@ -18,6 +19,8 @@
 #include <vector>
 
 using cmgpu::GainRow;
+using cmgpu::MixArgs;
+using cmgpu::MixRow;
 using cmgpu::TickArgs;
 
 namespace {
@@ -99,6 +102,16 @@ struct cmgpu_ctx {
 
     uint8_t *d_in = nullptr, *d_out = nullptr;     // rings
     uint8_t *h_ring = nullptr;                     // pinned staging ring
+
+    // EXTENSION (downmix contexts only): N -> M mix, separate output geometry, input-side meters
+    unsigned out_channels = 0;                     // 0: ordinary gain context
+    size_t stride_out = 0, slot_bytes_out = 0;
+    uint8_t *h_ring_out = nullptr;
+    MixRow *d_mix = nullptr;
+    std::vector<MixRow> h_mix;
+    bool mix_dirty = false;
+    unsigned long long *d_meters_in = nullptr;
+    unsigned row_in_u64 = 0;
     GainRow *d_gains = nullptr;
     std::vector<GainRow> h_gains;
     std::vector<uint16_t> h_scale, h_gain;         // adapted settings, [stream], [stream][channels]
@@ -330,6 +343,53 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
     const bool transform = (flags & CMGPU_TRANSFORM) != 0;
     if (!c->active)
         return CMGPU_OK;
+    if (c->out_channels) {
+        // EXTENSION: downmix contexts always mix and meter both sides
+        if (c->mix_dirty) {
+            CU(cudaMemcpyAsync(c->d_mix, c->h_mix.data(), sizeof(MixRow) * c->max_streams, cudaMemcpyHostToDevice, st));
+            c->mix_dirty = false;
+        }
+        MixArgs m;
+        memset(&m, 0, sizeof(m));
+        m.in = c->d_in + (size_t)slot * c->slot_bytes;
+        m.out = c->d_out + (size_t)slot * c->slot_bytes_out;
+        m.frames = c->has_frames[slot] ? c->d_frames + (size_t)slot * c->max_streams : nullptr;
+        m.rows = c->d_mix;
+        m.meters_in = c->d_meters_in;
+        m.meters_out = c->d_meters;
+        m.tick = c->d_tick;
+        m.pbits = c->pbits;
+        m.tick_offset = tick_offset;
+        m.tick_bump = tick_bump;
+        m.n_streams = c->active;
+        m.block_frames = c->block_frames;
+        m.stride_in = (uint32_t)c->stride;
+        m.stride_out = (uint32_t)c->stride_out;
+        const uint32_t target = 2048;
+        uint32_t items = (c->block_frames + target - 1) / target;
+        uint32_t per = ((c->block_frames + items - 1) / items + 31u) & ~31u;
+        m.items_per_block = (c->block_frames + per - 1) / per;
+        m.per_item = per;
+        m.cin = c->channels;
+        m.cout = c->out_channels;
+        const bool vec8 = c->channels == 8 && c->out_channels == 2 && !(c->flags & CMGPU_FORCE_GENERIC);
+        const uint64_t n_items = (uint64_t)m.n_streams * m.items_per_block;
+        uint64_t grid = (n_items + 3) / 4;
+        int occ = 0;
+        if ((vec8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cmgpu::mix_tick<true>, 128, 0)
+                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cmgpu::mix_tick<false>, 128, 0)) != cudaSuccess ||
+            occ < 1)
+            occ = 1;
+        if (grid > (uint64_t)occ * c->num_sms)
+            grid = (uint64_t)occ * c->num_sms;
+        if (vec8)
+            cmgpu::mix_tick<true><<<(unsigned)grid, 128, 0, st>>>(m);
+        else
+            cmgpu::mix_tick<false><<<(unsigned)grid, 128, 0, st>>>(m);
+        CU(cudaGetLastError());
+        c->launches++;
+        return CMGPU_OK;
+    }
     if (c->classes_dirty && (rc = rebuild_classes_locked(c)))
         return rc;
     const bool separate = c->d_out != nullptr;
@@ -436,10 +496,11 @@ void cmgpu_host_free(void *p)
         cudaFreeHost(p);
 }
 
-cmgpu_ctx_t *cmgpu_ctx_create(int device, unsigned channels, unsigned max_streams, unsigned ring_slots,
-                              unsigned block_frames, unsigned flags)
+static cmgpu_ctx_t *ctx_create_impl(int device, unsigned channels, unsigned out_channels, unsigned max_streams,
+                                    unsigned ring_slots, unsigned block_frames, unsigned flags)
 {
-    if (!channels || channels > CMGPU_MAX_CHANNELS || !max_streams || !ring_slots || !block_frames) {
+    if (!channels || channels > CMGPU_MAX_CHANNELS || out_channels > CMGPU_MAX_CHANNELS || !max_streams || !ring_slots ||
+        !block_frames) {
         fail(CMGPU_ERR_INVAL, "cmgpu_ctx_create: channels 1..16, streams, slots and block_frames must be non-zero");
         return nullptr;
     }
@@ -469,6 +530,16 @@ cmgpu_ctx_t *cmgpu_ctx_create(int device, unsigned channels, unsigned max_stream
     c->slot_bytes = c->stride * max_streams;
     c->row_u64 = 2 * channels + 2;
     c->pbits = ceil_log2(block_frames) ? ceil_log2(block_frames) : 1;
+    if (out_channels) {
+        // downmix context: the meter table a caller sees is the OUTPUT side's
+        c->out_channels = out_channels;
+        c->stride_out = (size_t)(((uint64_t)block_frames * out_channels * 2u + 15u) & ~15ull);
+        c->slot_bytes_out = c->stride_out * max_streams;
+        c->row_in_u64 = 2 * channels + 2;
+        c->row_u64 = 2 * out_channels + 2;
+        flags &= ~CMGPU_SEPARATE_OUT;
+        c->flags = flags;
+    }
 
     auto bail = [&](const char *what, cudaError_t e) -> cmgpu_ctx_t * {
         fail(e == cudaErrorMemoryAllocation ? CMGPU_ERR_NOMEM : CMGPU_ERR_GENERIC, "cmgpu_ctx_create: %s: %s", what,
@@ -486,10 +557,31 @@ cmgpu_ctx_t *cmgpu_ctx_create(int device, unsigned channels, unsigned max_stream
     const size_t ring = c->slot_bytes * ring_slots;
     if ((e = cudaMalloc(&c->d_in, ring)) != cudaSuccess)
         return bail("cudaMalloc(ring)", e);
-    if ((flags & CMGPU_SEPARATE_OUT) && (e = cudaMalloc(&c->d_out, ring)) != cudaSuccess)
+    const size_t ring_out = out_channels ? c->slot_bytes_out * ring_slots : ring;
+    if (((flags & CMGPU_SEPARATE_OUT) || out_channels) && (e = cudaMalloc(&c->d_out, ring_out)) != cudaSuccess)
         return bail("cudaMalloc(out ring)", e);
-    if ((e = cudaMemset(c->d_in, 0, ring)) != cudaSuccess || (c->d_out && (e = cudaMemset(c->d_out, 0, ring)) != cudaSuccess))
+    if ((e = cudaMemset(c->d_in, 0, ring)) != cudaSuccess ||
+        (c->d_out && (e = cudaMemset(c->d_out, 0, ring_out)) != cudaSuccess))
         return bail("cudaMemset", e);
+    if (out_channels) {
+        if (!(flags & CMGPU_NO_PINNED) && (e = cudaMallocHost(&c->h_ring_out, ring_out)) != cudaSuccess)
+            return bail("cudaMallocHost(out staging)", e);
+        if (c->h_ring_out)
+            memset(c->h_ring_out, 0, ring_out);
+        if ((e = cudaMalloc(&c->d_mix, sizeof(MixRow) * max_streams)) != cudaSuccess ||
+            (e = cudaMemset(c->d_mix, 0, sizeof(MixRow) * max_streams)) != cudaSuccess)
+            return bail("cudaMalloc(mix rows)", e);
+        if ((e = cudaMalloc(&c->d_meters_in, sizeof(uint64_t) * c->row_in_u64 * max_streams)) != cudaSuccess ||
+            (e = cudaMemset(c->d_meters_in, 0, sizeof(uint64_t) * c->row_in_u64 * max_streams)) != cudaSuccess)
+            return bail("cudaMalloc(input meters)", e);
+        c->h_mix.assign(max_streams, MixRow());
+        for (auto &r : c->h_mix) {
+            memset(&r, 0, sizeof(r));
+            r.magic = 0x80000001u;      // scale 1: M = 2^31 + 1, shift 31; all-zero weights = silence
+            r.shift = 31;
+        }
+        c->mix_dirty = true;
+    }
     if (!(flags & CMGPU_NO_PINNED) && (e = cudaMallocHost(&c->h_ring, ring)) != cudaSuccess)
         return bail("cudaMallocHost(staging)", e);
     if (c->h_ring)
@@ -533,6 +625,22 @@ cmgpu_ctx_t *cmgpu_ctx_create(int device, unsigned channels, unsigned max_stream
     return c;
 }
 
+cmgpu_ctx_t *cmgpu_ctx_create(int device, unsigned channels, unsigned max_streams, unsigned ring_slots,
+                              unsigned block_frames, unsigned flags)
+{
+    return ctx_create_impl(device, channels, 0, max_streams, ring_slots, block_frames, flags);
+}
+
+cmgpu_ctx_t *cmgpu_mix_ctx_create(int device, unsigned in_channels, unsigned out_channels, unsigned max_streams,
+                                  unsigned ring_slots, unsigned block_frames, unsigned flags)
+{
+    if (!out_channels) {
+        fail(CMGPU_ERR_INVAL, "cmgpu_mix_ctx_create: out_channels must be 1..16");
+        return nullptr;
+    }
+    return ctx_create_impl(device, in_channels, out_channels, max_streams, ring_slots, block_frames, flags);
+}
+
 void cmgpu_ctx_destroy(cmgpu_ctx_t *c)
 {
     if (!c)
@@ -556,6 +664,10 @@ void cmgpu_ctx_destroy(cmgpu_ctx_t *c)
     cudaFree(c->d_gains);
     cudaFree(c->d_meters);
     cudaFree(c->d_frames);
+    cudaFree(c->d_mix);
+    cudaFree(c->d_meters_in);
+    if (c->h_ring_out)
+        cudaFreeHost(c->h_ring_out);
     cudaFree(c->d_tick);
     if (c->h_ring)
         cudaFreeHost(c->h_ring);
@@ -570,7 +682,14 @@ unsigned cmgpu_block_frames(const cmgpu_ctx_t *c) { return c ? c->block_frames :
 size_t cmgpu_block_stride(const cmgpu_ctx_t *c) { return c ? c->stride : 0; }
 size_t cmgpu_slot_bytes(const cmgpu_ctx_t *c) { return c ? c->slot_bytes : 0; }
 uint64_t cmgpu_launch_count(const cmgpu_ctx_t *c) { return c ? c->launches : 0; }
-const char *cmgpu_kernel_name(const cmgpu_ctx_t *c) { return c ? c->kname : ""; }
+const char *cmgpu_kernel_name(const cmgpu_ctx_t *c)
+{
+    if (!c)
+        return "";
+    if (c->out_channels)
+        return (c->channels == 8 && c->out_channels == 2 && !(c->flags & CMGPU_FORCE_GENERIC)) ? "mix_tick<8->2>" : "mix_tick<generic>";
+    return c->kname;
+}
 unsigned cmgpu_meter_row_u64(const cmgpu_ctx_t *c) { return c ? c->row_u64 : 0; }
 void *cmgpu_device_meters(cmgpu_ctx_t *c) { return c ? c->d_meters : nullptr; }
 
@@ -651,8 +770,20 @@ void *cmgpu_device_slot(cmgpu_ctx_t *c, unsigned slot)
 }
 void *cmgpu_device_out_slot(cmgpu_ctx_t *c, unsigned slot)
 {
-    return slot_ok(c, slot) ? (c->d_out ? c->d_out : c->d_in) + (size_t)slot * c->slot_bytes : nullptr;
+    if (!slot_ok(c, slot))
+        return nullptr;
+    return (c->d_out ? c->d_out : c->d_in) + (size_t)slot * (c->out_channels ? c->slot_bytes_out : c->slot_bytes);
 }
+void *cmgpu_host_out_slot(cmgpu_ctx_t *c, unsigned slot)
+{
+    if (!slot_ok(c, slot))
+        return nullptr;
+    if (c->out_channels)
+        return c->h_ring_out ? c->h_ring_out + (size_t)slot * c->slot_bytes_out : nullptr;
+    return c->h_ring ? c->h_ring + (size_t)slot * c->slot_bytes : nullptr;
+}
+unsigned cmgpu_out_channels(const cmgpu_ctx_t *c) { return c ? (c->out_channels ? c->out_channels : c->channels) : 0; }
+size_t cmgpu_out_block_stride(const cmgpu_ctx_t *c) { return c ? (c->out_channels ? c->stride_out : c->stride) : 0; }
 
 int cmgpu_slot_set_frames(cmgpu_ctx_t *c, unsigned slot, const uint32_t *frames)
 {
@@ -713,15 +844,18 @@ int cmgpu_fetch(cmgpu_ctx_t *c, unsigned slot, void *host)
     if (!slot_ok(c, slot))
         return fail(c ? CMGPU_ERR_INVAL : CMGPU_ERR_FAULT, "bad context or slot");
     std::lock_guard<std::mutex> lk(c->mu);
+    const size_t out_slot = c->out_channels ? c->slot_bytes_out : c->slot_bytes;
+    const size_t out_stride = c->out_channels ? c->stride_out : c->stride;
+    uint8_t *staging = c->out_channels ? c->h_ring_out : c->h_ring;
     if (!host)
-        host = c->h_ring ? c->h_ring + (size_t)slot * c->slot_bytes : nullptr;
+        host = staging ? staging + (size_t)slot * out_slot : nullptr;
     if (!host)
         return fail(CMGPU_ERR_FAULT, "no host buffer and no pinned staging");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamWaitEvent(c->s_down, c->ev_cmp[slot], 0));
     CU(cudaStreamWaitEvent(c->s_down, c->ev_up[slot], 0));
-    const uint8_t *src = (c->d_out ? c->d_out : c->d_in) + (size_t)slot * c->slot_bytes;
-    CU(cudaMemcpyAsync(host, src, c->stride * c->active, cudaMemcpyDeviceToHost, c->s_down));
+    const uint8_t *src = (c->d_out ? c->d_out : c->d_in) + (size_t)slot * out_slot;
+    CU(cudaMemcpyAsync(host, src, out_stride * c->active, cudaMemcpyDeviceToHost, c->s_down));
     CU(cudaEventRecord(c->ev_down[slot], c->s_down));
     return CMGPU_OK;
 }
@@ -778,7 +912,53 @@ int cmgpu_meter_snapshot(cmgpu_ctx_t *c, unsigned first, unsigned count, cmgpu_m
         CU(cudaMemsetAsync(src, 0, n * sizeof(uint64_t), c->s_cmp));
     CU(cudaStreamSynchronize(c->s_cmp));
     for (unsigned i = 0; i < count; i++)
-        decode_row(c->scratch.data() + (size_t)i * c->row_u64, c->channels, out + i);
+        decode_row(c->scratch.data() + (size_t)i * c->row_u64, c->out_channels ? c->out_channels : c->channels, out + i);
+    return CMGPU_OK;
+}
+
+int cmgpu_mix_input_snapshot(cmgpu_ctx_t *c, unsigned first, unsigned count, cmgpu_meter_state_t *out, int reset)
+{
+    if (!c || !out)
+        return fail(CMGPU_ERR_FAULT, "NULL argument");
+    if (!c->out_channels)
+        return fail(CMGPU_ERR_INVAL, "not a downmix context");
+    if ((uint64_t)first + count > c->max_streams)
+        return fail(CMGPU_ERR_INVAL, "stream range out of bounds");
+    if (!count)
+        return CMGPU_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    const size_t n = (size_t)count * c->row_in_u64;
+    c->scratch.resize(n);
+    unsigned long long *src = c->d_meters_in + (size_t)first * c->row_in_u64;
+    CU(cudaMemcpyAsync(c->scratch.data(), src, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->s_cmp));
+    if (reset)
+        CU(cudaMemsetAsync(src, 0, n * sizeof(uint64_t), c->s_cmp));
+    CU(cudaStreamSynchronize(c->s_cmp));
+    for (unsigned i = 0; i < count; i++)
+        decode_row(c->scratch.data() + (size_t)i * c->row_in_u64, c->channels, out + i);
+    return CMGPU_OK;
+}
+
+int cmgpu_stream_set_mix(cmgpu_ctx_t *c, unsigned stream, uint16_t scale, const uint16_t *weights)
+{
+    if (!c || !weights)
+        return fail(CMGPU_ERR_FAULT, "NULL argument");
+    if (!c->out_channels)
+        return fail(CMGPU_ERR_INVAL, "not a downmix context");
+    if (stream >= c->max_streams || !scale)
+        return fail(CMGPU_ERR_INVAL, "stream out of range or scale 0");
+    std::lock_guard<std::mutex> lk(c->mu);
+    MixRow &r = c->h_mix[stream];
+    memset(&r, 0, sizeof(r));
+    for (unsigned m = 0; m < c->out_channels; m++)
+        for (unsigned ch = 0; ch < c->channels; ch++)
+            r.w[m][ch] = weights[(size_t)m * c->channels + ch];
+    const unsigned l = ceil_log2(scale);
+    r.shift = 31 + l;
+    r.magic = (uint32_t)((((uint64_t)1 << r.shift) / scale) + 1);     // < 2^32: 2^(31+l)/scale < 2^32 for scale > 2^(l-1)
+    c->mix_dirty = true;
+    c->config_gen++;
     return CMGPU_OK;
 }
 
@@ -793,6 +973,9 @@ int cmgpu_meter_reset(cmgpu_ctx_t *c, unsigned first, unsigned count)
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     CU(cudaMemsetAsync(c->d_meters + (size_t)first * c->row_u64, 0, sizeof(uint64_t) * c->row_u64 * count, c->s_cmp));
+    if (c->d_meters_in)
+        CU(cudaMemsetAsync(c->d_meters_in + (size_t)first * c->row_in_u64, 0, sizeof(uint64_t) * c->row_in_u64 * count,
+                           c->s_cmp));
     return CMGPU_OK;
 }
 
@@ -829,7 +1012,7 @@ int cmgpu_meter_result(cmgpu_ctx_t *c, unsigned stream, uint32_t rate, cmgpu_res
     int rc = cmgpu_meter_snapshot(c, stream, 1, &st, 0);
     if (rc)
         return rc;
-    rc = cmgpu_finalise(&st, rate, c->channels, out);
+    rc = cmgpu_finalise(&st, rate, c->out_channels ? c->out_channels : c->channels, out);
     if (rc)
         return rc;
     return cmgpu_meter_reset(c, stream, 1);

@@ -109,27 +109,28 @@ __device__ __forceinline__ uint64_t make_key(uint32_t mag, uint64_t pos)
 // The tick sequence number lives on the device so that a launch captured in a CUDA graph still
 // sees a fresh position base at every replay. Every thread reads it on entry; the CTA that
 // finishes last (all CTAs of a launch are co-resident, so by then all have read it) advances it.
-__device__ __forceinline__ uint64_t tick_begin(const TickArgs &a)
+__device__ __forceinline__ uint64_t tick_pos_base(const unsigned long long *tick, uint32_t offset, uint32_t pbits)
 {
-
-    const unsigned long long t = *reinterpret_cast<const volatile unsigned long long *>(a.tick) + a.tick_offset;
-    return ((uint64_t)t << a.pbits) & kKeyPosMask;
+    const unsigned long long t = *reinterpret_cast<const volatile unsigned long long *>(tick) + offset;
+    return ((uint64_t)t << pbits) & kKeyPosMask;
 }
-__device__ __forceinline__ void tick_end(const TickArgs &a)
+__device__ __forceinline__ void tick_finish(unsigned long long *tick, uint32_t bump)
 {
-    if (!a.tick_bump)
+    if (!bump)
         return;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        const unsigned long long done = atomicAdd(a.tick + 1, 1ull);
+        const unsigned long long done = atomicAdd(tick + 1, 1ull);
         if (done == (unsigned long long)gridDim.x - 1ull) {
-            a.tick[1] = 0ull;
+            tick[1] = 0ull;
             __threadfence();
-            atomicAdd(a.tick, (unsigned long long)a.tick_bump);
+            atomicAdd(tick, (unsigned long long)bump);
         }
     }
 }
+__device__ __forceinline__ uint64_t tick_begin(const TickArgs &a) { return tick_pos_base(a.tick, a.tick_offset, a.pbits); }
+__device__ __forceinline__ void tick_end(const TickArgs &a) { tick_finish(a.tick, a.tick_bump); }
 
 // One sample through the gain recipe (see GainRow).
 struct Recipe {

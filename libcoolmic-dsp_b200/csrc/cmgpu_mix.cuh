@@ -1,0 +1,190 @@
+// cmgpu_mix.cuh -- EXTENSION kernel: N -> M integer channel downmix with input and output metering.
+//
+// libcoolmic-dsp has no downmix or remap (transform.c only applies a
+// per-channel gain), but BASELINE.json's config 4 asks for "eight-channel streams with channel
+// remap/downmix to stereo plus per-channel VU metering". This kernel is OUR specification of
+// that operation in the reference's arithmetic style (transform.c:110-123):
+//
+//     out[m] = clamp16( trunc( sum_c (int64)x[c] * w[m][c]  /  scale ) ),   w, scale: uint16
+//
+// metered with the vumeter rules on the CIN input channels and on the COUT output channels.
+// PARITY UNPINNED: there is no reference code to compare with; the checker is our own CPU
+// restatement oracle_mix_process() (oracle/coolmic_oracle.c). Reported separately from the
+// parity-mode numbers (bench.py --workload cfg4b).
+//
+// HBM-bound: 2*CIN bytes read + 2*COUT bytes written per frame (8 -> 2: 20 B per frame).
+#pragma once
+
+#include "cmgpu_kernels.cuh"
+
+namespace cmgpu {
+
+// Per-stream mix recipe (device table row).
+struct MixRow {
+    uint16_t w[16][16];      // w[m][c]
+    uint32_t magic;          // M = floor(2^(31+l) / scale) + 1, l = ceil(log2(scale))
+    uint32_t shift;          // 31 + l
+    uint32_t pad[2];
+};
+static_assert(sizeof(MixRow) == 528, "MixRow layout");
+
+struct MixArgs {
+    const uint8_t *in;            // [stream][frames*CIN] S16, stride_in bytes apart
+    uint8_t *out;                 // [stream][frames*COUT] S16, stride_out bytes apart
+    const uint32_t *frames;
+    const MixRow *rows;
+    unsigned long long *meters_in;    // rows of (2*CIN+2) uint64
+    unsigned long long *meters_out;   // rows of (2*COUT+2) uint64
+    unsigned long long *tick;
+    uint32_t pbits, tick_offset, tick_bump;
+    uint32_t n_streams, block_frames;
+    uint32_t stride_in, stride_out;
+    uint32_t items_per_block, per_item;   // frames per item
+    uint32_t cin, cout;
+};
+
+__device__ __forceinline__ int mix_divide(long long n, uint32_t magic, uint32_t shift)
+{
+    // exact trunc(n / scale) wherever the quotient is inside the clamp range
+    const long long lim = 0x7fffffffll;
+    const long long c = n > lim ? lim : (n < -lim ? -lim : n);
+    const uint32_t a = (uint32_t)(c < 0 ? -c : c);
+    const uint32_t q = (uint32_t)(((unsigned long long)a * magic) >> shift);
+    const int y = c < 0 ? -(int)q : (int)q;
+    return max(min(y, 32767), -32768);
+}
+
+template <int NCH>
+__device__ __forceinline__ void mix_publish(unsigned long long *row, int nch, const volatile int16_t *pcm,
+                                            uint64_t pos_base, uint32_t f0, uint32_t lane,
+                                            const uint32_t (&kmax)[NCH], const uint64_t (&pacc)[NCH])
+{
+    uint64_t key = 0, pw = 0;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+        if (c < nch) {
+            const uint32_t mag = kmax[c] >> 16;
+            const uint32_t it = 0xffffu - (kmax[c] & 0xffffu);
+            uint64_t k = make_key(mag, pos_base + (f0 + lane + 32u * it));
+            uint64_t p = pacc[c];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                k = max(k, shfl_xor64(0xffffffffu, k, off));
+                p += shfl_xor64(0xffffffffu, p, off);
+            }
+            if ((int)lane == c) {
+                key = k;
+                pw = p;
+            }
+        }
+    }
+    if ((int)lane < nch) {
+        if (key) {
+            const uint64_t pos = (~(key >> 1)) & kKeyPosMask;
+            const uint32_t frame = (uint32_t)(pos - pos_base);
+            const int yv = pcm[(size_t)frame * nch + lane];
+            atomicMax(row + lane, (unsigned long long)(key | (yv < 0 ? 1ull : 0ull)));
+        }
+        if (pw)
+            atomicAdd(row + nch + lane, (unsigned long long)pw);
+    }
+}
+
+// One warp per (stream, chunk of frames), lane = frame. VEC8: CIN == 8 (a frame is one 16-byte
+// vector) and COUT == 2 (a frame's output is one 32-bit word) -- the config-4b shape.
+template <bool VEC8>
+__global__ void __launch_bounds__(128) mix_tick(const __grid_constant__ MixArgs a)
+{
+    __shared__ uint16_t s_w[4][16 * 16];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = threadIdx.x >> 5;
+    const int cin = VEC8 ? 8 : (int)a.cin;
+    const int cout = VEC8 ? 2 : (int)a.cout;
+    const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block;
+    const uint64_t stride = (uint64_t)gridDim.x * 4u;
+
+    for (uint64_t item = (uint64_t)blockIdx.x * 4u + warp; item < n_items; item += stride) {
+        const uint32_t s = (uint32_t)(item / a.items_per_block);
+        const uint32_t chunk = (uint32_t)(item - (uint64_t)s * a.items_per_block);
+        const uint32_t nfr = a.frames ? min(__ldg(a.frames + s), a.block_frames) : a.block_frames;
+        const uint32_t f0 = chunk * a.per_item;
+        const uint32_t f1 = min(f0 + a.per_item, nfr);
+        if (chunk == 0 && lane == 0 && nfr) {
+            atomicAdd(a.meters_in + (size_t)s * (2 * cin + 2) + 2 * cin, (unsigned long long)nfr);
+            atomicAdd(a.meters_out + (size_t)s * (2 * cout + 2) + 2 * cout, (unsigned long long)nfr);
+        }
+        if (f0 >= f1)
+            continue;
+
+        const MixRow *row = a.rows + s;
+        __syncwarp();
+        for (int i = (int)lane; i < 256; i += 32)
+            s_w[warp][i] = __ldg(&row->w[0][0] + i);
+        const uint32_t magic = __ldg(&row->magic), shift = __ldg(&row->shift);
+        __syncwarp();
+
+        const int16_t *in = reinterpret_cast<const int16_t *>(a.in + (size_t)s * a.stride_in);
+        int16_t *out = reinterpret_cast<int16_t *>(a.out + (size_t)s * a.stride_out);
+        uint32_t kin[16], kout[16];
+        uint64_t pin[16], pout[16];
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            kin[c] = kout[c] = 0;
+            pin[c] = pout[c] = 0;
+        }
+
+        uint32_t i = 0;
+        for (uint32_t f = f0 + lane; f < f1; f += 32, i++) {
+            const uint32_t radd = 0xffffu - i;
+            int x[16];
+            if (VEC8) {
+                const uint4 w = ld_stream(reinterpret_cast<const uint8_t *>(in + (size_t)f * 8));
+                const uint32_t v[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    x[2 * j] = (int)(short)(v[j] & 0xffffu);
+                    x[2 * j + 1] = (int)v[j] >> 16;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 16; c++)
+                    x[c] = c < cin ? (int)in[(size_t)f * cin + c] : 0;
+            }
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                if (c < cin) {
+                    const uint32_t m = (uint32_t)abs(x[c]);
+                    kin[c] = max(kin[c], (m << 16) + radd);
+                    pin[c] += (uint64_t)((int64_t)x[c] * x[c]);
+                }
+            }
+            int y[16];
+#pragma unroll
+            for (int m = 0; m < 16; m++) {
+                if (m < cout) {
+                    long long n = 0;
+#pragma unroll
+                    for (int c = 0; c < 16; c++)
+                        if (c < cin)
+                            n += (long long)x[c] * (int)s_w[warp][m * 16 + c];
+                    y[m] = mix_divide(n, magic, shift);
+                    const uint32_t mg = (uint32_t)abs(y[m]);
+                    kout[m] = max(kout[m], (mg << 16) + radd);
+                    pout[m] += (uint64_t)((int64_t)y[m] * y[m]);
+                    if (!VEC8)
+                        out[(size_t)f * cout + m] = (int16_t)y[m];
+                }
+            }
+            if (VEC8)
+                reinterpret_cast<uint32_t *>(out)[f] = ((uint32_t)y[0] & 0xffffu) | ((uint32_t)y[1] << 16);
+        }
+
+        const uint64_t pos_base = tick_pos_base(a.tick, a.tick_offset, a.pbits);
+        __syncwarp();
+        mix_publish<16>(a.meters_in + (size_t)s * (2 * cin + 2), cin, in, pos_base, f0, lane, kin, pin);
+        mix_publish<16>(a.meters_out + (size_t)s * (2 * cout + 2), cout, out, pos_base, f0, lane, kout, pout);
+    }
+    tick_finish(a.tick, a.tick_bump);
+}
+
+}  // namespace cmgpu

@@ -339,6 +339,32 @@ void oracle_batch(int16_t *pcm, size_t n_streams, size_t stride_samples, const u
     }
 }
 
+/* EXTENSION CHECKER: see coolmic_oracle.h. No reference lines to cite for the mix itself. */
+void oracle_mix_process(const int16_t *in, size_t frames, unsigned cin, unsigned cout, uint16_t scale,
+                        const uint16_t *w, int16_t *out, oracle_meter_t *min, oracle_meter_t *mout)
+{
+    size_t f;
+    unsigned m, c;
+
+    for (f = 0; f < frames; f++) {
+        for (m = 0; m < cout; m++) {
+            int64_t acc = 0;
+            for (c = 0; c < cin; c++)
+                acc += (int64_t)in[f * cin + c] * (int64_t)w[m * cin + c];
+            acc = acc / (int64_t)scale;
+            if (acc > 32767)
+                acc = 32767;
+            if (acc < -32768)
+                acc = -32768;
+            out[f * cout + m] = (int16_t)acc;
+        }
+    }
+    if (min)
+        oracle_meter_accumulate(min, in, frames, cin);
+    if (mout)
+        oracle_meter_accumulate(mout, out, frames, cout);
+}
+
 typedef struct batch_arg {
     int16_t *pcm;
     size_t begin, end, stride;

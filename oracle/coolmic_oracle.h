@@ -113,6 +113,14 @@ void oracle_batch(int16_t *pcm, size_t n_streams, size_t stride_samples, const u
                   unsigned channels, const uint16_t *scale, const uint16_t *gain,
                   oracle_meter_t *meters);
 
+/* EXTENSION CHECKER (parity unpinned: the reference has no downmix).
+ * Restates include/cmgpu.h's specification of the N -> M mix in the reference's arithmetic style
+ * (transform.c:110-123: int64 product, C division truncating toward zero, saturation):
+ *   out[f][m] = clamp16(trunc(sum_c (int64)in[f][c] * w[m][c] / scale)),  w: [cout][cin] uint16.
+ * Meters (vumeter.c:161-177 rules) accumulate onto *min (inputs) and *mout (outputs) if given. */
+void oracle_mix_process(const int16_t *in, size_t frames, unsigned cin, unsigned cout, uint16_t scale,
+                        const uint16_t *w, int16_t *out, oracle_meter_t *min, oracle_meter_t *mout);
+
 /* Multi-threaded form of oracle_batch for bench.py's cpu_baseline ("port"); returns seconds. */
 double oracle_batch_threads(int16_t *pcm, size_t n_streams, size_t stride_samples, const uint32_t *frames,
                             unsigned channels, const uint16_t *scale, const uint16_t *gain,

@@ -222,6 +222,9 @@ class PortLib(_Lib):
         L.oracle_gain_adapt.restype = C.c_int
         L.oracle_gain_adapt.argtypes = [C.c_uint, C.c_uint, C.c_uint16, C.POINTER(C.c_uint16),
                                         C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)]
+        L.oracle_mix_process.restype = None
+        L.oracle_mix_process.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_uint, C.c_uint16, C.POINTER(C.c_uint16),
+                                         C.c_void_p, C.POINTER(Meter), C.POINTER(Meter)]
         L.oracle_fnv1a64.restype = C.c_uint64
         L.oracle_fnv1a64.argtypes = [C.c_void_p, C.c_size_t]
 
@@ -273,6 +276,16 @@ class PortLib(_Lib):
             return meters, sec
         self.lib.oracle_batch(pcm2d.ctypes.data, n_streams, stride, frp, channels, sp, gp, meters)
         return meters, None
+
+    def mix(self, pcm: np.ndarray, frames: int, cin: int, cout: int, scale: int, weights, meter_in=None, meter_out=None):
+        """EXTENSION checker (parity unpinned): N -> M downmix of one stream; returns int16 [frames*cout]."""
+        src = np.ascontiguousarray(pcm, dtype=np.int16)
+        out = np.zeros(frames * cout, dtype=np.int16)
+        keep, wp = _u16(np.asarray(weights).reshape(-1))
+        self.lib.oracle_mix_process(src.ctypes.data, frames, cin, cout, scale, wp, out.ctypes.data,
+                                    C.byref(meter_in) if meter_in is not None else None,
+                                    C.byref(meter_out) if meter_out is not None else None)
+        return out
 
     def finalise(self, meter: Meter, rate: int, channels: int) -> dict:
         res = Result()
