@@ -139,18 +139,30 @@ struct Recipe {
     int mul;
 };
 
+// Returns the UNSATURATED result; callers saturate (cvt.pack.sat in the fast kernels).
 template <int GM>
-__device__ __forceinline__ int apply_gain(int x, const Recipe &r)
+__device__ __forceinline__ int apply_gain_raw(int x, const Recipe &r)
 {
     if (GM == GM_IDENTITY)
         return x;
     const int X = x * r.mul;
-    int y;
     if (GM == GM_ADDALL)
-        y = __mulhi(X, r.mw) + (X + (int)((unsigned)X >> 31));      // IMAD.HI with addend, LEA.HI
-    else
-        y = __mulhi(X, r.mw) + (X & r.addm) + (int)((unsigned)X >> 31);
-    return max(min(y, 32767), -32768);
+        return __mulhi(X, r.mw) + (X + (int)((unsigned)X >> 31));      // IMAD.HI with addend, LEA.HI
+    return __mulhi(X, r.mw) + (X & r.addm) + (int)((unsigned)X >> 31);
+}
+
+template <int GM>
+__device__ __forceinline__ int apply_gain(int x, const Recipe &r)
+{
+    return max(min(apply_gain_raw<GM>(x, r), 32767), -32768);
+}
+
+// Two 32-bit results -> one word of two saturated int16 (I2IP.S16.S32.SAT: clamp and pack at once).
+__device__ __forceinline__ uint32_t pack_sat16(int hi, int lo)
+{
+    uint32_t r;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(r) : "r"(hi), "r"(lo));
+    return r;
 }
 
 // ---- fast kernels: channel counts that divide (or are a multiple of) one 16-byte vector -----
@@ -180,9 +192,13 @@ template <int C, int G>
 struct Tune {
     static constexpr int kUnroll = (G == 8) ? 2 : (C >= 4 ? CMGPU_UNROLL_WIDE : CMGPU_UNROLL);
     static constexpr int kMinCtas = (G == 8) ? (C >= 4 ? 3 : 4) : (C >= 4 ? CMGPU_MIN_CTAS_WIDE : CMGPU_MIN_CTAS);
+    static constexpr bool kSatPack = (G == 8) || (C >= 4);
 };
 
-template <int C, int GM, bool METER, bool MASKED>
+// SATPACK: saturate and pack two results with one I2IP and meter what was packed (one ALU
+// instruction per sample less; needs a few more live registers, so only the 128-register and the
+// 8-lane kernels use it -- in the 80-register stereo kernel it spills and loses 8 %).
+template <int C, int GM, bool METER, bool MASKED, bool SATPACK>
 __device__ __forceinline__ uint4 do_vector(uint4 w, const Recipe (&rc)[Shape<C>::kPerLane], uint32_t radd,
                                            uint32_t (&kmax)[8], uint64_t (&pacc)[Shape<C>::kPerLane], int nvalid)
 {
@@ -192,15 +208,39 @@ __device__ __forceinline__ uint4 do_vector(uint4 w, const Recipe (&rc)[Shape<C>:
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const int k0 = 2 * j, k1 = 2 * j + 1;
-        int x0 = (int)(short)(in[j] & 0xffffu);
-        int x1 = (int)in[j] >> 16;
-        int y0 = apply_gain<GM>(x0, rc[k0 % P]);
-        int y1 = apply_gain<GM>(x1, rc[k1 % P]);
-        int m0 = y0, m1 = y1;
+        const int x0 = (int)(short)(in[j] & 0xffffu);
+        const int x1 = (int)in[j] >> 16;
+        int m0, m1;
+        if (GM == GM_IDENTITY) {
+            o[j] = in[j];
+            m0 = x0;
+            m1 = x1;
+        } else if (!SATPACK) {
+            int y0 = apply_gain<GM>(x0, rc[k0 % P]);
+            int y1 = apply_gain<GM>(x1, rc[k1 % P]);
+            if (MASKED) {
+                if (k0 >= nvalid) y0 = x0;
+                if (k1 >= nvalid) y1 = x1;
+            }
+            o[j] = ((uint32_t)y0 & 0xffffu) | ((uint32_t)y1 << 16);
+            m0 = y0;
+            m1 = y1;
+        } else {
+            int r0 = apply_gain_raw<GM>(x0, rc[k0 % P]);
+            int r1 = apply_gain_raw<GM>(x1, rc[k1 % P]);
+            if (MASKED) {
+                // samples past the valid frames pass through untouched
+                if (k0 >= nvalid) r0 = x0;
+                if (k1 >= nvalid) r1 = x1;
+            }
+            o[j] = pack_sat16(r1, r0);                      // saturate both, pack: one instruction
+            m0 = (int)(short)(o[j] & 0xffffu);              // what was actually written, for the meter
+            m1 = (int)o[j] >> 16;
+        }
         if (MASKED) {
-            // samples past the valid frames: pass through, invisible to the meter
-            if (k0 >= nvalid) { y0 = x0; m0 = 0; }
-            if (k1 >= nvalid) { y1 = x1; m1 = 0; }
+            // ... and are invisible to the meter
+            if (k0 >= nvalid) m0 = 0;
+            if (k1 >= nvalid) m1 = 0;
         }
         if (METER) {
             const uint32_t a0 = (uint32_t)abs(m0), a1 = (uint32_t)abs(m1);
@@ -210,7 +250,6 @@ __device__ __forceinline__ uint4 do_vector(uint4 w, const Recipe (&rc)[Shape<C>:
             pacc[k0 % P] += (uint64_t)((int64_t)m0 * (int64_t)m0);
             pacc[k1 % P] += (uint64_t)((int64_t)m1 * (int64_t)m1);
         }
-        o[j] = ((uint32_t)y0 & 0xffffu) | ((uint32_t)y1 << 16);
     }
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
@@ -392,7 +431,7 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
 #define CMGPU_DO_BATCH(buf, it, b)                                                      \
     _Pragma("unroll") for (int u = 0; u < UNROLL; u++) {                                \
         const uint32_t iu = (b) * UNROLL + u;                                           \
-        const uint4 o = do_vector<C, GM, METER, false>(buf[u], rc, 0xffffu - iu, kmax, pacc, 8); \
+        const uint4 o = do_vector<C, GM, METER, false, Tune<C, G>::kSatPack>(buf[u], rc, 0xffffu - iu, kmax, pacc, 8); \
         if (a.store)                                                                    \
             st_stream((it).dst + (size_t)iu * kStep, o);                                \
     }
@@ -431,7 +470,7 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
 #pragma unroll
             for (int u = 0; u < UNROLL - 1; u++) {
                 if (rem0 + u < cur.n_i) {
-                    const uint4 o = do_vector<C, GM, METER, false>(bufB[u], rc, 0xffffu - (rem0 + u), kmax, pacc, 8);
+                    const uint4 o = do_vector<C, GM, METER, false, Tune<C, G>::kSatPack>(bufB[u], rc, 0xffffu - (rem0 + u), kmax, pacc, 8);
                     if (a.store)
                         st_stream(cur.dst + (size_t)(rem0 + u) * kStep, o);
                 }
@@ -441,7 +480,7 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
             // the one vector that straddles the end of the valid frames
             const size_t off = (size_t)cur.s * a.stride_bytes + (size_t)cur.tail_vec * 16;
             const uint4 w = ld_stream(a.in + off);
-            const uint4 o = do_vector<C, GM, METER, true>(w, rc, 0xffffu - cur.tail_step, kmax, pacc, cur.tail_valid);
+            const uint4 o = do_vector<C, GM, METER, true, Tune<C, G>::kSatPack>(w, rc, 0xffffu - cur.tail_step, kmax, pacc, cur.tail_valid);
             if (a.store)
                 st_stream(a.out + off, o);
         }
