@@ -48,11 +48,15 @@ extern "C" {
                                       (the reference works in place, transform.c:120) */
 #define CMGPU_NO_PINNED      0x2u  /* do not allocate the pinned host staging rings */
 #define CMGPU_FORCE_GENERIC  0x4u  /* always use the any-channel-count kernel (test hook) */
+#define CMGPU_PLANAR_F32     0x8u  /* also keep a ring of de-interleaved float planes (see CMGPU_PLANAR) */
 
 /* cmgpu_process flags */
 #define CMGPU_TRANSFORM      0x1u  /* apply the gain tables (else pass PCM through untouched) */
 #define CMGPU_METER          0x2u  /* accumulate the meters over what the slot holds afterwards */
 #define CMGPU_FUSED          (CMGPU_TRANSFORM | CMGPU_METER)
+#define CMGPU_PLANAR         0x4u  /* second output of the same pass: per channel a plane of
+                                      sample / 32768.f floats, what enc_vorbis.c:108-117 builds for
+                                      vorbis_analysis_buffer(); needs a CMGPU_PLANAR_F32 context */
 
 typedef struct cmgpu_ctx cmgpu_ctx_t;
 
@@ -138,6 +142,12 @@ int cmgpu_process_cycle(cmgpu_ctx_t *ctx, unsigned first_slot, unsigned n_slots,
 /* Device -> host copy of the slot's (transformed) PCM on the download stream, ordered after
  * the slot's last tick. `host` NULL = the pinned staging slot. Asynchronous if page-locked. */
 int cmgpu_fetch(cmgpu_ctx_t *ctx, unsigned slot, void *host);
+/* Float planes of a slot (CMGPU_PLANAR): [stream][channel][cmgpu_plane_stride()] float, valid for
+ * the stream's frames of the tick. Device pointer, and a download like cmgpu_fetch (`host` must be
+ * given: max_streams * channels * plane_stride floats). */
+void  *cmgpu_device_planar_slot(cmgpu_ctx_t *ctx, unsigned slot);
+size_t cmgpu_plane_stride(const cmgpu_ctx_t *ctx);           /* in floats */
+int    cmgpu_fetch_planar(cmgpu_ctx_t *ctx, unsigned slot, float *host);
 /* Wait for everything queued on the context. */
 int cmgpu_sync(cmgpu_ctx_t *ctx);
 /* Wait until the slot's last fetch (or tick, if none) has completed. */

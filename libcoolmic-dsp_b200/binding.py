@@ -13,8 +13,8 @@ import os
 LIB_PATH = Path(os.environ.get("CMGPU_LIB", PKG / "lib" / "libcoolmic_b200.so"))
 MAX_CH = 16
 
-SEPARATE_OUT, NO_PINNED, FORCE_GENERIC = 0x1, 0x2, 0x4
-TRANSFORM, METER = 0x1, 0x2
+SEPARATE_OUT, NO_PINNED, FORCE_GENERIC, PLANAR_F32 = 0x1, 0x2, 0x4, 0x8
+TRANSFORM, METER, PLANAR = 0x1, 0x2, 0x4
 FUSED = TRANSFORM | METER
 
 
@@ -84,6 +84,9 @@ SYMBOLS = {
     "cmgpu_process": (C.c_int, [_P, C.c_uint, C.c_uint]),
     "cmgpu_process_cycle": (C.c_int, [_P, C.c_uint, C.c_uint, C.c_uint]),
     "cmgpu_fetch": (C.c_int, [_P, C.c_uint, _P]),
+    "cmgpu_device_planar_slot": (_P, [_P, C.c_uint]),
+    "cmgpu_plane_stride": (C.c_size_t, [_P]),
+    "cmgpu_fetch_planar": (C.c_int, [_P, C.c_uint, C.POINTER(C.c_float)]),
     "cmgpu_sync": (C.c_int, [_P]),
     "cmgpu_slot_wait": (C.c_int, [_P, C.c_uint]),
     "cmgpu_meter_snapshot": (C.c_int, [_P, C.c_uint, C.c_uint, C.POINTER(MeterState), C.c_int]),
@@ -256,6 +259,13 @@ class Engine:
         if host is not None:
             assert host.nbytes >= self.out_stride * self.active and host.flags.c_contiguous
         _check(self.L.cmgpu_fetch(self.ctx, slot, ptr), "cmgpu_fetch")
+
+    def fetch_planar(self, slot: int) -> np.ndarray:
+        """float32 [max_streams][channels][plane_stride] of the slot's last CMGPU_PLANAR tick (after sync())."""
+        ps = int(self.L.cmgpu_plane_stride(self.ctx))
+        out = np.zeros((self.max_streams, self.channels, ps), dtype=np.float32)
+        _check(self.L.cmgpu_fetch_planar(self.ctx, slot, out.ctypes.data_as(C.POINTER(C.c_float))), "cmgpu_fetch_planar")
+        return out
 
     def sync(self):
         _check(self.L.cmgpu_sync(self.ctx), "cmgpu_sync")

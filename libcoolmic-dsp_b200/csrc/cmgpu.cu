@@ -102,6 +102,8 @@ struct cmgpu_ctx {
 
     uint8_t *d_in = nullptr, *d_out = nullptr;     // rings
     uint8_t *h_ring = nullptr;                     // pinned staging ring
+    float *d_planar = nullptr;                     // optional [slot][stream][channel][plane_stride] float
+    size_t plane_stride = 0, planar_slot_floats = 0;
 
     // EXTENSION (downmix contexts only): N -> M mix, separate output geometry, input-side meters
     unsigned out_channels = 0;                     // 0: ordinary gain context
@@ -153,9 +155,16 @@ namespace {
 using TickKernel = void (*)(const TickArgs);
 
 template <int C, int G>
-TickKernel fast_kernel(int gm, bool meter)
+TickKernel fast_kernel(int gm, bool meter, bool planar)
 {
     using namespace cmgpu;
+    if (planar) {           // planes are a second output of the fused (metering) pass only
+        switch (gm) {
+        case GM_IDENTITY: return fused_tick<C, G, GM_IDENTITY, true, true>;
+        case GM_ADDALL:   return fused_tick<C, G, GM_ADDALL, true, true>;
+        default:          return fused_tick<C, G, GM_MASKED, true, true>;
+        }
+    }
     switch (gm) {
     case GM_IDENTITY: return meter ? fused_tick<C, G, GM_IDENTITY, true> : fused_tick<C, G, GM_IDENTITY, false>;
     case GM_ADDALL:   return meter ? fused_tick<C, G, GM_ADDALL, true> : fused_tick<C, G, GM_ADDALL, false>;
@@ -164,11 +173,11 @@ TickKernel fast_kernel(int gm, bool meter)
 }
 
 template <int C>
-TickKernel fast_kernel_g(int g, int gm, bool meter)
+TickKernel fast_kernel_g(int g, int gm, bool meter, bool planar)
 {
     if (g == 8 && C != 16)
-        return fast_kernel<C, (C == 16 ? 32 : 8)>(gm, meter);
-    return fast_kernel<C, 32>(gm, meter);
+        return fast_kernel<C, (C == 16 ? 32 : 8)>(gm, meter, planar);
+    return fast_kernel<C, 32>(gm, meter, planar);
 }
 
 using GenericKernel = void (*)(const TickArgs, const int);
@@ -183,14 +192,14 @@ GenericKernel generic_kernel(int gm, bool meter)
     }
 }
 
-TickKernel pick_fast(const cmgpu_ctx *c, int gm, bool meter)
+TickKernel pick_fast(const cmgpu_ctx *c, int gm, bool meter, bool planar = false)
 {
     switch (c->channels) {
-    case 1:  return fast_kernel_g<1>(c->plan_g, gm, meter);
-    case 2:  return fast_kernel_g<2>(c->plan_g, gm, meter);
-    case 4:  return fast_kernel_g<4>(c->plan_g, gm, meter);
-    case 8:  return fast_kernel_g<8>(c->plan_g, gm, meter);
-    default: return fast_kernel_g<16>(c->plan_g, gm, meter);
+    case 1:  return fast_kernel_g<1>(c->plan_g, gm, meter, planar);
+    case 2:  return fast_kernel_g<2>(c->plan_g, gm, meter, planar);
+    case 4:  return fast_kernel_g<4>(c->plan_g, gm, meter, planar);
+    case 8:  return fast_kernel_g<8>(c->plan_g, gm, meter, planar);
+    default: return fast_kernel_g<16>(c->plan_g, gm, meter, planar);
     }
 }
 
@@ -219,7 +228,7 @@ cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter, cud
     if (c->plan_g == 0)
         generic_kernel(gm, meter)<<<(unsigned)grid, 128, 0, st>>>(a, (int)c->channels);
     else
-        pick_fast(c, gm, meter)<<<(unsigned)grid, 256, 0, st>>>(a);
+        pick_fast(c, gm, meter, a.planar != nullptr)<<<(unsigned)grid, 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -400,7 +409,10 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
     else if (transform && c->n_mode[cmgpu::GM_ADDALL])
         gm = (c->plan_g == 0) ? cmgpu::GM_MASKED : cmgpu::GM_ADDALL;   // generic kernel: masked covers it
     const bool store = gm != cmgpu::GM_IDENTITY || separate;
-    if (!store && !meter)
+    const bool planar = (flags & CMGPU_PLANAR) != 0;
+    if (planar && (!c->d_planar || !meter))
+        return fail(CMGPU_ERR_INVAL, "CMGPU_PLANAR needs a CMGPU_PLANAR_F32 context and goes with CMGPU_METER (the fused pass)");
+    if (!store && !meter && !planar)
         return CMGPU_OK;                 // in-place pass-through without metering: nothing to do
 
     TickArgs a;
@@ -421,6 +433,8 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
     a.per_item = c->plan_per_item;
     a.row_u64 = c->row_u64;
     a.store = store ? 1u : 0u;
+    a.planar = planar ? c->d_planar + (size_t)slot * c->planar_slot_floats : nullptr;
+    a.plane_stride = (uint32_t)c->plane_stride;
     CU(launch_tick(c, a, gm, meter, st));
     c->launches++;
     return CMGPU_OK;
@@ -586,6 +600,13 @@ static cmgpu_ctx_t *ctx_create_impl(int device, unsigned channels, unsigned out_
         return bail("cudaMallocHost(staging)", e);
     if (c->h_ring)
         memset(c->h_ring, 0, ring);
+    if ((flags & CMGPU_PLANAR_F32) && !out_channels) {
+        c->plane_stride = ((size_t)block_frames + 3u) & ~(size_t)3u;
+        c->planar_slot_floats = c->plane_stride * channels * max_streams;
+        if ((e = cudaMalloc(&c->d_planar, c->planar_slot_floats * ring_slots * sizeof(float))) != cudaSuccess ||
+            (e = cudaMemset(c->d_planar, 0, c->planar_slot_floats * ring_slots * sizeof(float))) != cudaSuccess)
+            return bail("cudaMalloc(planes)", e);
+    }
     if ((e = cudaMalloc(&c->d_gains, sizeof(GainRow) * max_streams)) != cudaSuccess)
         return bail("cudaMalloc(gains)", e);
     if ((e = cudaMalloc(&c->d_meters, sizeof(uint64_t) * c->row_u64 * max_streams)) != cudaSuccess)
@@ -664,6 +685,7 @@ void cmgpu_ctx_destroy(cmgpu_ctx_t *c)
     cudaFree(c->d_gains);
     cudaFree(c->d_meters);
     cudaFree(c->d_frames);
+    cudaFree(c->d_planar);
     cudaFree(c->d_mix);
     cudaFree(c->d_meters_in);
     if (c->h_ring_out)
@@ -856,6 +878,29 @@ int cmgpu_fetch(cmgpu_ctx_t *c, unsigned slot, void *host)
     CU(cudaStreamWaitEvent(c->s_down, c->ev_up[slot], 0));
     const uint8_t *src = (c->d_out ? c->d_out : c->d_in) + (size_t)slot * out_slot;
     CU(cudaMemcpyAsync(host, src, out_stride * c->active, cudaMemcpyDeviceToHost, c->s_down));
+    CU(cudaEventRecord(c->ev_down[slot], c->s_down));
+    return CMGPU_OK;
+}
+
+void *cmgpu_device_planar_slot(cmgpu_ctx_t *c, unsigned slot)
+{
+    return slot_ok(c, slot) && c->d_planar ? c->d_planar + (size_t)slot * c->planar_slot_floats : nullptr;
+}
+size_t cmgpu_plane_stride(const cmgpu_ctx_t *c) { return c ? c->plane_stride : 0; }
+
+int cmgpu_fetch_planar(cmgpu_ctx_t *c, unsigned slot, float *host)
+{
+    if (!slot_ok(c, slot))
+        return fail(c ? CMGPU_ERR_INVAL : CMGPU_ERR_FAULT, "bad context or slot");
+    if (!host)
+        return fail(CMGPU_ERR_FAULT, "NULL host buffer");
+    if (!c->d_planar)
+        return fail(CMGPU_ERR_INVAL, "context has no float planes (CMGPU_PLANAR_F32)");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamWaitEvent(c->s_down, c->ev_cmp[slot], 0));
+    CU(cudaMemcpyAsync(host, c->d_planar + (size_t)slot * c->planar_slot_floats,
+                       c->plane_stride * c->channels * c->active * sizeof(float), cudaMemcpyDeviceToHost, c->s_down));
     CU(cudaEventRecord(c->ev_down[slot], c->s_down));
     return CMGPU_OK;
 }

@@ -81,6 +81,8 @@ struct TickArgs {
     uint32_t per_item;          // vectors (fast kernels) or frames (generic kernel) per item
     uint32_t row_u64;           // meter row length in uint64
     uint32_t store;             // write PCM to `out` (0 only for identity streams in place)
+    float *planar;              // optional second output: [stream][channel][plane_stride] float = y / 32768.f
+    uint32_t plane_stride;      // floats per plane (block_frames rounded up to 4)
 };
 
 // ---- small helpers -----------------------------------------------------------------------
@@ -254,6 +256,44 @@ __device__ __forceinline__ uint4 do_vector(uint4 w, const Recipe (&rc)[Shape<C>:
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// Optional second output: the encoder-side sample-format stage of
+// enc_vorbis.c:108-117 -- de-interleave and `sample / 32768.f` into one float plane per channel,
+// which is what vorbis_analysis_buffer() wants. The division by 2^15 is exact in binary32, so
+// multiplying by 2^-15 gives bit-identical floats. Only the PLANAR instantiations of the kernel call
+// it (a run-time flag in the plain kernels cost them 2 %); it stays out of line there.
+template <int C>
+__device__ __noinline__ void store_planar(float *planar, uint32_t plane_stride, uint32_t s, uint32_t v, uint4 o,
+                                          int nvalid)
+{
+    constexpr int P = Shape<C>::kPerLane;
+    const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        f[2 * j] = (float)(int)(short)(w[j] & 0xffffu) * (1.0f / 32768.0f);
+        f[2 * j + 1] = (float)((int)w[j] >> 16) * (1.0f / 32768.0f);
+    }
+    const uint32_t cbase = (C == 16) ? (v & 1u) * 8u : 0u;
+    const uint32_t frame0 = (C <= 8) ? v * (uint32_t)Shape<C>::kFramesPerVec8 : (v >> 1);
+    float *base = planar + ((size_t)s * C + cbase) * plane_stride + frame0;
+    if (nvalid >= 8 && C == 1) {
+        reinterpret_cast<float4 *>(base)[0] = make_float4(f[0], f[1], f[2], f[3]);
+        reinterpret_cast<float4 *>(base)[1] = make_float4(f[4], f[5], f[6], f[7]);
+    } else if (nvalid >= 8 && C == 2) {
+        *reinterpret_cast<float4 *>(base) = make_float4(f[0], f[2], f[4], f[6]);
+        *reinterpret_cast<float4 *>(base + plane_stride) = make_float4(f[1], f[3], f[5], f[7]);
+    } else if (nvalid >= 8 && C == 4) {
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            *reinterpret_cast<float2 *>(base + (size_t)c * plane_stride) = make_float2(f[c], f[4 + c]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (k < nvalid)
+                base[(size_t)(k % P) * plane_stride + (k / P)] = f[k];
+    }
+}
+
 // What a lane needs to know about one work item.
 struct Item {
     const uint8_t *src;      // the lane's first vector of the item
@@ -402,7 +442,7 @@ __device__ __forceinline__ void item_publish(const TickArgs &a, const Item &it, 
 //     register sets alternate roles, nothing is copied;
 //   * across items, the next item's recipes and first batch are requested BEFORE the current
 //     item's meter epilogue (shuffles, one dependent re-read, atomics), whose latency they hide.
-template <int C, int G, int GM, bool METER>
+template <int C, int G, int GM, bool METER, bool PLANAR = false>
 __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __grid_constant__ TickArgs a)
 {
     constexpr int P = Shape<C>::kPerLane;
@@ -434,6 +474,8 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
         const uint4 o = do_vector<C, GM, METER, false, Tune<C, G>::kSatPack>(buf[u], rc, 0xffffu - iu, kmax, pacc, 8); \
         if (a.store)                                                                    \
             st_stream((it).dst + (size_t)iu * kStep, o);                                \
+        if (PLANAR)                                                                     \
+            store_planar<C>(a.planar, a.plane_stride, (it).s, (it).first + iu * G, o, 8); \
     }
 
     uint64_t item = (uint64_t)blockIdx.x * groups_per_cta + threadIdx.x / G;
@@ -473,6 +515,8 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
                     const uint4 o = do_vector<C, GM, METER, false, Tune<C, G>::kSatPack>(bufB[u], rc, 0xffffu - (rem0 + u), kmax, pacc, 8);
                     if (a.store)
                         st_stream(cur.dst + (size_t)(rem0 + u) * kStep, o);
+                    if (PLANAR)
+                        store_planar<C>(a.planar, a.plane_stride, cur.s, cur.first + (rem0 + u) * G, o, 8);
                 }
             }
         }
@@ -483,6 +527,8 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
             const uint4 o = do_vector<C, GM, METER, true, Tune<C, G>::kSatPack>(w, rc, 0xffffu - cur.tail_step, kmax, pacc, cur.tail_valid);
             if (a.store)
                 st_stream(a.out + off, o);
+            if (PLANAR)
+                store_planar<C>(a.planar, a.plane_stride, cur.s, cur.tail_vec, o, cur.tail_valid);
         }
 
         // next item: recipes and first batch go out before this item's epilogue
@@ -566,6 +612,8 @@ __device__ __forceinline__ void run_item_generic(const TickArgs &a, int C, uint3
                 const int y = apply_gain<GM>(x, rc[c]);
                 if (a.store)
                     out[o + c] = (int16_t)y;
+                if (a.planar)       // planes of lane = frame are coalesced as they are
+                    a.planar[((size_t)s * C + c) * a.plane_stride + f] = (float)y * (1.0f / 32768.0f);
                 if (METER) {
                     const uint32_t m = (uint32_t)abs(y);
                     kmax[c] = max(kmax[c], (m << 16) + radd);

@@ -411,3 +411,48 @@ def test_graph_cycle_equals_individual_ticks(cm, port):
             assert states[s]["channel_peak"][0] == int(meters[s].channel_peak[0]), f"stream {s}"
             assert states[s]["global_peak"] == int(meters[s].global_peak)
     assert all(results[0][1][s]["channel_peak"][0] == 100 for s in range(7))
+
+
+@pytest.mark.parametrize("channels,block", [(1, 320), (2, 1000), (2, 4799), (4, 333), (8, 257), (16, 100), (6, 500), (3, 77)])
+def test_planar_float_second_output(cm, port, channels, block):
+    """the encoder-side sample-format stage (enc_vorbis.c:108-117: de-interleave,
+    sample / 32768.f) as an optional second output of the fused pass. Dividing an int16 by 2^15 is
+    exact in binary32, so the planes must equal numpy's float32 division bit for bit. The reference
+    file needs libvorbis and cannot be built here: this row is checked against that one-line
+    restatement only."""
+    rng = np.random.default_rng(channels + block)
+    n_streams = 21
+    with cm.Engine(channels, n_streams, block, flags=cm.PLANAR_F32) as eng:
+        host = eng.host_slot(0)
+        host[:] = make_pcm(rng, "full", host.shape)
+        scale, gain = make_gains(rng, n_streams, channels)
+        eng.set_gain_table(scale, gain)
+        frames = rng.integers(0, block + 1, size=n_streams).astype(np.uint32)
+        frames[0] = block
+        eng.set_frames(0, frames)
+        want, meters = oracle_batch(port, host.copy(), frames, channels, scale, gain)
+        eng.submit(0)
+        eng.process(0, cm.FUSED | cm.PLANAR)
+        eng.fetch(0)
+        eng.sync()
+        planes = eng.fetch_planar(0)
+        eng.sync()
+        assert np.array_equal(eng.host_slot(0), want)
+        check_meters(cm, port, eng, meters, n_streams, channels)
+        for s in range(n_streams):
+            n = int(frames[s])
+            y = want[s, : n * channels].reshape(n, channels)
+            ref = (y.astype(np.float32) / np.float32(32768.0)).T            # [channel][frame]
+            got = planes[s, :, :n]
+            assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), ref.view(np.uint32)), f"stream {s}"
+    with cm.Engine(2, 2, 16) as eng:                                       # no plane ring: the flag is refused
+        eng.submit(0)
+        with pytest.raises(cm.CmgpuError):
+            eng.process(0, cm.FUSED | cm.PLANAR)
+
+
+def test_opus_sized_blocks(cm, port):
+    """ticks of exactly 2,880 frames (60 ms at 48 kHz), the packet size enc_opus.c:341
+    hands to opus_encode -- each stream-block is then one ready-made, contiguous encoder input."""
+    run_case(cm, port, 2, 64, 2880, None, "gauss", seed=2880)
+    run_case(cm, port, 1, 64, 2880, None, "gauss", seed=2881)
