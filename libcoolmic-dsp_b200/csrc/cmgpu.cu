@@ -144,7 +144,8 @@ struct cmgpu_ctx {
     bool classes_dirty = true;
 
     // launch plan (depends on shape only)
-    int plan_g = 32;              // lanes per item (fast kernels); 0 = generic kernel
+    int plan_g = 32;              // lanes per item (fast kernels); 0 = frame-per-lane generic kernel; -1 = any_tick
+    int plan_lanes = 32;          // any_tick: lanes of a warp that take part
     uint32_t plan_items = 1, plan_per_item = 0;
     int grid_cap[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // resident CTAs per (gain mode, meter) kernel
     char kname[64] = "";
@@ -192,6 +193,17 @@ GenericKernel generic_kernel(int gm, bool meter)
     }
 }
 
+using AnyKernel = void (*)(const TickArgs, const int, const int);
+
+AnyKernel any_kernel(int gm, bool meter)
+{
+    using namespace cmgpu;
+    switch (gm) {
+    case GM_IDENTITY: return meter ? any_tick<GM_IDENTITY, true> : any_tick<GM_IDENTITY, false>;
+    default:          return meter ? any_tick<GM_MASKED, true> : any_tick<GM_MASKED, false>;
+    }
+}
+
 TickKernel pick_fast(const cmgpu_ctx *c, int gm, bool meter, bool planar = false)
 {
     switch (c->channels) {
@@ -209,8 +221,9 @@ int resident_ctas(cmgpu_ctx *c, int gm, bool meter)
     if (cap)
         return cap;
     int n = 0;
-    cudaError_t e = c->plan_g ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pick_fast(c, gm, meter), 256, 0)
-                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, generic_kernel(gm, meter), 128, 0);
+    cudaError_t e = c->plan_g > 0   ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pick_fast(c, gm, meter), 256, 0)
+                    : c->plan_g < 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, any_kernel(gm, meter), 256, 0)
+                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, generic_kernel(gm, meter), 128, 0);
     if (e != cudaSuccess || n < 1)
         n = 1;
     cap = n * c->num_sms;
@@ -220,12 +233,14 @@ int resident_ctas(cmgpu_ctx *c, int gm, bool meter)
 cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter, cudaStream_t st)
 {
     const uint64_t items = (uint64_t)a.n_streams * a.items_per_block;
-    const uint64_t per_cta = c->plan_g ? 256u / (unsigned)c->plan_g : 4u;
+    const uint64_t per_cta = c->plan_g > 0 ? 256u / (unsigned)c->plan_g : (c->plan_g < 0 ? 8u : 4u);
     uint64_t grid = (items + per_cta - 1) / per_cta;
     const uint64_t cap = (uint64_t)resident_ctas(c, gm, meter);
     if (grid > cap)
         grid = cap;
-    if (c->plan_g == 0)
+    if (c->plan_g < 0)
+        any_kernel(gm, meter)<<<(unsigned)grid, 256, 0, st>>>(a, (int)c->channels, c->plan_lanes);
+    else if (c->plan_g == 0)
         generic_kernel(gm, meter)<<<(unsigned)grid, 128, 0, st>>>(a, (int)c->channels);
     else
         pick_fast(c, gm, meter, a.planar != nullptr)<<<(unsigned)grid, 256, 0, st>>>(a);
@@ -237,6 +252,26 @@ void make_plan(cmgpu_ctx *c)
 {
     const unsigned C = c->channels;
     const bool fast = !(c->flags & CMGPU_FORCE_GENERIC) && (C == 1 || C == 2 || C == 4 || C == 8 || C == 16);
+    if (!fast && !(c->flags & CMGPU_FORCE_GENERIC)) {
+        // any_tick: vectors over frames that straddle them; L lanes, 8*L a multiple of C
+        unsigned g = 8, x = C;
+        while (x) { unsigned t = g % x; g = x; x = t; }          // gcd(8, C)
+        const unsigned m = C / g;
+        const unsigned lanes = 32 - 32 % m;
+        const uint32_t nvec = (uint32_t)(c->stride / 16);
+        const uint32_t quantum = lanes * 8u;                      // two batches of 4 per lane
+        const uint32_t target = 2048;
+        uint32_t items = (nvec + target - 1) / target;
+        uint32_t per = (nvec + items - 1) / items;
+        per = (per + quantum - 1) / quantum * quantum;
+        items = (nvec + per - 1) / per;
+        c->plan_g = -1;
+        c->plan_lanes = (int)lanes;
+        c->plan_items = items;
+        c->plan_per_item = per;
+        snprintf(c->kname, sizeof(c->kname), "any_tick<C=%u,L=%u>", C, lanes);
+        return;
+    }
     if (!fast) {
         // generic: one warp per item, 32 frames per step; aim for <= 2048 frames per item
         const uint32_t target = 2048;
@@ -407,7 +442,7 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
     if (transform && c->n_mode[cmgpu::GM_MASKED])
         gm = cmgpu::GM_MASKED;
     else if (transform && c->n_mode[cmgpu::GM_ADDALL])
-        gm = (c->plan_g == 0) ? cmgpu::GM_MASKED : cmgpu::GM_ADDALL;   // generic kernel: masked covers it
+        gm = (c->plan_g <= 0) ? cmgpu::GM_MASKED : cmgpu::GM_ADDALL;   // generic / any kernels: masked covers it
     const bool store = gm != cmgpu::GM_IDENTITY || separate;
     const bool planar = (flags & CMGPU_PLANAR) != 0;
     if (planar && (!c->d_planar || !meter))

@@ -561,6 +561,190 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
     tick_end(a);
 }
 
+// Float planes for any channel count: one scalar store per sample (secondary path).
+__device__ __noinline__ void store_planar_any(float *planar, uint32_t plane_stride, uint32_t s, int C, uint32_t v,
+                                              uint4 o, int nvalid)
+{
+    const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+    const uint64_t sample0 = (uint64_t)v * 8u;
+    uint32_t frame = (uint32_t)(sample0 / (uint32_t)C);
+    int ch = (int)(sample0 - (uint64_t)frame * (uint32_t)C);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int y = (k & 1) ? ((int)w[k >> 1] >> 16) : (int)(short)(w[k >> 1] & 0xffffu);
+        if (k < nvalid)
+            planar[((size_t)s * C + ch) * plane_stride + frame] = (float)y * (1.0f / 32768.0f);
+        if (++ch == C) {
+            ch = 0;
+            frame++;
+        }
+    }
+}
+
+// ---- any_tick: channel counts that do not tile a 16-byte vector (3, 5, 6, 7, 9..15) ------------
+//
+// Same vector pipeline as fused_tick, for frames that straddle vectors. A warp uses L <= 32 lanes,
+// L a multiple of C / gcd(8, C) (30 for 3/5/6/10/12/15 channels, 28 for 7/14, 27 for 9, 26 for 13,
+// 22 for 11): the sample offset between a lane's consecutive vectors, 8*L, is then a multiple of
+// C, so each of the lane's 8 sample slots keeps ONE channel for the whole item -- the hot loop is
+// the 8-channel one (do_vector<8>: a recipe, a peak key and a power sum per slot), only the
+// recipes are gathered per lane and the epilogue folds slots into channels by a per-lane map.
+template <int GM, bool METER>
+__global__ void __launch_bounds__(256, 2) any_tick(const __grid_constant__ TickArgs a, const int C, const int L)
+{
+    constexpr int UNROLL = 4;
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool active = (int)lane < L;
+    const size_t kStep = (size_t)L * 16;
+    const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block;
+    const uint64_t stride = (uint64_t)gridDim.x * 8u;
+
+    for (uint64_t item = (uint64_t)blockIdx.x * 8u + (threadIdx.x >> 5); item < n_items; item += stride) {
+        const uint32_t s = (uint32_t)(item / a.items_per_block);
+        const uint32_t chunk = (uint32_t)(item - (uint64_t)s * a.items_per_block);
+        const uint32_t nfr = a.frames ? min(__ldg(a.frames + s), a.block_frames) : a.block_frames;
+        const uint32_t valid_bytes = nfr * (uint32_t)(2 * C);
+        const uint32_t nvec = (valid_bytes + 15u) >> 4;
+        const uint32_t v0 = chunk * a.per_item;
+        const uint32_t v1 = min(v0 + a.per_item, nvec);
+        if (METER && chunk == 0 && lane == 0 && nfr)
+            atomicAdd(a.meters + (size_t)s * a.row_u64 + 2 * C, (unsigned long long)nfr);
+        if (v0 >= v1)
+            continue;
+
+        const size_t base = (size_t)s * a.stride_bytes;
+        const uint32_t first = v0 + lane;
+        const uint32_t vfull = min(v1, valid_bytes >> 4);
+        const uint32_t n_i = (active && first < vfull) ? (vfull - first + (uint32_t)L - 1u) / (uint32_t)L : 0u;
+        const uint8_t *src = a.in + base + (size_t)first * 16;
+        uint8_t *dst = a.out + base + (size_t)first * 16;
+
+        // the lane's slot -> channel map and recipes
+        int chan[8];
+        Recipe rc[8];
+        {
+            int ch = (int)(((uint64_t)first * 8u) % (uint32_t)C);
+            const GainRow *g = a.gains + s;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                chan[k] = ch;
+                rc[k].mw = rc[k].addm = 0;
+                rc[k].mul = 1;
+                if (GM != GM_IDENTITY) {
+                    rc[k].mw = (int)__ldg(&g->mw[ch]);
+                    rc[k].mul = (int)__ldg(&g->mul[ch]);
+                    rc[k].addm = (int)__ldg(&g->addm[ch]);
+                }
+                ch = ch + 1 == C ? 0 : ch + 1;
+            }
+        }
+        uint32_t kmax[8];
+        uint64_t pacc[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            kmax[k] = 0;
+            pacc[k] = 0;
+        }
+
+        uint4 bufA[UNROLL], bufB[UNROLL];
+        const uint32_t nb = n_i / UNROLL;
+#define CMGPU_LOAD_BATCH(buf, b)                                                        \
+    _Pragma("unroll") for (int u = 0; u < UNROLL; u++)                                  \
+        buf[u] = ld_stream(src + (size_t)((b) * UNROLL + u) * kStep);
+#define CMGPU_DO_BATCH(buf, b)                                                          \
+    _Pragma("unroll") for (int u = 0; u < UNROLL; u++) {                                \
+        const uint32_t iu = (b) * UNROLL + u;                                           \
+        const uint4 o = do_vector<8, GM, METER, false, true>(buf[u], rc, 0xffffu - iu, kmax, pacc, 8); \
+        if (a.store)                                                                    \
+            st_stream(dst + (size_t)iu * kStep, o);                                     \
+        if (a.planar)                                                                   \
+            store_planar_any(a.planar, a.plane_stride, s, C, first + iu * (uint32_t)L, o, 8); \
+    }
+        if (nb > 0) {
+            CMGPU_LOAD_BATCH(bufA, 0u)
+        }
+        for (uint32_t b = 0; b < nb; b += 2) {
+            if (b + 1 < nb) {
+                CMGPU_LOAD_BATCH(bufB, b + 1)
+            }
+            CMGPU_DO_BATCH(bufA, b)
+            if (b + 2 < nb) {
+                CMGPU_LOAD_BATCH(bufA, b + 2)
+            }
+            if (b + 1 < nb) {
+                CMGPU_DO_BATCH(bufB, b + 1)
+            }
+        }
+#undef CMGPU_LOAD_BATCH
+#undef CMGPU_DO_BATCH
+        for (uint32_t i = nb * UNROLL; i < n_i; i++) {
+            const uint4 w = ld_stream(src + (size_t)i * kStep);
+            const uint4 o = do_vector<8, GM, METER, false, true>(w, rc, 0xffffu - i, kmax, pacc, 8);
+            if (a.store)
+                st_stream(dst + (size_t)i * kStep, o);
+            if (a.planar)
+                store_planar_any(a.planar, a.plane_stride, s, C, first + i * (uint32_t)L, o, 8);
+        }
+        if (active && vfull < v1 && (vfull << 4) < valid_bytes && ((vfull - v0) % (uint32_t)L) == lane) {
+            const uint32_t step = (vfull - v0) / (uint32_t)L;
+            const int nvalid = (int)((valid_bytes - (vfull << 4)) >> 1);
+            const uint4 w = ld_stream(a.in + base + (size_t)vfull * 16);
+            const uint4 o = do_vector<8, GM, METER, true, true>(w, rc, 0xffffu - step, kmax, pacc, nvalid);
+            if (a.store)
+                st_stream(a.out + base + (size_t)vfull * 16, o);
+            if (a.planar)
+                store_planar_any(a.planar, a.plane_stride, s, C, vfull, o, nvalid);
+        }
+        if (!METER)
+            continue;
+
+        // ---- epilogue: slots -> position keys, fold by the lane's channel map, combine lanes ----
+        const uint64_t pos_base = tick_begin(a);
+        uint64_t key8[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t mag = kmax[k] >> 16;
+            const uint32_t step = 0xffffu - (kmax[k] & 0xffffu);
+            const uint64_t sample = ((uint64_t)first + (uint64_t)step * (uint32_t)L) * 8u + (uint32_t)k;
+            key8[k] = make_key(mag, pos_base + (uint32_t)(sample / (uint32_t)C));
+        }
+        uint64_t key = 0, pw = 0;
+        for (int c = 0; c < C; c++) {
+            uint64_t kc = 0, pc = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (chan[k] == c) {
+                    kc = max(kc, key8[k]);
+                    pc += pacc[k];
+                }
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                kc = max(kc, shfl_xor64(0xffffffffu, kc, off));
+                pc += shfl_xor64(0xffffffffu, pc, off);
+            }
+            if ((int)lane == c) {
+                key = kc;
+                pw = pc;
+            }
+        }
+        __syncwarp();
+        if ((int)lane < C) {
+            unsigned long long *row = a.meters + (size_t)s * a.row_u64;
+            if (key) {
+                const uint64_t pos = (~(key >> 1)) & kKeyPosMask;
+                const uint32_t frame = (uint32_t)(pos - pos_base);
+                const volatile int16_t *y = reinterpret_cast<const volatile int16_t *>(a.out + base);
+                const int yv = y[(size_t)frame * C + lane];
+                atomicMax(row + lane, (unsigned long long)(key | (yv < 0 ? 1ull : 0ull)));
+            }
+            if (pw)
+                atomicAdd(row + C + lane, (unsigned long long)pw);
+        }
+    }
+    tick_end(a);
+}
+
 // Closes a cycle of concurrently running ticks: advances the tick sequence number once all of
 // them are done (the graph orders it after every tick node).
 __global__ void bump_tick(unsigned long long *tick, unsigned n)
