@@ -678,6 +678,12 @@ static cmgpu_ctx_t *ctx_create_impl(int device, unsigned channels, unsigned out_
     c->dirty_lo = 0;
     c->dirty_hi = max_streams;
     make_plan(c);
+    if ((uint64_t)max_streams * c->plan_items >= 0xffffffffull) {
+        fail(CMGPU_ERR_INVAL, "cmgpu_ctx_create: %u streams x %u work items per stream-block exceed 2^32", max_streams,
+             c->plan_items);
+        cmgpu_ctx_destroy(c);
+        return nullptr;
+    }
     return c;
 }
 

@@ -320,8 +320,10 @@ __device__ __forceinline__ bool item_setup(const TickArgs &a, uint64_t item, uin
     it.dst = a.out;
     if (item >= n_items)
         return false;
-    const uint32_t s = (uint32_t)(item / a.items_per_block);
-    const uint32_t chunk = (uint32_t)(item - (uint64_t)s * a.items_per_block);
+    // (the host keeps n_streams * items_per_block below 2^32: 32-bit division, none for one item per block)
+    const uint32_t item32 = (uint32_t)item;
+    const uint32_t s = a.items_per_block == 1 ? item32 : item32 / a.items_per_block;
+    const uint32_t chunk = item32 - s * a.items_per_block;
     const uint32_t nfr = a.frames ? min(__ldg(a.frames + s), a.block_frames) : a.block_frames;
     const uint32_t valid_bytes = nfr * (uint32_t)(2 * C);
     const uint32_t nvec = (valid_bytes + 15u) >> 4;
@@ -379,18 +381,24 @@ __device__ __forceinline__ void item_publish(const TickArgs &a, const Item &it, 
     const uint64_t pos_base = tick_begin(a);
     uint64_t kc[P];
 #pragma unroll
-    for (int c = 0; c < P; c++)
-        kc[c] = 0;
+    for (int c = 0; c < P; c++) {
+        // a channel's slots c, c+P, c+2P, ... are in time order inside a vector: fold them in the
+        // cheap 32-bit domain first (strict '>' keeps the earlier slot), widen only the winner
+        uint32_t best = kmax[c];
+        uint32_t sub = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const uint32_t mag = kmax[k] >> 16;
-        const uint32_t step = 0xffffu - (kmax[k] & 0xffffu);
+        for (int j = 1; j < 8 / P; j++) {
+            if (kmax[c + j * P] > best) {
+                best = kmax[c + j * P];
+                sub = (uint32_t)j;
+            }
+        }
+        const uint32_t mag = best >> 16;
+        const uint32_t step = 0xffffu - (best & 0xffffu);
         const uint32_t v = it.first + step * G;
-        // frame index of slot k of vector v inside the stream-block
-        const uint32_t frame = (C <= 8) ? (v * (uint32_t)Shape<C>::kFramesPerVec8 + (uint32_t)(k / P))
-                                        : (v >> 1);
-        const uint64_t key = make_key(mag, pos_base + frame);
-        kc[k % P] = max(kc[k % P], key);
+        // frame index of that slot of vector v inside the stream-block
+        const uint32_t frame = (C <= 8) ? (v * (uint32_t)Shape<C>::kFramesPerVec8 + sub) : (v >> 1);
+        kc[c] = make_key(mag, pos_base + frame);
     }
 #pragma unroll
     for (int off = G / 2; off >= Shape<C>::kLanesPerFrame; off >>= 1) {
