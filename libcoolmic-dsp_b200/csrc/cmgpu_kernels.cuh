@@ -30,6 +30,13 @@
 #ifndef CMGPU_MIN_CTAS_WIDE
 #define CMGPU_MIN_CTAS_WIDE 2
 #endif
+// 8-lane-group kernels (stream-blocks of <= 1 KiB)
+#ifndef CMGPU_G8_CTAS
+#define CMGPU_G8_CTAS 3
+#endif
+#ifndef CMGPU_G8_CTAS_WIDE
+#define CMGPU_G8_CTAS_WIDE 2
+#endif
 
 namespace cmgpu {
 
@@ -192,8 +199,8 @@ struct Shape {
 // and as many resident groups as possible so that one wave covers all streams of a tick.
 template <int C, int G>
 struct Tune {
-    static constexpr int kUnroll = (G == 8) ? 2 : (C >= 4 ? CMGPU_UNROLL_WIDE : CMGPU_UNROLL);
-    static constexpr int kMinCtas = (G == 8) ? (C >= 4 ? 3 : 4) : (C >= 4 ? CMGPU_MIN_CTAS_WIDE : CMGPU_MIN_CTAS);
+    static constexpr int kUnroll = (G == 8) ? 4 : (C >= 4 ? CMGPU_UNROLL_WIDE : CMGPU_UNROLL);
+    static constexpr int kMinCtas = (G == 8) ? (C >= 4 ? CMGPU_G8_CTAS_WIDE : CMGPU_G8_CTAS) : (C >= 4 ? CMGPU_MIN_CTAS_WIDE : CMGPU_MIN_CTAS);
     static constexpr bool kSatPack = (G == 8) || (C >= 4);
 };
 
@@ -490,14 +497,40 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
     Item cur;
     Recipe rc[P];
     bool have = item_setup<C, G>(a, item, n_items, gl, cur);
+    // 8-lane groups walk stream-blocks of at most 64 vectors: a lane's (at most 8) vectors are all
+    // requested at once, predicated, into the two register sets -- one memory latency per item.
+#define CMGPU_LOAD_ALL(it)                                                              \
+    _Pragma("unroll") for (int u = 0; u < UNROLL; u++) {                                \
+        if ((uint32_t)u < (it).n_i)                                                     \
+            bufA[u] = ld_stream((it).src + (size_t)u * kStep);                          \
+        if ((uint32_t)(UNROLL + u) < (it).n_i)                                          \
+            bufB[u] = ld_stream((it).src + (size_t)(UNROLL + u) * kStep);               \
+    }
+#define CMGPU_DO_ALL(buf, it, base)                                                     \
+    _Pragma("unroll") for (int u = 0; u < UNROLL; u++) {                                \
+        const uint32_t iu = (base) + u;                                                 \
+        if (iu < (it).n_i) {                                                            \
+            const uint4 o = do_vector<C, GM, METER, false, Tune<C, G>::kSatPack>(buf[u], rc, 0xffffu - iu, kmax, pacc, 8); \
+            if (a.store)                                                                \
+                st_stream((it).dst + (size_t)iu * kStep, o);                            \
+            if (PLANAR)                                                                 \
+                store_planar<C>(a.planar, a.plane_stride, (it).s, (it).first + iu * G, o, 8); \
+        }                                                                               \
+    }
     if (have) {
         load_recipes<C, GM>(a, cur.s, gl, rc);
-        if (cur.n_i >= (uint32_t)UNROLL) {
+        if (G == 8) {
+            CMGPU_LOAD_ALL(cur)
+        } else if (cur.n_i >= (uint32_t)UNROLL) {
             CMGPU_LOAD_BATCH(bufA, cur, 0u)
         }
     }
     while (have) {
-        const uint32_t nb = cur.n_i / UNROLL;             // full batches of this lane; batch 0 is in flight
+        const uint32_t nb = (G == 8) ? 0u : cur.n_i / UNROLL;   // full batches of this lane; batch 0 is in flight
+        if (G == 8) {
+            CMGPU_DO_ALL(bufA, cur, 0u)
+            CMGPU_DO_ALL(bufB, cur, (uint32_t)UNROLL)
+        }
         for (uint32_t b = 0; b < nb; b += 2) {
             if (b + 1 < nb) {
                 CMGPU_LOAD_BATCH(bufB, cur, b + 1)
@@ -512,7 +545,7 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
         }
         // what is left of the lane's vectors (< UNROLL): requested together, then worked on
         const uint32_t rem0 = nb * UNROLL;
-        if (rem0 < cur.n_i) {
+        if (G != 8 && rem0 < cur.n_i) {
 #pragma unroll
             for (int u = 0; u < UNROLL - 1; u++)
                 if (rem0 + u < cur.n_i)
@@ -546,7 +579,9 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
         have = item_setup<C, G>(a, item, n_items, gl, nxt);
         if (have) {
             load_recipes<C, GM>(a, nxt.s, gl, rcn);
-            if (nxt.n_i >= (uint32_t)UNROLL) {
+            if (G == 8) {
+                CMGPU_LOAD_ALL(nxt)
+            } else if (nxt.n_i >= (uint32_t)UNROLL) {
                 CMGPU_LOAD_BATCH(bufA, nxt, 0u)
             }
         }
@@ -566,6 +601,8 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
     }
 #undef CMGPU_LOAD_BATCH
 #undef CMGPU_DO_BATCH
+#undef CMGPU_LOAD_ALL
+#undef CMGPU_DO_ALL
     tick_end(a);
 }
 
