@@ -411,23 +411,24 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
         m.stride_out = (uint32_t)c->stride_out;
         const uint32_t target = 2048;
         uint32_t items = (c->block_frames + target - 1) / target;
-        uint32_t per = ((c->block_frames + items - 1) / items + 31u) & ~31u;
+        uint32_t per = ((c->block_frames + items - 1) / items + 255u) & ~255u;
         m.items_per_block = (c->block_frames + per - 1) / per;
         m.per_item = per;
         m.cin = c->channels;
         m.cout = c->out_channels;
         const bool vec8 = c->channels == 8 && c->out_channels == 2 && !(c->flags & CMGPU_FORCE_GENERIC);
         const uint64_t n_items = (uint64_t)m.n_streams * m.items_per_block;
-        uint64_t grid = (n_items + 3) / 4;
+        const unsigned per_cta = vec8 ? 8 : 4;
+        uint64_t grid = (n_items + per_cta - 1) / per_cta;
         int occ = 0;
-        if ((vec8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cmgpu::mix_tick<true>, 128, 0)
+        if ((vec8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cmgpu::mix8to2_tick, 256, 0)
                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cmgpu::mix_tick<false>, 128, 0)) != cudaSuccess ||
             occ < 1)
             occ = 1;
         if (grid > (uint64_t)occ * c->num_sms)
             grid = (uint64_t)occ * c->num_sms;
         if (vec8)
-            cmgpu::mix_tick<true><<<(unsigned)grid, 128, 0, st>>>(m);
+            cmgpu::mix8to2_tick<<<(unsigned)grid, 256, 0, st>>>(m);
         else
             cmgpu::mix_tick<false><<<(unsigned)grid, 128, 0, st>>>(m);
         CU(cudaGetLastError());
@@ -750,7 +751,7 @@ const char *cmgpu_kernel_name(const cmgpu_ctx_t *c)
     if (!c)
         return "";
     if (c->out_channels)
-        return (c->channels == 8 && c->out_channels == 2 && !(c->flags & CMGPU_FORCE_GENERIC)) ? "mix_tick<8->2>" : "mix_tick<generic>";
+        return (c->channels == 8 && c->out_channels == 2 && !(c->flags & CMGPU_FORCE_GENERIC)) ? "mix8to2_tick" : "mix_tick<generic>";
     return c->kname;
 }
 unsigned cmgpu_meter_row_u64(const cmgpu_ctx_t *c) { return c ? c->row_u64 : 0; }
@@ -1040,6 +1041,13 @@ int cmgpu_stream_set_mix(cmgpu_ctx_t *c, unsigned stream, uint16_t scale, const 
     for (unsigned m = 0; m < c->out_channels; m++)
         for (unsigned ch = 0; ch < c->channels; ch++)
             r.w[m][ch] = weights[(size_t)m * c->channels + ch];
+    if (c->channels == 8 && c->out_channels == 2) {
+        for (unsigned m = 0; m < 2; m++)
+            for (unsigned p = 0; p < 4; p++) {
+                const uint32_t w0 = r.w[m][2 * p], w1 = r.w[m][2 * p + 1];
+                r.packed[m][p] = (w0 & 0xffu) | ((w1 & 0xffu) << 8) | ((w0 >> 8) << 16) | ((w1 >> 8) << 24);
+            }
+    }
     const unsigned l = ceil_log2(scale);
     r.shift = 31 + l;
     r.magic = (uint32_t)((((uint64_t)1 << r.shift) / scale) + 1);     // < 2^32: 2^(31+l)/scale < 2^32 for scale > 2^(l-1)

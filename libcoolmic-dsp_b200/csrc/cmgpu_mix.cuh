@@ -25,8 +25,11 @@ struct MixRow {
     uint32_t magic;          // M = floor(2^(31+l) / scale) + 1, l = ceil(log2(scale))
     uint32_t shift;          // 31 + l
     uint32_t pad[2];
+    // 8 -> 2 fast path: for output m and channel pair p the bytes { lo(w[2p]), lo(w[2p+1]), hi(w[2p]), hi(w[2p+1]) },
+    // so that two dp2a per pair give sum(x * lo) and sum(x * hi) straight from the packed input word
+    uint32_t packed[2][4];
 };
-static_assert(sizeof(MixRow) == 528, "MixRow layout");
+static_assert(sizeof(MixRow) == 560, "MixRow layout");
 
 struct MixArgs {
     const uint8_t *in;            // [stream][frames*CIN] S16, stride_in bytes apart
@@ -183,6 +186,145 @@ __global__ void __launch_bounds__(128) mix_tick(const __grid_constant__ MixArgs 
         __syncwarp();
         mix_publish<16>(a.meters_in + (size_t)s * (2 * cin + 2), cin, in, pos_base, f0, lane, kin, pin);
         mix_publish<16>(a.meters_out + (size_t)s * (2 * cout + 2), cout, out, pos_base, f0, lane, kout, pout);
+    }
+    tick_finish(a.tick, a.tick_bump);
+}
+
+__device__ __forceinline__ int dp2a_lo_su(uint32_t a_s16x2, uint32_t b_u8x4, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_s16x2), "r"(b_u8x4), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(uint32_t a_s16x2, uint32_t b_u8x4, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_s16x2), "r"(b_u8x4), "r"(c));
+    return d;
+}
+
+// 8 -> 2 (the config-4b shape) with the fused kernels' memory pipeline: one warp per (stream, chunk
+// of frames), a frame = one 128-bit load, loads in double-buffered batches of 4 per lane, output =
+// one 32-bit word per frame. The input side is metered by the 8-channel hot loop itself
+// (do_vector<8, identity>); the mix is 8 dp2a (signed 16-bit x unsigned 8-bit, weights split into
+// low and high bytes) + one 64-bit recombination per output instead of 8 half-rate IMAD.WIDE.
+__global__ void __launch_bounds__(256, 2) mix8to2_tick(const __grid_constant__ MixArgs a)
+{
+    constexpr int UNROLL = 4;
+    constexpr size_t kStep = 32 * 16;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block;
+    const uint64_t stride = (uint64_t)gridDim.x * 8u;
+
+    TickArgs ta;                      // the input side looks like an 8-channel identity tick to item_publish
+    ta.in = a.in;
+    ta.out = const_cast<uint8_t *>(a.in);
+    ta.meters = a.meters_in;
+    ta.tick = a.tick;
+    ta.pbits = a.pbits;
+    ta.tick_offset = a.tick_offset;
+    ta.stride_bytes = a.stride_in;
+    ta.row_u64 = 18;
+
+    for (uint64_t item = (uint64_t)blockIdx.x * 8u + (threadIdx.x >> 5); item < n_items; item += stride) {
+        const uint32_t s = (uint32_t)(item / a.items_per_block);
+        const uint32_t chunk = (uint32_t)(item - (uint64_t)s * a.items_per_block);
+        const uint32_t nfr = a.frames ? min(__ldg(a.frames + s), a.block_frames) : a.block_frames;
+        const uint32_t f0 = chunk * a.per_item;
+        const uint32_t f1 = min(f0 + a.per_item, nfr);
+        if (chunk == 0 && lane == 0 && nfr)
+            atomicAdd(a.meters_out + (size_t)s * 6 + 4, (unsigned long long)nfr);
+        if (f0 >= f1)
+            continue;
+
+        const MixRow *row = a.rows + s;
+        uint32_t B[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; m++)
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                B[m][p] = __ldg(&row->packed[m][p]);
+        const uint32_t magic = __ldg(&row->magic), shift = __ldg(&row->shift);
+
+        Item it;
+        it.s = s;
+        it.first = f0 + lane;
+        it.n_i = it.first < f1 ? (f1 - it.first + 31u) / 32u : 0u;
+        it.src = a.in + (size_t)s * a.stride_in + (size_t)it.first * 16;
+        it.dst = nullptr;
+        it.tail_vec = it.tail_step = 0;
+        it.tail_valid = 0;
+        it.count_frames = (chunk == 0 && lane == 0) ? nfr : 0;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(a.out + (size_t)s * a.stride_out) + it.first;
+
+        Recipe none[8];
+        uint32_t kin[8], kout[2] = {0, 0};
+        uint64_t pin[8], pout[2] = {0, 0};
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            none[k].mw = none[k].addm = 0;
+            none[k].mul = 1;
+            kin[k] = 0;
+            pin[k] = 0;
+        }
+
+        uint4 bufA[UNROLL], bufB[UNROLL];
+        const uint32_t nb = it.n_i / UNROLL;
+#define CMGPU_MIX_FRAME(vec_, iu)                                                             \
+    {                                                                                       \
+        const uint32_t radd = 0xffffu - (iu);                                               \
+        do_vector<8, GM_IDENTITY, true, false, false>(vec_, none, radd, kin, pin, 8);       \
+        const uint32_t xw[4] = {(vec_).x, (vec_).y, (vec_).z, (vec_).w};                    \
+        int y[2];                                                                           \
+        _Pragma("unroll") for (int m = 0; m < 2; m++) {                                     \
+            int lo = 0, hi = 0;                                                             \
+            _Pragma("unroll") for (int p = 0; p < 4; p++) {                                 \
+                lo = dp2a_lo_su(xw[p], B[m][p], lo);                                        \
+                hi = dp2a_hi_su(xw[p], B[m][p], hi);                                        \
+            }                                                                               \
+            y[m] = mix_divide((long long)hi * 256 + lo, magic, shift);                      \
+            const uint32_t mg = (uint32_t)abs(y[m]);                                        \
+            kout[m] = max(kout[m], (mg << 16) + radd);                                      \
+            pout[m] += (uint64_t)((int64_t)y[m] * y[m]);                                    \
+        }                                                                                   \
+        dst[(size_t)(iu) * 32] = ((uint32_t)y[0] & 0xffffu) | ((uint32_t)y[1] << 16);       \
+    }
+#define CMGPU_MIX_LOAD(buf, b)                                                              \
+    _Pragma("unroll") for (int u = 0; u < UNROLL; u++)                                      \
+        buf[u] = ld_stream(it.src + (size_t)((b) * UNROLL + u) * kStep);
+#define CMGPU_MIX_DO(buf, b)                                                                \
+    _Pragma("unroll") for (int u = 0; u < UNROLL; u++)                                      \
+        CMGPU_MIX_FRAME(buf[u], (b) * UNROLL + u)
+        if (nb > 0) {
+            CMGPU_MIX_LOAD(bufA, 0u)
+        }
+        for (uint32_t b = 0; b < nb; b += 2) {
+            if (b + 1 < nb) {
+                CMGPU_MIX_LOAD(bufB, b + 1)
+            }
+            CMGPU_MIX_DO(bufA, b)
+            if (b + 2 < nb) {
+                CMGPU_MIX_LOAD(bufA, b + 2)
+            }
+            if (b + 1 < nb) {
+                CMGPU_MIX_DO(bufB, b + 1)
+            }
+        }
+        for (uint32_t i = nb * UNROLL; i < it.n_i; i++) {
+            const uint4 w = ld_stream(it.src + (size_t)i * kStep);
+            CMGPU_MIX_FRAME(w, i)
+        }
+#undef CMGPU_MIX_FRAME
+#undef CMGPU_MIX_LOAD
+#undef CMGPU_MIX_DO
+
+        // input side: exactly the 8-channel epilogue (re-reads the sign from the input ring)
+        item_publish<8, 32>(ta, it, lane, 0xffffffffu, kin, pin);
+        // output side: two channels, lane = frame
+        const uint64_t pos_base = tick_pos_base(a.tick, a.tick_offset, a.pbits);
+        __syncwarp();
+        mix_publish<2>(a.meters_out + (size_t)s * 6, 2, reinterpret_cast<const volatile int16_t *>(a.out + (size_t)s * a.stride_out),
+                       pos_base, f0, lane, kout, pout);
     }
     tick_finish(a.tick, a.tick_bump);
 }
