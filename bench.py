@@ -49,6 +49,9 @@ WORKLOADS = {
     "cfg4a": dict(channels=8, streams=4096, rate=48000, frames=96000, ticks=1, ring=1, graph=False,
                   e2e_frames=9600, e2e_ticks=10,
                   desc="4,096 x 48 kHz 8-channel S16 streams x 2 s per GPU, per-channel gain + 8-channel meter (parity mode)"),
+    "cfg5x": dict(channels=2, streams=65536, rate=48000, frames=49152, ticks=1, ring=1, graph=False,
+                  e2e_frames=4800, e2e_ticks=10, strong=True,
+                  desc="DIAGNOSTIC: cfg5 with 49,152 frames per stream (stream-blocks that divide into equal work items)"),
     "cfg6ch": dict(channels=6, streams=4096, rate=48000, frames=48000, ticks=1, ring=1, graph=False,
                    e2e_frames=4800, e2e_ticks=10,
                    desc="DIAGNOSTIC: 4,096 x 48 kHz 6-channel (5.1) streams x 1 s per GPU -- a channel count that does not tile a "
