@@ -207,7 +207,10 @@ struct Tune {
 // SATPACK: saturate and pack two results with one I2IP and meter what was packed (one ALU
 // instruction per sample less; needs a few more live registers, so only the 128-register and the
 // 8-lane kernels use it -- in the 80-register stereo kernel it spills and loses 8 %).
-template <int C, int GM, bool METER, bool MASKED, bool SATPACK>
+// SIGNKEY: the in-loop peak key also carries the sample's sign in bit 0 (below the step bits, so it
+// never decides a comparison); the caller passes radd = (0x7fff - step) << 1. Used where the
+// written PCM cannot be re-read for the sign (the TMA kernel's stores are asynchronous).
+template <int C, int GM, bool METER, bool MASKED, bool SATPACK, bool SIGNKEY = false>
 __device__ __forceinline__ uint4 do_vector(uint4 w, const Recipe (&rc)[Shape<C>::kPerLane], uint32_t radd,
                                            uint32_t (&kmax)[8], uint64_t (&pacc)[Shape<C>::kPerLane], int nvalid)
 {
@@ -253,8 +256,13 @@ __device__ __forceinline__ uint4 do_vector(uint4 w, const Recipe (&rc)[Shape<C>:
         }
         if (METER) {
             const uint32_t a0 = (uint32_t)abs(m0), a1 = (uint32_t)abs(m1);
-            kmax[k0] = max(kmax[k0], (a0 << 16) + radd);
-            kmax[k1] = max(kmax[k1], (a1 << 16) + radd);
+            if (SIGNKEY) {
+                kmax[k0] = max(kmax[k0], (a0 << 16) + radd + ((uint32_t)m0 >> 31));
+                kmax[k1] = max(kmax[k1], (a1 << 16) + radd + ((uint32_t)m1 >> 31));
+            } else {
+                kmax[k0] = max(kmax[k0], (a0 << 16) + radd);
+                kmax[k1] = max(kmax[k1], (a1 << 16) + radd);
+            }
             // exact: |y| <= 32768, so y*y <= 2^30; one IMAD.WIDE with 64-bit accumulate per sample
             pacc[k0 % P] += (uint64_t)((int64_t)m0 * (int64_t)m0);
             pacc[k1 % P] += (uint64_t)((int64_t)m1 * (int64_t)m1);

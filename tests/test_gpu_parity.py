@@ -456,3 +456,46 @@ def test_opus_sized_blocks(cm, port):
     hands to opus_encode -- each stream-block is then one ready-made, contiguous encoder input."""
     run_case(cm, port, 2, 64, 2880, None, "gauss", seed=2880)
     run_case(cm, port, 1, 64, 2880, None, "gauss", seed=2881)
+
+
+@pytest.mark.parametrize("channels,block", [(2, 65536), (1, 131072 + 5), (2, 40001), (1, 200003)])
+@pytest.mark.parametrize("kind", ["ties", "full"])
+def test_tma_staged_kernel(cm, port, channels, block, kind, monkeypatch):
+    """The opt-in TMA-staged kernel (cmgpu_tma.cuh, CMGPU_TMA=1) for long mono / stereo
+    stream-blocks: ragged frame counts, a partial last vector, several ticks onto the same meter
+    window -- same bit-exact bar as the default kernel."""
+    monkeypatch.setenv("CMGPU_TMA", "1")
+    rng = np.random.default_rng(block + channels)
+    n_streams = 23
+    frames = rng.integers(0, block + 1, size=n_streams)
+    frames[0] = block
+    frames[1] = 0
+    frames[2] = block - 1
+    frames[3] = 1
+    name = run_case(cm, port, channels, n_streams, block, frames, kind, seed=block)
+    assert name == f"tma_tick<C={channels}>"
+    # several ticks into one window, in place
+    data = make_pcm(rng, kind, (3, 5, block * channels))
+    scale, gain = make_gains(rng, 5, channels)
+    with cm.Engine(channels, 5, block) as eng:
+        eng.set_gain_table(scale, gain)
+        meters = None
+        for t in range(3):
+            eng.host_slot(0)[:, : block * channels] = data[t]
+            fr = rng.integers(block // 2, block + 1, size=5).astype(np.uint32)
+            eng.set_frames(0, fr)
+            eng.submit(0)
+            eng.process(0)
+            eng.fetch(0)
+            eng.sync()
+            ref = data[t].copy()
+            meters, _ = port.batch(ref, fr, channels, scale, gain, meters=meters)
+            assert np.array_equal(eng.host_slot(0)[:, : block * channels], ref)
+        check_meters(cm, port, eng, meters, 5, channels)
+
+
+def test_tma_and_ldg_kernels_agree(cm, port, monkeypatch):
+    b = run_case(cm, port, 2, 7, 50000, None, "ties", seed=5)
+    monkeypatch.setenv("CMGPU_TMA", "1")
+    a = run_case(cm, port, 2, 7, 50000, None, "ties", seed=5)
+    assert a == "tma_tick<C=2>" and b == "fused_tick<C=2,G=32>"
