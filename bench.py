@@ -284,7 +284,7 @@ def main():
             cpu_reference_run(channels, rate, frames * ticks, budget_s=1.0)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            runs.append(cpu_reference_run(channels, rate, frames * ticks, budget_s=max(1.0, 60.0 / max(args.steps, 1))))
+            runs.append(cpu_reference_run(channels, rate, frames * ticks, budget_s=max(0.25, 45.0 / max(args.steps, 1))))
         wall = time.perf_counter() - t0
         value = float(np.mean([r["value"] for r in runs]))
         base = dict(runs[-1]); base["value"] = value
