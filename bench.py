@@ -378,6 +378,18 @@ def main():
     # meter sanity on what was just measured: K identical ticks -> K * frames frames per stream
     snap = eng.snapshot(0, min(4, streams_per_gpu))
     assert int(snap[0].frames) == (args.steps * ticks * frames if pflags & cm.METER else 0), "meter did not see every timed tick"
+    # small-buffer regime: one tick alone, device time and launch-to-complete
+    if wl["graph"]:
+        dev_us = min(eng.time_process(1, 0, 1, flags=pflags) for _ in range(20)) * 1e3
+        walls = []
+        for _ in range(20):
+            eng.sync()
+            t0 = time.perf_counter()
+            eng.process(0, pflags)
+            eng.sync()
+            walls.append((time.perf_counter() - t0) * 1e6)
+        config["single_tick"] = {"device_us": dev_us, "launch_to_complete_us": float(np.median(walls)),
+                                 "note": "one tick of the same shape issued alone, outside the timed steps"}
     kernel = eng.kernel_name()
     peak, peak_src = measured_peak()
     launches_per_step = max(1, launches // max(args.steps, 1))

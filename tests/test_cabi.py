@@ -103,3 +103,16 @@ def test_shim_harness_and_argument_checks(cm):
     shim = ShimLib()
     assert shim.lib.shimh_sizeof_result() == 192          # the reference's result struct on LP64
     assert shim.lib.shimh_null_checks() == 0
+
+
+@pytest.mark.gpu
+def test_out_of_memory_is_reported_not_survived(cm):
+    """A ring that cannot fit in HBM: NULL + COOLMIC_ERROR_NOMEM-style message, nothing falls back."""
+    lib = cm.lib()
+    ctx = lib.cmgpu_ctx_create(0, 16, 1 << 20, 64, 1 << 16, cm.NO_PINNED)      # 16 ch x 1 Mi streams x 64 slots x 2 MiB
+    assert not ctx
+    assert b"cudaMalloc" in lib.cmgpu_last_error()
+    with cm.Engine(2, 4, 16) as eng:                                              # and the library still works afterwards
+        eng.submit(0)
+        eng.process(0)
+        eng.sync()
