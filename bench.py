@@ -428,6 +428,7 @@ def main():
                 synth_block(first_stream + lo, hi - lo, channels, tick_frames, pin_in.array[t, lo:hi], t * tick_frames)
         meter_rows = None
         gathered = None
+        gather_s = [0.0]
 
         def e2e_step():
             nonlocal meter_rows, gathered
@@ -438,11 +439,14 @@ def main():
                 eng.fetch(slot, pin_out.array[t])
             eng.sync()
             if dist is not None:
+                tg = time.perf_counter()
                 gathered = gather_meters(cm, eng, dist, rank, world)
+                gather_s[0] += time.perf_counter() - tg
             meter_rows = eng.snapshot(reset=True)      # D2H of the integer meter state, then reset
 
         for _ in range(2):
             e2e_step()
+        gather_s[0] = 0.0
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -461,6 +465,7 @@ def main():
                "value": samples_per_step_rank * world * e2e_steps / wall / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": n_ticks * slot_bytes, "d2h_bytes_per_step": n_ticks * out_slot_bytes + meter_bytes,
                "steps": e2e_steps, "ms_per_step": 1e3 * wall / e2e_steps,
+               "nccl_gather_ms_per_step": (1e3 * gather_s[0] / e2e_steps) if dist is not None else None,
                "how": f"{n_ticks} ticks of {tick_frames} frames per step through a 4-slot ring, pinned host buffers, "
                       "upload/compute/download on three CUDA streams, meter snapshot (+ NCCL gather to rank 0 when N>1) per step"}
         eng.close()
