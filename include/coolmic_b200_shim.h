@@ -14,7 +14,8 @@
  * reference count; igloo_ro_ref()/igloo_ro_unref() semantics are provided by coolmic_b200_ref()
  * / coolmic_b200_unref() when the library is built stand-alone (libigloo is an external,
  * un-vendored dependency of the reference). When built into libcoolmic-dsp proper, compile the
- * csrc/host sources with -DCOOLMIC_B200_WITH_IGLOO and they use <igloo/ro.h> directly.
+ * csrc/host sources with -DCOOLMIC_B200_WITH_IGLOO: they then include the reference's own headers,
+ * are libigloo objects, and use the reference's iohandle.c (see below and INTEGRATION.md).
  *
  * The arithmetic of every read runs on the GPU (one tick of a private one-stream cmgpu context
  * per object); there is no CPU implementation behind these calls. Thousands of streams should
@@ -31,6 +32,22 @@
 extern "C" {
 #endif
 
+#ifdef COOLMIC_B200_WITH_IGLOO
+/* Integration build (the sources under csrc/host compiled INTO libcoolmic-dsp in place of
+ * src/transform.c and src/vumeter.c): no prototype of the reference's API is restated here. The
+ * reference's own headers declare it, so the compiler checks every definition in csrc/host against
+ * include/coolmic-dsp/{iohandle,transform,vumeter}.h, and objects are libigloo objects
+ * (igloo_ro_new_raw / igloo_ro_ref / igloo_ro_unref, like src/transform.c:60-81). iohandle.c stays
+ * the reference's. oracle/Makefile builds exactly this configuration into
+ * oracle/_ref/libcoolmic_dropin.so for tests/test_gpu_dropin.py. */
+#include "types_private.h"                /* reference src/types_private.h: igloo types + ro.h */
+#include <coolmic-dsp/coolmic-dsp.h>
+#include <coolmic-dsp/iohandle.h>
+#include <coolmic-dsp/transform.h>
+#include <coolmic-dsp/vumeter.h>
+typedef igloo_ro_t coolmic_b200_ro_t;
+#define COOLMIC_B200_MAX_CHANNELS COOLMIC_DSP_TRANSFORM_MAX_CHANNELS
+#else
 #ifndef COOLMIC_ERROR_NONE
 #define COOLMIC_ERROR_NONE      (0)
 #define COOLMIC_ERROR_GENERIC   (-1)
@@ -38,18 +55,14 @@ extern "C" {
 #define COOLMIC_ERROR_FAULT     (-9)
 #define COOLMIC_ERROR_INVAL     (-10)
 #define COOLMIC_ERROR_NOMEM     (-11)
+#define COOLMIC_ERROR_BUSY      (-12)
 #endif
 
 #define COOLMIC_B200_MAX_CHANNELS 16
 
-#ifdef COOLMIC_B200_WITH_IGLOO
-#include <igloo/ro.h>
-typedef igloo_ro_t coolmic_b200_ro_t;
-#else
 typedef void *coolmic_b200_ro_t;                 /* what igloo_ro_t is to callers: any object */
 int coolmic_b200_ref(coolmic_b200_ro_t object);  /* igloo_ro_ref:   0, or non-zero for NULL */
 int coolmic_b200_unref(coolmic_b200_ro_t object);/* igloo_ro_unref: frees at zero            */
-#endif
 
 typedef struct coolmic_iohandle  coolmic_iohandle_t;
 typedef struct coolmic_transform coolmic_transform_t;
@@ -85,6 +98,7 @@ int                coolmic_vumeter_reset(coolmic_vumeter_t *self);
 int                coolmic_vumeter_attach_iohandle(coolmic_vumeter_t *self, coolmic_iohandle_t *handle);
 ssize_t            coolmic_vumeter_read(coolmic_vumeter_t *self, ssize_t maxlen);
 int                coolmic_vumeter_result(coolmic_vumeter_t *self, coolmic_vumeter_result_t *result);
+#endif /* COOLMIC_B200_WITH_IGLOO */
 
 /* ---- batch mode: the same objects, many streams per GPU tick ---------------
  * A batch owns one cmgpu context for `channels`-channel streams. Its member transforms are

@@ -40,9 +40,9 @@ struct coolmic_b200_batch {
     batch_cursor_t *cursors;
 };
 
-static void batch_destroy(void *self)
+static void batch_destroy(shim_self_t self)
 {
-    coolmic_b200_batch_t *b = self;
+    coolmic_b200_batch_t *b = SHIM_SELF(self, coolmic_b200_batch_t);
     while (b->cursors) {
         batch_cursor_t *c = b->cursors;
         b->cursors = c->next;
@@ -56,13 +56,15 @@ static void batch_destroy(void *self)
     free(b->frames);
 }
 
+SHIM_TYPE(coolmic_b200_batch_t, batch_destroy);
+
 coolmic_b200_batch_t *coolmic_b200_batch_new(int device, unsigned int channels, unsigned int max_streams,
                                              unsigned int block_frames)
 {
     coolmic_b200_batch_t *b;
     if (!channels || channels > COOLMIC_B200_MAX_CHANNELS || !max_streams || !block_frames)
         return NULL;
-    b = shim_alloc(sizeof(*b), batch_destroy);
+    b = SHIM_NEW(coolmic_b200_batch_t, batch_destroy, "batch", SHIM_RO_NULL);
     if (!b)
         return NULL;
     b->channels = channels;
@@ -148,7 +150,7 @@ int coolmic_b200_batch_tick(coolmic_b200_batch_t *b)
     if (!b)
         return COOLMIC_ERROR_FAULT;
     if (coolmic_b200_batch_pending(b))
-        return -12;                                    /* COOLMIC_ERROR_BUSY: a reader has not caught up */
+        return COOLMIC_ERROR_BUSY;                     /* a reader has not caught up */
     slot = cmgpu_host_slot(b->ctx, 0);
     for (s = 0; s < b->max_streams; s++) {
         coolmic_transform_t *t = b->member[s];

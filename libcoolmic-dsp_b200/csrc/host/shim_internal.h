@@ -6,17 +6,28 @@
 #include "../../../include/coolmic_b200_shim.h"
 
 #ifdef COOLMIC_B200_WITH_IGLOO
+/* Integration build: libigloo objects, declared and allocated the way src/transform.c:60-75 does. */
+typedef igloo_ro_base_t shim_base_t;
+typedef igloo_ro_t shim_self_t;
+#define SHIM_SELF(self, T)            igloo_RO_TO_TYPE(self, T)
+#define SHIM_RO_NULL                  igloo_RO_NULL
+#define SHIM_TYPE(T, cb)              igloo_RO_PUBLIC_TYPE(T, igloo_RO_TYPEDECL_FREE(cb))
+#define SHIM_NEW(T, cb, name, assoc)  igloo_ro_new_raw(T, name, assoc)
 #define shim_ref(o)   igloo_ro_ref(o)
 #define shim_unref(o) igloo_ro_unref(o)
-#error "integration build: declare the three types with igloo_RO_PUBLIC_TYPE and allocate with igloo_ro_new_raw (INTEGRATION.md)"
 #else
 /* Stand-alone object base: reference count + destructor, first member of every object. */
 typedef struct shim_base {
     size_t refcount;
     void (*on_free)(void *self);
 } shim_base_t;
+typedef void *shim_self_t;
 
 void *shim_alloc(size_t size, void (*on_free)(void *self));
+#define SHIM_SELF(self, T)            ((T *)(self))
+#define SHIM_RO_NULL                  NULL
+#define SHIM_TYPE(T, cb)              typedef T shim_type_decl_unused_##T
+#define SHIM_NEW(T, cb, name, assoc)  ((void)(name), (void)(assoc), (T *)shim_alloc(sizeof(T), cb))
 #define shim_ref(o)   coolmic_b200_ref(o)
 #define shim_unref(o) coolmic_b200_unref(o)
 #endif

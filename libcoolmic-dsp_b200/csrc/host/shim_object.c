@@ -11,6 +11,7 @@
 static int g_device = -1;
 static uint64_t g_launches;
 
+#ifndef COOLMIC_B200_WITH_IGLOO
 void *shim_alloc(size_t size, void (*on_free)(void *self))
 {
     shim_base_t *b = calloc(1, size);
@@ -42,6 +43,7 @@ int coolmic_b200_unref(coolmic_b200_ro_t object)
     }
     return COOLMIC_ERROR_NONE;
 }
+#endif /* !COOLMIC_B200_WITH_IGLOO */
 
 int shim_device(void)
 {
@@ -63,7 +65,8 @@ int coolmic_b200_set_device(int device)
 void shim_count_launches(uint64_t n) { __atomic_add_fetch(&g_launches, n, __ATOMIC_RELAXED); }
 uint64_t coolmic_b200_shim_launches(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
-/* ---- iohandle ------------------------------------------------------------------------- */
+/* ---- iohandle (stand-alone build only; the integration build keeps the reference's iohandle.c) */
+#ifndef COOLMIC_B200_WITH_IGLOO
 struct coolmic_iohandle {
     shim_base_t base;
     void *userdata;
@@ -121,3 +124,4 @@ int coolmic_iohandle_eof(coolmic_iohandle_t *self)
         return COOLMIC_ERROR_FAULT;
     return self->eof_cb ? self->eof_cb(self->userdata) : 0;
 }
+#endif /* !COOLMIC_B200_WITH_IGLOO */

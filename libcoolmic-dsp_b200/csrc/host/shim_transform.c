@@ -11,9 +11,9 @@
 #include <stdlib.h>
 #include <string.h>
 
-static void transform_destroy(void *self)
+static void transform_destroy(shim_self_t self)
 {
-    coolmic_transform_t *t = self;
+    coolmic_transform_t *t = SHIM_SELF(self, coolmic_transform_t);
     shim_unref(t->io);
     if (t->ctx)
         cmgpu_ctx_destroy(t->ctx);
@@ -21,15 +21,16 @@ static void transform_destroy(void *self)
         shim_batch_release(t->batch, t->stream);
 }
 
+SHIM_TYPE(coolmic_transform_t, transform_destroy);
+
 coolmic_transform_t *coolmic_transform_new(const char *name, coolmic_b200_ro_t associated,
                                            uint_least32_t rate, unsigned int channels)
 {
     coolmic_transform_t *t;
-    (void)name, (void)associated;
     /* the reference indexes gain[16] with `channels` unchecked (transform.c:69-70); refuse instead */
     if (!rate || !channels || channels > COOLMIC_B200_MAX_CHANNELS)
         return NULL;
-    t = shim_alloc(sizeof(*t), transform_destroy);
+    t = SHIM_NEW(coolmic_transform_t, transform_destroy, name, associated);
     if (!t)
         return NULL;
     t->rate = rate;
@@ -190,7 +191,7 @@ coolmic_iohandle_t *coolmic_transform_get_iohandle(coolmic_transform_t *self)
         rd->cursor = self->batch ? shim_batch_cursor_new(self->batch, self->stream) : NULL;
     }
     h = rd && (!self->batch || rd->cursor)
-            ? coolmic_iohandle_new(NULL, NULL, rd, transform_release, transform_read, transform_eof) : NULL;
+            ? coolmic_iohandle_new(NULL, SHIM_RO_NULL, rd, transform_release, transform_read, transform_eof) : NULL;
     if (!h) {
         if (rd && rd->cursor)
             shim_batch_cursor_free(self->batch, rd->cursor);

@@ -12,9 +12,9 @@
 
 #include <string.h>
 
-static void vumeter_destroy(void *self)
+static void vumeter_destroy(shim_self_t self)
 {
-    coolmic_vumeter_t *v = self;
+    coolmic_vumeter_t *v = SHIM_SELF(self, coolmic_vumeter_t);
     shim_unref(v->in);
     if (v->ctx)
         cmgpu_ctx_destroy(v->ctx);
@@ -22,14 +22,15 @@ static void vumeter_destroy(void *self)
         shim_unref(v->batch);
 }
 
+SHIM_TYPE(coolmic_vumeter_t, vumeter_destroy);
+
 coolmic_vumeter_t *coolmic_vumeter_new(const char *name, coolmic_b200_ro_t associated,
                                        uint_least32_t rate, unsigned int channels)
 {
     coolmic_vumeter_t *v;
-    (void)name, (void)associated;
     if (!rate || !channels || channels > COOLMIC_B200_MAX_CHANNELS)
         return NULL;
-    v = shim_alloc(sizeof(*v), vumeter_destroy);
+    v = SHIM_NEW(coolmic_vumeter_t, vumeter_destroy, name, associated);
     if (!v)
         return NULL;
     v->rate = rate;

@@ -5,6 +5,11 @@ ctypes bindings for the two CPU checkers built by oracle/Makefile:
 * ``ref``  -- oracle/_ref/libcoolmic_ref.so: the reference's own transform.c / vumeter.c /
   tee.c / iohandle.c / snddev*.c object code behind oracle/ref_harness.c. ``None`` when the
   prebuilt file is absent and /root/reference is not there to build it from.
+* ``dropin`` -- oracle/_ref/libcoolmic_dropin.so: the same harness and the reference's own iohandle.c /
+  tee.c / snddev*.c, but with the PRODUCT's transform + vumeter host shim compiled in where
+  src/transform.c and src/vumeter.c were (oracle/Makefile). Same ``RefLib`` interface; every
+  transform / vumeter read in it runs on the GPU through the product library. It is the thing
+  being tested, not a checker. GPU tests only.
 * ``port`` -- oracle/_build/libcoolmic_port.so: our plain-C restatement (coolmic_oracle.c).
 
 May be imported only from tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs.
@@ -20,6 +25,7 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 REF_SO = HERE / "_ref" / "libcoolmic_ref.so"
+DROPIN_SO = HERE / "_ref" / "libcoolmic_dropin.so"
 PORT_SO = HERE / "_build" / "libcoolmic_port.so"
 MAX_CH = 16
 
@@ -316,6 +322,20 @@ def fnv1a64(data) -> int:
 
 _ref = None
 _port = None
+_dropin = None
+
+
+def dropin():
+    """The reference pipeline with the product's transform + vumeter dropped in, or None when
+    the prebuilt library is absent and cannot be built here."""
+    global _dropin
+    if _dropin is None:
+        if not DROPIN_SO.exists() and os.path.isdir("/root/reference/src"):
+            build()
+        if DROPIN_SO.exists():
+            _dropin = RefLib(DROPIN_SO)
+            _dropin.kind = "dropin"
+    return _dropin
 
 
 def port() -> PortLib:

@@ -105,6 +105,34 @@ def test_shim_harness_and_argument_checks(cm):
     assert shim.lib.shimh_null_checks() == 0
 
 
+def test_dropin_build_exports_the_reference_api(cm):
+    """oracle/_ref/libcoolmic_dropin.so = the reference's iohandle.c / tee.c / snddev*.c + the product's
+    transform / vumeter shim compiled against the reference's own headers (oracle/Makefile). It must
+    load, export the reference's names, and take every cmgpu_* call from the product library."""
+    import subprocess
+    from oracle import pyoracle
+    d = pyoracle.dropin()
+    if d is None:
+        pytest.skip("oracle/_ref/libcoolmic_dropin.so is not available here")
+    for name in ["coolmic_transform_new", "coolmic_transform_attach_iohandle", "coolmic_transform_get_iohandle",
+                 "coolmic_transform_set_master_gain", "coolmic_vumeter_new", "coolmic_vumeter_reset",
+                 "coolmic_vumeter_attach_iohandle", "coolmic_vumeter_read", "coolmic_vumeter_result",
+                 "coolmic_iohandle_new", "coolmic_iohandle_read", "coolmic_iohandle_eof",
+                 "coolmic_tee_new", "coolmic_tee_attach_iohandle", "coolmic_tee_get_iohandle", "coolmic_snddev_new"]:
+        assert hasattr(d.lib, name), name
+    assert d.sizeof_result() == 192
+    nm = subprocess.run(["nm", "-D", "--undefined-only", str(d.path)], capture_output=True, text=True).stdout
+    wanted = sorted(set(re.findall(r"\bU (cmgpu_[a-z_0-9]+)", nm)))
+    assert len(wanted) >= 10
+    assert all(hasattr(cm.lib(), n) for n in wanted)
+    # no GPU here: constructing the objects works (host-side), the first read that needs the device fails
+    # loudly instead of computing anything on the CPU
+    if cm.lib().cmgpu_device_count() == 0:
+        import numpy as np
+        out, results, rc = d.pipeline(np.arange(64, dtype=np.int16), 2, (2, 4, [3, 5]), result_every=0)
+        assert out.size == 0 and results[-1].get("rc") == -10
+
+
 @pytest.mark.gpu
 def test_out_of_memory_is_reported_not_survived(cm):
     """A ring that cannot fit in HBM: NULL + COOLMIC_ERROR_NOMEM-style message, nothing falls back."""
