@@ -44,8 +44,8 @@ WORKLOADS = {
                  desc="1,024 x 48 kHz stereo S16 streams x 10 s per GPU, one device ring, one fused tick per step"),
     "cfg3": dict(channels=1, streams=16384, rate=16000, frames=320, ticks=50, ring=50, graph=True,
                  e2e_frames=320, e2e_ticks=50,
-                 desc="16,384 x 16 kHz mono streams, 20 ms (320-frame, 640-byte) stream-blocks; step = 50 ticks over a "
-                      "50-slot ring (1.05 GB in+out) replayed as one CUDA graph"),
+                 desc="16,384 x 16 kHz mono streams, 20 ms (320-frame, 640-byte) stream-blocks; step = one cycle of 50 "
+                      "ticks over a 50-slot ring (1.05 GB in+out) issued as ONE span launch (cmgpu_process_cycle)"),
     "cfg4a": dict(channels=8, streams=4096, rate=48000, frames=96000, ticks=1, ring=1, graph=False,
                   e2e_frames=9600, e2e_ticks=10,
                   desc="4,096 x 48 kHz 8-channel S16 streams x 2 s per GPU, per-channel gain + 8-channel meter (parity mode)"),
@@ -269,7 +269,7 @@ def main():
     ring_bytes = 2 * ring * streams_per_gpu * frames * channels * 2
     config = {"workload": f"{args.workload}: {desc}", "streams_per_gpu": streams_per_gpu, "channels": channels,
               "rate_hz": rate, "frames_per_tick": frames, "ticks_per_step": ticks, "ring_slots": ring,
-              "cuda_graph": bool(wl["graph"]), "gains": "every stream active, scale 1000+s%9000, gain ~0.75..3.1",
+              "cycle_api": bool(wl["graph"]), "gains": "every stream active, scale 1000+s%9000, gain ~0.75..3.1",
               "l2": f"in+out rings of {ring_bytes / 1e9:.2f} GB per GPU cycled every step: far larger than the 126 MB L2, no flush needed",
               "sharding": "by stream, one process per GPU, no data-path collective"}
     if args.mode != "fused":

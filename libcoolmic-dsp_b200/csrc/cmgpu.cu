@@ -71,11 +71,11 @@ RecipeHost make_recipe(uint16_t g, uint16_t d)
 
 int recipe_eval(const RecipeHost &r, int x)
 {
-    // bit-for-bit what apply_gain<true>() does on the device, in plain integer C
+    // bit-for-bit what apply_gain<GM_MASKED>() does on the device, in plain integer C
     const int32_t X = (int32_t)((uint32_t)x * r.mul);
-    const int32_t mh = (int32_t)(((int64_t)X * (int64_t)(int32_t)r.mw) >> 32);
-    const int32_t hi = (int32_t)((uint32_t)mh + ((uint32_t)X & r.addm));
-    int32_t y = (int32_t)((uint32_t)hi + ((uint32_t)X >> 31));
+    const uint64_t add = ((uint64_t)((uint32_t)X & r.addm) << 32) | (X < 0 ? 0xffffffffull : 0ull);
+    const uint64_t acc = (uint64_t)((int64_t)X * (int64_t)(int32_t)r.mw) + add;       // wraps like the device's 64-bit add
+    int32_t y = (int32_t)(uint32_t)(acc >> 32);
     if (y > 32767)
         y = 32767;
     if (y < -32768)
@@ -161,9 +161,16 @@ namespace {
 using TickKernel = void (*)(const TickArgs);
 
 template <int C, int G>
-TickKernel fast_kernel(int gm, bool meter, bool planar)
+TickKernel fast_kernel(int gm, bool meter, bool planar, bool nc)
 {
     using namespace cmgpu;
+    if (nc && !planar) {    // separate output ring: loads through the read-only path
+        switch (gm) {
+        case GM_IDENTITY: return meter ? fused_tick<C, G, GM_IDENTITY, true, false, true> : fused_tick<C, G, GM_IDENTITY, false, false, true>;
+        case GM_ADDALL:   return meter ? fused_tick<C, G, GM_ADDALL, true, false, true> : fused_tick<C, G, GM_ADDALL, false, false, true>;
+        default:          return meter ? fused_tick<C, G, GM_MASKED, true, false, true> : fused_tick<C, G, GM_MASKED, false, false, true>;
+        }
+    }
     if (planar) {           // planes are a second output of the fused (metering) pass only
         switch (gm) {
         case GM_IDENTITY: return fused_tick<C, G, GM_IDENTITY, true, true>;
@@ -179,11 +186,11 @@ TickKernel fast_kernel(int gm, bool meter, bool planar)
 }
 
 template <int C>
-TickKernel fast_kernel_g(int g, int gm, bool meter, bool planar)
+TickKernel fast_kernel_g(int g, int gm, bool meter, bool planar, bool nc)
 {
     if (g == 8 && C != 16)
-        return fast_kernel<C, (C == 16 ? 32 : 8)>(gm, meter, planar);
-    return fast_kernel<C, 32>(gm, meter, planar);
+        return fast_kernel<C, (C == 16 ? 32 : 8)>(gm, meter, planar, nc);
+    return fast_kernel<C, 32>(gm, meter, planar, nc);
 }
 
 using GenericKernel = void (*)(const TickArgs, const int);
@@ -210,7 +217,13 @@ TickKernel tma_kernel_c(int gm, bool meter)
 }
 TickKernel tma_kernel(const cmgpu_ctx *c, int gm, bool meter)
 {
-    return c->channels == 1 ? tma_kernel_c<1>(gm, meter) : tma_kernel_c<2>(gm, meter);
+    switch (c->channels) {
+    case 1:  return tma_kernel_c<1>(gm, meter);
+    case 2:  return tma_kernel_c<2>(gm, meter);
+    case 4:  return tma_kernel_c<4>(gm, meter);
+    case 8:  return tma_kernel_c<8>(gm, meter);
+    default: return tma_kernel_c<16>(gm, meter);
+    }
 }
 
 using AnyKernel = void (*)(const TickArgs, const int, const int);
@@ -226,12 +239,13 @@ AnyKernel any_kernel(int gm, bool meter)
 
 TickKernel pick_fast(const cmgpu_ctx *c, int gm, bool meter, bool planar = false)
 {
+    const bool nc = c->d_out != nullptr;        // CMGPU_SEPARATE_OUT: the input ring is read-only for a tick
     switch (c->channels) {
-    case 1:  return fast_kernel_g<1>(c->plan_g, gm, meter, planar);
-    case 2:  return fast_kernel_g<2>(c->plan_g, gm, meter, planar);
-    case 4:  return fast_kernel_g<4>(c->plan_g, gm, meter, planar);
-    case 8:  return fast_kernel_g<8>(c->plan_g, gm, meter, planar);
-    default: return fast_kernel_g<16>(c->plan_g, gm, meter, planar);
+    case 1:  return fast_kernel_g<1>(c->plan_g, gm, meter, planar, nc);
+    case 2:  return fast_kernel_g<2>(c->plan_g, gm, meter, planar, nc);
+    case 4:  return fast_kernel_g<4>(c->plan_g, gm, meter, planar, nc);
+    case 8:  return fast_kernel_g<8>(c->plan_g, gm, meter, planar, nc);
+    default: return fast_kernel_g<16>(c->plan_g, gm, meter, planar, nc);
     }
 }
 
@@ -273,7 +287,7 @@ cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter, cud
         k<<<(unsigned)grid, cmgpu::kTmaThreads, cmgpu::kTmaSmemBytes, st>>>(t);
         return cudaGetLastError();
     }
-    const uint64_t items = (uint64_t)a.n_streams * a.items_per_block;
+    const uint64_t items = (uint64_t)a.n_streams * a.items_per_block * (a.n_ticks > 1 ? a.n_ticks : 1u);
     const uint64_t per_cta = c->plan_g > 0 ? 256u / (unsigned)c->plan_g : (c->plan_g < 0 ? 8u : 4u);
     uint64_t grid = (items + per_cta - 1) / per_cta;
     const uint64_t cap = (uint64_t)resident_ctas(c, gm, meter);
@@ -345,7 +359,7 @@ void make_plan(cmgpu_ctx *c)
     // memory with TMA bulk copies. Measured on B200: as a pure copy it beats the LDG
     // pattern (0.632 vs 0.650 ms on cfg2), fused it does not (0.684 vs 0.650 ms) -- the fused tick is
     // instruction-bound by then -- so the LDG kernel stays the default.
-    if ((C == 1 || C == 2) && nvec >= 8192 && getenv("CMGPU_TMA")) {
+    if (nvec >= 8192 && getenv("CMGPU_TMA")) {
         uint32_t tile_target = 8 * cmgpu::kTmaTileVecs;
         if (const char *e = getenv("CMGPU_TMA_ITEM_TILES"))         // tuning hook
             tile_target = (uint32_t)(strtoul(e, nullptr, 10) ? strtoul(e, nullptr, 10) : 8) * cmgpu::kTmaTileVecs;
@@ -433,8 +447,9 @@ int rebuild_classes_locked(cmgpu_ctx *c)
 
 // One tick on stream `st`. In a cycle (cmgpu_process_cycle) the ticks run concurrently: each gets
 // its place in the sequence as `tick_offset` and leaves advancing the counter to the cycle's end.
+// n_ticks > 1: a span -- ONE launch over the consecutive slots [slot, slot + n_ticks) (span_ok() says when).
 int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st = nullptr, unsigned tick_offset = 0,
-                  unsigned tick_bump = 1)
+                  unsigned tick_bump = 1, unsigned n_ticks = 1)
 {
     if (!st)
         st = c->s_cmp;
@@ -529,6 +544,9 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
     a.store = store ? 1u : 0u;
     a.planar = planar ? c->d_planar + (size_t)slot * c->planar_slot_floats : nullptr;
     a.plane_stride = (uint32_t)c->plane_stride;
+    a.n_ticks = n_ticks;
+    a.frames_stride = c->max_streams;
+    a.slot_bytes = c->slot_bytes;
     CU(launch_tick(c, a, gm, meter, st));
     c->launches++;
     return CMGPU_OK;
@@ -1195,6 +1213,23 @@ int cmgpu_time_process(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, un
     return CMGPU_OK;
 }
 
+// A cycle of the vector kernels needs no graph at all: the ring is one allocation, so ONE launch can
+// walk all its slots as a span (work items numbered (tick, stream, chunk), positions ordered by
+// tick). That turns the launch-bound small-buffer regime into the same software-pipelined stream of
+// items as a large tick. Needs the fast kernels, no float planes, and per-slot frame counts given
+// for all of the span's slots or for none.
+static bool span_ok(const cmgpu_ctx *c, unsigned first_slot, unsigned n_slots, unsigned flags)
+{
+    if (n_slots < 2 || c->plan_g <= 0 || c->tma || c->out_channels || (flags & CMGPU_PLANAR) || getenv("CMGPU_NO_SPAN"))
+        return false;
+    if ((uint64_t)n_slots * c->active * c->plan_items >= (1ull << 32))
+        return false;
+    unsigned with_frames = 0;
+    for (unsigned i = 0; i < n_slots; i++)
+        with_frames += c->has_frames[first_slot + i] ? 1u : 0u;
+    return with_frames == 0 || with_frames == n_slots;
+}
+
 static int build_cycle_locked(cmgpu_ctx *c, unsigned first_slot, unsigned n_slots, unsigned flags)
 {
     if (c->graph && c->graph_gen == c->config_gen && c->graph_first == first_slot && c->graph_n == n_slots &&
@@ -1266,7 +1301,8 @@ int cmgpu_process_cycle(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, u
         return fail(CMGPU_ERR_INVAL, "slot range out of bounds");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
-    int rc = build_cycle_locked(c, first_slot, n_slots, flags);
+    const bool span = span_ok(c, first_slot, n_slots, flags);
+    int rc = span ? CMGPU_OK : build_cycle_locked(c, first_slot, n_slots, flags);
     if (rc)
         return rc;
     // order the cycle after the uploads of its slots and before their next download
@@ -1274,8 +1310,13 @@ int cmgpu_process_cycle(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, u
         CU(cudaStreamWaitEvent(c->s_cmp, c->ev_up[first_slot + i], 0));
         CU(cudaStreamWaitEvent(c->s_cmp, c->ev_down[first_slot + i], 0));
     }
-    CU(cudaGraphLaunch(c->graph, c->s_cmp));
-    c->launches += c->graph_launches;
+    if (span) {
+        if ((rc = launch_locked(c, first_slot, flags, c->s_cmp, 0, n_slots, n_slots)))
+            return rc;
+    } else {
+        CU(cudaGraphLaunch(c->graph, c->s_cmp));
+        c->launches += c->graph_launches;
+    }
     for (unsigned i = 0; i < n_slots; i++)
         CU(cudaEventRecord(c->ev_cmp[first_slot + i], c->s_cmp));
     return CMGPU_OK;
@@ -1291,13 +1332,19 @@ int cmgpu_time_cycles(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, uns
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->s_up));
     CU(cudaStreamSynchronize(c->s_down));
-    int rc = build_cycle_locked(c, first_slot, n_slots, flags);
+    const bool span = span_ok(c, first_slot, n_slots, flags);
+    int rc = span ? upload_gains_locked(c) : build_cycle_locked(c, first_slot, n_slots, flags);
     if (rc)
         return rc;
     CU(cudaEventRecord(c->ev_t0, c->s_cmp));
     for (unsigned r = 0; r < cycles; r++) {
-        CU(cudaGraphLaunch(c->graph, c->s_cmp));
-        c->launches += c->graph_launches;
+        if (span) {
+            if ((rc = launch_locked(c, first_slot, flags, c->s_cmp, 0, n_slots, n_slots)))
+                return rc;
+        } else {
+            CU(cudaGraphLaunch(c->graph, c->s_cmp));
+            c->launches += c->graph_launches;
+        }
     }
     CU(cudaEventRecord(c->ev_t1, c->s_cmp));
     CU(cudaEventSynchronize(c->ev_t1));

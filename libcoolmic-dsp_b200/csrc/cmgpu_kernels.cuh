@@ -31,6 +31,17 @@
 #define CMGPU_MIN_CTAS_WIDE 2
 #endif
 // 8-lane-group kernels (stream-blocks of <= 1 KiB)
+#ifndef CMGPU_SATPACK_ALL
+#define CMGPU_SATPACK_ALL 1   // 0: the 80-register 1- and 2-channel kernels clamp with two VIMNMX and pack with PRMT instead of I2IP
+#endif
+#ifndef CMGPU_VEC_FENCE
+#define CMGPU_VEC_FENCE 0
+#endif
+#if CMGPU_VEC_FENCE
+#define CMGPU_VEC_FENCE_STMT asm volatile("" ::: "memory");
+#else
+#define CMGPU_VEC_FENCE_STMT
+#endif
 #ifndef CMGPU_G8_CTAS
 #define CMGPU_G8_CTAS 3
 #endif
@@ -44,8 +55,7 @@ namespace cmgpu {
 
 // Per-stream gain recipe, one row per stream (device resident, 16-byte aligned).
 // For channel c:   X  = x * mul[c]                      (mul = 2^pre, pre in 0..16)
-//                  hi = mulhi_s32(X, (int)mw[c]) + (X & addm[c])
-//                  y  = clamp16(hi + (X >>> 31))
+//                  y  = clamp16((X * (int)mw[c] + ((X & addm[c]) << 32) + (X < 0 ? 2^32 - 1 : 0)) >> 32)
 // which equals trunc(x*g/d) for every int16 x wherever the true quotient is inside the clamp
 // range and clamps identically outside (proof: DESIGN.md "Exact division"; exhaustive test:
 // tests/test_recipe.py through cmgpu_recipe_eval()).
@@ -90,17 +100,43 @@ struct TickArgs {
     uint32_t store;             // write PCM to `out` (0 only for identity streams in place)
     float *planar;              // optional second output: [stream][channel][plane_stride] float = y / 32768.f
     uint32_t plane_stride;      // floats per plane (block_frames rounded up to 4)
+    // A span: ONE launch walks n_ticks consecutive ring slots (fused_tick only; 0 or 1 = a plain tick).
+    // Work items then number (tick, stream, chunk); tick t of the span sits slot_bytes * t further
+    // into both rings and frames_stride * t further into `frames`, and takes the position base
+    // tick[0] + tick_offset + t, so the meter keys order its samples after those of tick t - 1.
+    uint32_t n_ticks;
+    uint32_t frames_stride;
+    uint64_t slot_bytes;
 };
 
 // ---- small helpers -----------------------------------------------------------------------
 
-__device__ __forceinline__ uint4 ld_stream(const uint8_t *p)
+// Streaming accesses. Measured on B200 (cfg2, tools/sweep_mode.sh): the evict-first
+// hint (.cs) costs the LOADS 1-3 % against a plain or non-coherent load, while the stores keep it.
+// `nc` = the input ring is not written by this launch (separate output ring): the read-only path
+// (LDG.E.CONSTANT) is then legal and the fastest; in place the plain load is used.
+#ifndef CMGPU_ST_HINT
+#define CMGPU_ST_HINT 0      // 0 = .cs (evict first), 1 = default
+#endif
+// Written as volatile asm with a memory clobber on purpose: where the compiler is free to move
+// them it sinks a batch of loads down to its first use (seen in SASS), which throws away the
+// prefetch distance the kernels are built around and costs up to 8 %.
+__device__ __forceinline__ uint4 ld_stream(const uint8_t *p, bool nc = false)
 {
-    return __ldcs(reinterpret_cast<const uint4 *>(p));
+    uint4 v;
+    if (nc)
+        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    else
+        asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ void st_stream(uint8_t *p, uint4 v)
 {
-    __stcs(reinterpret_cast<uint4 *>(p), v);
+#if CMGPU_ST_HINT == 0
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#else
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#endif
 }
 
 __device__ __forceinline__ uint64_t shfl_xor64(unsigned mask, uint64_t v, int off)
@@ -108,6 +144,14 @@ __device__ __forceinline__ uint64_t shfl_xor64(unsigned mask, uint64_t v, int of
     uint32_t lo = __shfl_xor_sync(mask, (uint32_t)v, off);
     uint32_t hi = __shfl_xor_sync(mask, (uint32_t)(v >> 32), off);
     return ((uint64_t)hi << 32) | lo;
+}
+
+// Hides where a value came from, so that recomputing something from it is really recomputed
+// (and its first copy does not have to stay in registers across the hot loop).
+__device__ __forceinline__ uint64_t opaque(uint64_t v)
+{
+    asm volatile("" : "+l"(v));
+    return v;
 }
 
 __device__ __forceinline__ uint64_t make_key(uint32_t mag, uint64_t pos)
@@ -149,15 +193,22 @@ struct Recipe {
 };
 
 // Returns the UNSATURATED result; callers saturate (cvt.pack.sat in the fast kernels).
+// One 64-bit multiply-add, of which only the high word is kept (IMAD.HI with a register-pair addend):
+//     y = (X * (int)mw + { hi: X or X & addm, lo: X >> 31 }) >> 32
+// The high word of the addend supplies the "+X" that a signed multiply by mw >= 2^31 misses; the low
+// word is 2^32-1 for negative X, which turns the floor of the shift into a ceiling, i.e. rounds
+// toward zero like the reference's division (X*M/2^32 is never an integer for x != 0 inside the
+// clamp range: DESIGN.md "Exact division"). Both halves of the addend come for one SHF, where a
+// separate "+ (X >>> 31)" on the high word cost an add plus a zeroed pair register per sample.
 template <int GM>
 __device__ __forceinline__ int apply_gain_raw(int x, const Recipe &r)
 {
     if (GM == GM_IDENTITY)
         return x;
     const int X = x * r.mul;
-    if (GM == GM_ADDALL)
-        return __mulhi(X, r.mw) + (X + (int)((unsigned)X >> 31));      // IMAD.HI with addend, LEA.HI
-    return __mulhi(X, r.mw) + (X & r.addm) + (int)((unsigned)X >> 31);
+    const uint32_t hi = (GM == GM_ADDALL) ? (uint32_t)X : (uint32_t)(X & r.addm);
+    const long long add = (long long)(((unsigned long long)hi << 32) | (uint32_t)(X >> 31));
+    return (int)(((long long)X * (long long)r.mw + add) >> 32);
 }
 
 template <int GM>
@@ -201,7 +252,7 @@ template <int C, int G>
 struct Tune {
     static constexpr int kUnroll = (G == 8) ? 4 : (C >= 4 ? CMGPU_UNROLL_WIDE : CMGPU_UNROLL);
     static constexpr int kMinCtas = (G == 8) ? (C >= 4 ? CMGPU_G8_CTAS_WIDE : CMGPU_G8_CTAS) : (C >= 4 ? CMGPU_MIN_CTAS_WIDE : CMGPU_MIN_CTAS);
-    static constexpr bool kSatPack = (G == 8) || (C >= 4);
+    static constexpr bool kSatPack = CMGPU_SATPACK_ALL ? true : ((G == 8) || (C >= 4));
 };
 
 // SATPACK: saturate and pack two results with one I2IP and meter what was packed (one ALU
@@ -210,7 +261,10 @@ struct Tune {
 // SIGNKEY: the in-loop peak key also carries the sample's sign in bit 0 (below the step bits, so it
 // never decides a comparison); the caller passes radd = (0x7fff - step) << 1. Used where the
 // written PCM cannot be re-read for the sign (the TMA kernel's stores are asynchronous).
-template <int C, int GM, bool METER, bool MASKED, bool SATPACK, bool SIGNKEY = false>
+// MERGE: all slots of a channel share ONE running key (kmax[channel], not kmax[slot]): equal keys of
+// one vector tie, and item_publish finds the first of them by looking at the winning vector again.
+// Fewer live registers (2 instead of 8 in the stereo kernel) and pairs of max() fold into VIMNMX3.
+template <int C, int GM, bool METER, bool MASKED, bool SATPACK, bool SIGNKEY = false, bool MERGE = false>
 __device__ __forceinline__ uint4 do_vector(uint4 w, const Recipe (&rc)[Shape<C>::kPerLane], uint32_t radd,
                                            uint32_t (&kmax)[8], uint64_t (&pacc)[Shape<C>::kPerLane], int nvalid)
 {
@@ -256,12 +310,13 @@ __device__ __forceinline__ uint4 do_vector(uint4 w, const Recipe (&rc)[Shape<C>:
         }
         if (METER) {
             const uint32_t a0 = (uint32_t)abs(m0), a1 = (uint32_t)abs(m1);
+            const int q0 = MERGE ? k0 % P : k0, q1 = MERGE ? k1 % P : k1;
             if (SIGNKEY) {
-                kmax[k0] = max(kmax[k0], (a0 << 16) + radd + ((uint32_t)m0 >> 31));
-                kmax[k1] = max(kmax[k1], (a1 << 16) + radd + ((uint32_t)m1 >> 31));
+                kmax[q0] = max(kmax[q0], (a0 << 16) + radd + ((uint32_t)m0 >> 31));
+                kmax[q1] = max(kmax[q1], (a1 << 16) + radd + ((uint32_t)m1 >> 31));
             } else {
-                kmax[k0] = max(kmax[k0], (a0 << 16) + radd);
-                kmax[k1] = max(kmax[k1], (a1 << 16) + radd);
+                kmax[q0] = max(kmax[q0], (a0 << 16) + radd);
+                kmax[q1] = max(kmax[q1], (a1 << 16) + radd);
             }
             // exact: |y| <= 32768, so y*y <= 2^30; one IMAD.WIDE with 64-bit accumulate per sample
             pacc[k0 % P] += (uint64_t)((int64_t)m0 * (int64_t)m0);
@@ -312,7 +367,8 @@ __device__ __noinline__ void store_planar(float *planar, uint32_t plane_stride, 
 // What a lane needs to know about one work item.
 struct Item {
     const uint8_t *src;      // the lane's first vector of the item
-    uint8_t *dst;
+    size_t base;             // byte offset of the item's stream-block in the rings (slot of the span included)
+    uint32_t tk;             // which tick of the span the item belongs to (0 for a plain tick)
     uint32_t s;              // stream
     uint32_t first;          // index of that vector in the stream-block
     uint32_t n_i;            // how many entirely valid vectors the lane visits
@@ -329,26 +385,34 @@ __device__ __forceinline__ bool item_setup(const TickArgs &a, uint64_t item, uin
     it.tail_valid = 0;
     it.count_frames = 0;
     it.s = 0;
+    it.tk = 0;
+    it.base = 0;
     it.first = 0;
     it.tail_vec = it.tail_step = 0;
     it.src = a.in;
-    it.dst = a.out;
     if (item >= n_items)
         return false;
-    // (the host keeps n_streams * items_per_block below 2^32: 32-bit division, none for one item per block)
+    // (the host keeps n_ticks * n_streams * items_per_block below 2^32: 32-bit divisions, none for
+    //  one item per block and a plain tick)
     const uint32_t item32 = (uint32_t)item;
-    const uint32_t s = a.items_per_block == 1 ? item32 : item32 / a.items_per_block;
-    const uint32_t chunk = item32 - s * a.items_per_block;
-    const uint32_t nfr = a.frames ? min(__ldg(a.frames + s), a.block_frames) : a.block_frames;
+    const uint32_t sv = a.items_per_block == 1 ? item32 : item32 / a.items_per_block;   // (tick, stream)
+    const uint32_t chunk = item32 - sv * a.items_per_block;
+    uint32_t tk = 0, s = sv;
+    if (a.n_ticks > 1) {
+        tk = sv / a.n_streams;
+        s = sv - tk * a.n_streams;
+    }
+    const uint32_t nfr = a.frames ? min(__ldg(a.frames + (size_t)tk * a.frames_stride + s), a.block_frames) : a.block_frames;
     const uint32_t valid_bytes = nfr * (uint32_t)(2 * C);
     const uint32_t nvec = (valid_bytes + 15u) >> 4;
     const uint32_t v0 = chunk * a.per_item;
     const uint32_t v1 = min(v0 + a.per_item, nvec);
-    const size_t base = (size_t)s * a.stride_bytes;
+    const size_t base = (size_t)tk * a.slot_bytes + (size_t)s * a.stride_bytes;
     it.s = s;
+    it.tk = tk;
+    it.base = base;
     it.first = v0 + gl;
     it.src = a.in + base + (size_t)it.first * 16;
-    it.dst = a.out + base + (size_t)it.first * 16;
     it.count_frames = (chunk == 0 && gl == 0) ? nfr : 0;
     if (v0 < v1) {
         const uint32_t vfull = min(v1, valid_bytes >> 4);        // vectors [v0, vfull) are entirely valid
@@ -388,29 +452,34 @@ __device__ __forceinline__ void load_recipes(const TickArgs &a, uint32_t s, uint
 
 // Meter epilogue of one item: widen the lane's in-loop keys to position keys, fold slots of the
 // same channel, combine the group's lanes with shuffles, publish one channel per lane.
-template <int C, int G>
+// STRIDE: vectors between a lane's consecutive steps (G in fused_tick; the consumer count in tma_tick,
+// where G is only the width of the shuffle tree).
+template <int C, int G, bool MERGE = false, int STRIDE = G>
 __device__ __forceinline__ void item_publish(const TickArgs &a, const Item &it, uint32_t gl, unsigned gmask,
                                              const uint32_t (&kmax)[8], uint64_t (&pacc)[Shape<C>::kPerLane])
 {
     constexpr int P = Shape<C>::kPerLane;
-    const uint64_t pos_base = tick_begin(a);
+    constexpr int S = (C <= 8) ? 8 / P : 1;      // slots of one channel in a vector (= frames per vector)
+    const uint64_t pos_base = tick_pos_base(a.tick, a.tick_offset + it.tk, a.pbits);
     uint64_t kc[P];
 #pragma unroll
     for (int c = 0; c < P; c++) {
         // a channel's slots c, c+P, c+2P, ... are in time order inside a vector: fold them in the
         // cheap 32-bit domain first (strict '>' keeps the earlier slot), widen only the winner
         uint32_t best = kmax[c];
-        uint32_t sub = 0;
+        uint32_t sub = 0;          // MERGE: the key is per vector; the slot is found after the reduction
+        if (!MERGE) {
 #pragma unroll
-        for (int j = 1; j < 8 / P; j++) {
-            if (kmax[c + j * P] > best) {
-                best = kmax[c + j * P];
-                sub = (uint32_t)j;
+            for (int j = 1; j < 8 / P; j++) {
+                if (kmax[c + j * P] > best) {
+                    best = kmax[c + j * P];
+                    sub = (uint32_t)j;
+                }
             }
         }
         const uint32_t mag = best >> 16;
         const uint32_t step = 0xffffu - (best & 0xffffu);
-        const uint32_t v = it.first + step * G;
+        const uint32_t v = it.first + step * STRIDE;
         // frame index of that slot of vector v inside the stream-block
         const uint32_t frame = (C <= 8) ? (v * (uint32_t)Shape<C>::kFramesPerVec8 + sub) : (v >> 1);
         kc[c] = make_key(mag, pos_base + frame);
@@ -442,9 +511,29 @@ __device__ __forceinline__ void item_publish(const TickArgs &a, const Item &it, 
             const uint64_t pos = (~(key >> 1)) & kKeyPosMask;
             const uint32_t frame = (uint32_t)(pos - pos_base);
             const volatile int16_t *y =
-                reinterpret_cast<const volatile int16_t *>(a.out + (size_t)it.s * a.stride_bytes);
-            const int yv = y[(size_t)frame * C + ch];
-            atomicMax(row + ch, (unsigned long long)(key | (yv < 0 ? 1ull : 0ull)));
+                reinterpret_cast<const volatile int16_t *>(a.out + it.base);
+            if (MERGE && S > 1) {
+                // `frame` is the first frame of the winning vector: the channel's first sample in it
+                // that has the winning magnitude is the peak (slots past the valid frames of a tail
+                // vector come after every valid one, so they can only match after it)
+                const uint32_t mag = (uint32_t)(key >> kKeyMagShift);
+                uint32_t j = 0;
+                int yv = 0;
+                bool found = false;
+#pragma unroll
+                for (int q = 0; q < S; q++) {
+                    const int v = y[((size_t)frame + q) * C + ch];
+                    if (!found && (uint32_t)abs(v) == mag) {
+                        found = true;
+                        j = (uint32_t)q;
+                        yv = v;
+                    }
+                }
+                atomicMax(row + ch, (unsigned long long)(make_key(mag, pos + j) | (yv < 0 ? 1ull : 0ull)));
+            } else {
+                const int yv = y[(size_t)frame * C + ch];
+                atomicMax(row + ch, (unsigned long long)(key | (yv < 0 ? 1ull : 0ull)));
+            }
         }
         if (pw)
             atomicAdd(row + C + ch, (unsigned long long)pw);
@@ -465,7 +554,10 @@ __device__ __forceinline__ void item_publish(const TickArgs &a, const Item &it, 
 //     register sets alternate roles, nothing is copied;
 //   * across items, the next item's recipes and first batch are requested BEFORE the current
 //     item's meter epilogue (shuffles, one dependent re-read, atomics), whose latency they hide.
-template <int C, int G, int GM, bool METER, bool PLANAR = false>
+// NC: the launch does not write its input ring (separate output ring), so the loads may take the
+// read-only path; in place they are plain loads. A compile-time choice: as a run-time flag it cost
+// the 8-channel kernel 5 %.
+template <int C, int G, int GM, bool METER, bool PLANAR = false, bool NC = false>
 __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __grid_constant__ TickArgs a)
 {
     constexpr int P = Shape<C>::kPerLane;
@@ -475,7 +567,7 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
     const uint32_t gl = threadIdx.x & (G - 1);
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(uint32_t)(G - 1)));
     const uint32_t groups_per_cta = 256 / G;
-    const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block;
+    const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block * (a.n_ticks > 1 ? a.n_ticks : 1u);
     const uint64_t stride = (uint64_t)gridDim.x * groups_per_cta;
 
     uint32_t kmax[8];
@@ -487,18 +579,22 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
     for (int c = 0; c < P; c++)
         pacc[c] = 0;
 
+    // the output ring mirrors the input ring: one uniform distance instead of a second pointer per lane
+    const ptrdiff_t out_delta = a.out - a.in;
+    constexpr bool nc = NC;
     uint4 bufA[UNROLL], bufB[UNROLL];
 #define CMGPU_LOAD_BATCH(buf, it, b)                                                    \
     _Pragma("unroll") for (int u = 0; u < UNROLL; u++)                                  \
-        buf[u] = ld_stream((it).src + (size_t)((b) * UNROLL + u) * kStep);
+        buf[u] = ld_stream((it).src + (size_t)((b) * UNROLL + u) * kStep, nc);
 #define CMGPU_DO_BATCH(buf, it, b)                                                      \
     _Pragma("unroll") for (int u = 0; u < UNROLL; u++) {                                \
         const uint32_t iu = (b) * UNROLL + u;                                           \
-        const uint4 o = do_vector<C, GM, METER, false, Tune<C, G>::kSatPack>(buf[u], rc, 0xffffu - iu, kmax, pacc, 8); \
+        const uint4 o = do_vector<C, GM, METER, false, Tune<C, G>::kSatPack, false, true>(buf[u], rc, 0xffffu - iu, kmax, pacc, 8); \
         if (a.store)                                                                    \
-            st_stream((it).dst + (size_t)iu * kStep, o);                                \
+            st_stream(dstp + (size_t)iu * kStep, o);                                    \
         if (PLANAR)                                                                     \
             store_planar<C>(a.planar, a.plane_stride, (it).s, (it).first + iu * G, o, 8); \
+        CMGPU_VEC_FENCE_STMT                                                            \
     }
 
     uint64_t item = (uint64_t)blockIdx.x * groups_per_cta + threadIdx.x / G;
@@ -510,17 +606,17 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
 #define CMGPU_LOAD_ALL(it)                                                              \
     _Pragma("unroll") for (int u = 0; u < UNROLL; u++) {                                \
         if ((uint32_t)u < (it).n_i)                                                     \
-            bufA[u] = ld_stream((it).src + (size_t)u * kStep);                          \
+            bufA[u] = ld_stream((it).src + (size_t)u * kStep, nc);                          \
         if ((uint32_t)(UNROLL + u) < (it).n_i)                                          \
-            bufB[u] = ld_stream((it).src + (size_t)(UNROLL + u) * kStep);               \
+            bufB[u] = ld_stream((it).src + (size_t)(UNROLL + u) * kStep, nc);               \
     }
 #define CMGPU_DO_ALL(buf, it, base)                                                     \
     _Pragma("unroll") for (int u = 0; u < UNROLL; u++) {                                \
         const uint32_t iu = (base) + u;                                                 \
         if (iu < (it).n_i) {                                                            \
-            const uint4 o = do_vector<C, GM, METER, false, Tune<C, G>::kSatPack>(buf[u], rc, 0xffffu - iu, kmax, pacc, 8); \
+            const uint4 o = do_vector<C, GM, METER, false, Tune<C, G>::kSatPack, false, true>(buf[u], rc, 0xffffu - iu, kmax, pacc, 8); \
             if (a.store)                                                                \
-                st_stream((it).dst + (size_t)iu * kStep, o);                            \
+                st_stream(dstp + (size_t)iu * kStep, o); \
             if (PLANAR)                                                                 \
                 store_planar<C>(a.planar, a.plane_stride, (it).s, (it).first + iu * G, o, 8); \
         }                                                                               \
@@ -534,6 +630,8 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
         }
     }
     while (have) {
+        // (opaque: otherwise ptxas re-derives the address from src at every store, 8 instructions each)
+        uint8_t *const dstp = reinterpret_cast<uint8_t *>(opaque(reinterpret_cast<uint64_t>(cur.src) + (uint64_t)out_delta));
         const uint32_t nb = (G == 8) ? 0u : cur.n_i / UNROLL;   // full batches of this lane; batch 0 is in flight
         if (G == 8) {
             CMGPU_DO_ALL(bufA, cur, 0u)
@@ -557,23 +655,27 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
 #pragma unroll
             for (int u = 0; u < UNROLL - 1; u++)
                 if (rem0 + u < cur.n_i)
-                    bufB[u] = ld_stream(cur.src + (size_t)(rem0 + u) * kStep);
+                    bufB[u] = ld_stream(cur.src + (size_t)(rem0 + u) * kStep, nc);
 #pragma unroll
             for (int u = 0; u < UNROLL - 1; u++) {
                 if (rem0 + u < cur.n_i) {
-                    const uint4 o = do_vector<C, GM, METER, false, Tune<C, G>::kSatPack>(bufB[u], rc, 0xffffu - (rem0 + u), kmax, pacc, 8);
+                    const uint4 o = do_vector<C, GM, METER, false, Tune<C, G>::kSatPack, false, true>(bufB[u], rc, 0xffffu - (rem0 + u), kmax, pacc, 8);
                     if (a.store)
-                        st_stream(cur.dst + (size_t)(rem0 + u) * kStep, o);
+                        st_stream(dstp + (size_t)(rem0 + u) * kStep, o);
                     if (PLANAR)
                         store_planar<C>(a.planar, a.plane_stride, cur.s, cur.first + (rem0 + u) * G, o, 8);
                 }
             }
         }
+        // Everything about the item that the loops above did not need (stream, tail vector, frame
+        // count) is derived again here instead of being carried through them in registers.
+        if (!PLANAR)
+            item_setup<C, G>(a, opaque(item), n_items, gl, cur);
         if (cur.tail_valid) {
             // the one vector that straddles the end of the valid frames
-            const size_t off = (size_t)cur.s * a.stride_bytes + (size_t)cur.tail_vec * 16;
-            const uint4 w = ld_stream(a.in + off);
-            const uint4 o = do_vector<C, GM, METER, true, Tune<C, G>::kSatPack>(w, rc, 0xffffu - cur.tail_step, kmax, pacc, cur.tail_valid);
+            const size_t off = cur.base + (size_t)cur.tail_vec * 16;
+            const uint4 w = ld_stream(a.in + off, nc);
+            const uint4 o = do_vector<C, GM, METER, true, Tune<C, G>::kSatPack, false, true>(w, rc, 0xffffu - cur.tail_step, kmax, pacc, cur.tail_valid);
             if (a.store)
                 st_stream(a.out + off, o);
             if (PLANAR)
@@ -594,7 +696,7 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
             }
         }
         if (METER) {
-            item_publish<C, G>(a, cur, gl, gmask, kmax, pacc);
+            item_publish<C, G, true>(a, cur, gl, gmask, kmax, pacc);
 #pragma unroll
             for (int k = 0; k < 8; k++)
                 kmax[k] = 0;

@@ -248,10 +248,11 @@ __global__ void __launch_bounds__(256, 2) mix8to2_tick(const __grid_constant__ M
 
         Item it;
         it.s = s;
+        it.tk = 0;
+        it.base = (size_t)s * a.stride_in;
         it.first = f0 + lane;
         it.n_i = it.first < f1 ? (f1 - it.first + 31u) / 32u : 0u;
         it.src = a.in + (size_t)s * a.stride_in + (size_t)it.first * 16;
-        it.dst = nullptr;
         it.tail_vec = it.tail_step = 0;
         it.tail_valid = 0;
         it.count_frames = (chunk == 0 && lane == 0) ? nfr : 0;

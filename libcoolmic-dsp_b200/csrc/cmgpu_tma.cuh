@@ -1,26 +1,29 @@
-// cmgpu_tma.cuh -- the fused tick for long mono / stereo stream-blocks, staged through shared
-// memory with TMA bulk copies (cp.async.bulk, SASS UBLKCP).
+// cmgpu_tma.cuh -- the fused tick with its loads staged through shared memory by TMA bulk copies
+// (cp.async.bulk global -> shared, SASS UBLKCP) and its stores written straight from registers.
 //
-// Why it exists: a plain device copy reaches 6.10 TB/s with the batched-LDG pattern of fused_tick,
-// 6.47 TB/s with 16 KiB TMA bulk tiles and 6.55 TB/s with cudaMemcpy (tools/copy_probe.cu on this
-// B200); the LDG kernel already sits on the first number, so only a different way of moving the
-// bytes could lift it further.
-// What was measured (cfg2): in copy mode this kernel is faster than fused_tick
-// (0.632-0.647 ms vs 0.650), with gain + meter it is slower (0.684 vs 0.650): by then the tick is
-// bound by instruction issue, and this design adds a sign op per sample, LDS/STS and per-tile
-// barrier traffic, and makes all 8 consumer warps wait on the same tile. It is therefore OPT-IN
-// (CMGPU_TMA=1), kept bit-exact by the same tests, as the starting point for round 2.
+// Why it exists. fused_tick keeps its loads in flight in registers: one batch of 4 vectors per lane,
+// 48 KiB per SM at 24 warps. ncu shows what that costs (profiles/): 38 % of warp-cycles wait on the
+// first use of a batch (long_scoreboard) and the tick sits at the copy rate of that access pattern;
+// making the per-sample code SHORTER made the tick slower, not faster -- the bytes in flight, not the
+// instructions, set the pace. Registers cannot hold more; shared memory can: here a ring of
+// CMGPU_TMA_STAGES x 16 KiB tiles per CTA (192 KiB per SM) is kept full by one producer thread, and
+// the consumer warps never wait on global memory at all.
 //
-// One CTA = 8 consumer warps + 1 producer warp (one elected thread). The producer walks the CTA's
-// work items (stream, chunk) tile by tile: 16 KiB bulk load global -> shared into a 4-slot ring
-// (mbarrier complete_tx), and, once the consumers have finished a slot, bulk store shared -> global
-// of the transformed tile. The consumers take a slot when its barrier flips, each thread owning 4 of
-// the tile's 1,024 vectors (conflict-free LDS.128 / STS.128), run the same per-sample code as
-// fused_tick in place in shared memory, fence to the async proxy and arrive on the slot's
-// "consumed" barrier. Meter state stays in registers across an item's tiles; at the item's end the
-// warps combine through shuffles and a small shared array, and one thread per channel issues the
-// atomics. Because the stores are asynchronous the winner's sign cannot be re-read from memory: it
-// rides in bit 0 of the in-loop key instead (do_vector<SIGNKEY>).
+// One CTA = NW consumer warps + 1 producer warp (one elected thread).
+//   producer   walks the CTA's work items (stream, chunk of per_item vectors) tile by tile: waits for
+//              the slot's `empty` barrier (every consumer warp has read the previous tile out of it),
+//              arms `full` with the tile's byte count and issues ONE bulk load.
+//   consumers  wait for `full`, pull their CMGPU_TMA_VPT vectors of the tile into registers
+//              (conflict-free LDS.128: thread t owns vectors t, t+256, ...), release the slot at once
+//              (one arrive per warp), then run the same per-sample code as fused_tick
+//              (do_vector) and write the result with coalesced 128-bit streaming stores.
+// Meter state stays in registers across the tiles of an item; at its end every warp publishes its
+// own partial result with the shuffle tree + atomics of fused_tick (item_publish): position keys
+// make the merge exact in any order. Nothing is written back to shared memory, so there is no
+// proxy fence and no bulk store to wait for. The next item's recipes are fetched one item ahead.
+//
+// The first version of this file (round 1, in-place in shared memory + bulk stores, 4 x 16 KiB) is in
+// the history: 0.684 ms fused on cfg2 against 0.650 for fused_tick; DESIGN.md 4.6 has both.
 #pragma once
 
 #include "cmgpu_kernels.cuh"
@@ -34,10 +37,10 @@ namespace cmgpu {
 #define CMGPU_TMA_VPT 4         // vectors of a tile each consumer thread owns
 #endif
 #ifndef CMGPU_TMA_STAGES
-#define CMGPU_TMA_STAGES 4      // tiles in the shared-memory ring
+#define CMGPU_TMA_STAGES 6      // tiles in the shared-memory ring
 #endif
 #ifndef CMGPU_TMA_CTAS
-#define CMGPU_TMA_CTAS 3        // resident CTAs per SM the kernel is compiled for
+#define CMGPU_TMA_CTAS 2        // resident CTAs per SM the kernel is compiled for
 #endif
 constexpr int kTmaStages = CMGPU_TMA_STAGES;
 constexpr int kTmaConsumerWarps = CMGPU_TMA_NW;
@@ -73,15 +76,12 @@ __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint3
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void bulk_store(void *dst, const void *src_smem, uint32_t bytes)
+__device__ __forceinline__ uint4 lds128(const void *p)
 {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+    return v;
 }
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kTmaConsumers) : "memory"); }
 
 // The geometry of one work item, computed identically by producer and consumers.
 struct TmaItem {
@@ -106,11 +106,10 @@ __device__ __forceinline__ TmaItem tma_item(const TickArgs &a, uint64_t item)
 template <int C, int GM, bool METER>
 __global__ void __launch_bounds__(kTmaThreads, CMGPU_TMA_CTAS) tma_tick(const __grid_constant__ TickArgs a)
 {
-    static_assert(C == 1 || C == 2, "tma_tick: mono and stereo");
     constexpr int P = Shape<C>::kPerLane;
+    constexpr bool kSat = C >= 4;
     extern __shared__ __align__(128) uint8_t ring[];
-    __shared__ uint64_t full[kTmaStages], consumed[kTmaStages];
-    __shared__ unsigned long long red_key[2][kTmaConsumerWarps][2], red_pow[2][kTmaConsumerWarps][2];
+    __shared__ uint64_t full[kTmaStages], empty[kTmaStages];
 
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5, lane = tid & 31u;
@@ -119,7 +118,7 @@ __global__ void __launch_bounds__(kTmaThreads, CMGPU_TMA_CTAS) tma_tick(const __
     if (tid == 0) {
         for (int s = 0; s < kTmaStages; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&consumed[s], kTmaConsumers);
+            mbar_init(&empty[s], kTmaConsumerWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -128,41 +127,23 @@ __global__ void __launch_bounds__(kTmaThreads, CMGPU_TMA_CTAS) tma_tick(const __
     if (warp == kTmaConsumerWarps) {
         // ---------------------------------------------------------------- producer (one thread)
         if (lane == 0) {
-            uint8_t *pend_dst[kTmaStages];
-            uint32_t pend_bytes[kTmaStages];
             uint32_t k = 0;
             for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const TmaItem it = tma_item<C>(a, item);
-                const size_t base = (size_t)it.s * a.stride_bytes;
+                const uint8_t *src = a.in + (size_t)it.s * a.stride_bytes;
                 for (uint32_t t = 0; t < it.ntile; t++, k++) {
                     const uint32_t slot = k % kTmaStages;
                     const uint32_t tv0 = it.v0 + t * kTmaTileVecs;
                     const uint32_t bytes = min((uint32_t)kTmaTileVecs, it.v1 - tv0) * 16u;
-                    if (k >= kTmaStages) {
-                        // the tile that used this slot: wait for the consumers, send it home, free the slot
-                        mbar_wait(&consumed[slot], (k / kTmaStages - 1) & 1u);
-                        if (a.store) {
-                            bulk_store(pend_dst[slot], ring + (size_t)slot * kTmaTileBytes, pend_bytes[slot]);
-                            bulk_wait_read_all();
-                        }
-                    }
-                    pend_dst[slot] = a.out + base + (size_t)tv0 * 16;
-                    pend_bytes[slot] = bytes;
+                    if (k >= kTmaStages)          // every consumer warp has read the slot's previous tile
+                        mbar_wait(&empty[slot], (k / kTmaStages - 1) & 1u);
                     mbar_expect_tx(&full[slot], bytes);
-                    bulk_load(ring + (size_t)slot * kTmaTileBytes, a.in + base + (size_t)tv0 * 16, bytes, &full[slot]);
+                    bulk_load(ring + (size_t)slot * kTmaTileBytes, src + (size_t)tv0 * 16, bytes, &full[slot]);
                 }
             }
-            // drain: the last min(k, stages) tiles are still in their slots
-            for (uint32_t j = k > kTmaStages ? k - kTmaStages : 0; j < k; j++) {
-                const uint32_t slot = j % kTmaStages;
-                mbar_wait(&consumed[slot], (j / kTmaStages) & 1u);
-                if (a.store)
-                    bulk_store(pend_dst[slot], ring + (size_t)slot * kTmaTileBytes, pend_bytes[slot]);
-            }
-            bulk_wait_all();
         }
     } else {
-        // ---------------------------------------------------------------- consumers (8 warps)
+        // ---------------------------------------------------------------- consumers
         uint32_t kmax[8];
         uint64_t pacc[P];
 #pragma unroll
@@ -171,103 +152,84 @@ __global__ void __launch_bounds__(kTmaThreads, CMGPU_TMA_CTAS) tma_tick(const __
 #pragma unroll
         for (int c = 0; c < P; c++)
             pacc[c] = 0;
-        uint32_t k = 0, par = 0;
-        for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const TmaItem it = tma_item<C>(a, item);
-            Recipe rc[P];
-            load_recipes<C, GM>(a, it.s, 0, rc);
+        uint32_t k = 0;
+        uint64_t item = blockIdx.x;
+        Recipe rc[P], rcn[P];
+        TmaItem it;
+        if (item < n_items) {
+            it = tma_item<C>(a, item);
+            load_recipes<C, GM>(a, it.s, tid, rc);
+        }
+        while (item < n_items) {
+            // the next item's stream and recipes, one item ahead of their use
+            const uint64_t item_n = item + gridDim.x;
+            TmaItem itn;
+            if (item_n < n_items) {
+                itn = tma_item<C>(a, item_n);
+                load_recipes<C, GM>(a, itn.s, tid, rcn);
+            }
+            const size_t base = (size_t)it.s * a.stride_bytes;
+            uint8_t *const dst = a.out + base + ((size_t)it.v0 + tid) * 16;
             for (uint32_t t = 0; t < it.ntile; t++, k++) {
                 const uint32_t slot = k % kTmaStages;
-                uint8_t *tile = ring + (size_t)slot * kTmaTileBytes;
+                const uint8_t *tile = ring + (size_t)slot * kTmaTileBytes;
                 const uint32_t tv0 = it.v0 + t * kTmaTileVecs;
                 const uint32_t nv = min((uint32_t)kTmaTileVecs, it.v1 - tv0);
                 // the block's very last vector may straddle the end of the valid frames
                 const bool partial = ((tv0 + nv) << 4) > it.valid_bytes;
                 const uint32_t nfull = partial ? nv - 1 : nv;
                 mbar_wait(&full[slot], (k / kTmaStages) & 1u);
+                uint4 vbuf[kTmaVecsPerThread];
 #pragma unroll
                 for (int u = 0; u < kTmaVecsPerThread; u++) {
                     const uint32_t vi = (uint32_t)u * kTmaConsumers + tid;
+                    if (vi < nv)
+                        vbuf[u] = lds128(tile + (size_t)vi * 16);
+                }
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(&empty[slot]);         // the slot may be refilled while we compute
+#pragma unroll
+                for (int u = 0; u < kTmaVecsPerThread; u++) {
+                    const uint32_t vi = (uint32_t)u * kTmaConsumers + tid;
+                    const uint32_t step = t * kTmaVecsPerThread + (uint32_t)u;
                     if (vi < nfull) {
-                        const uint32_t radd = (0x7fffu - (t * kTmaVecsPerThread + (uint32_t)u)) << 1;
-                        uint4 *p = reinterpret_cast<uint4 *>(tile + (size_t)vi * 16);
-                        const uint4 o = do_vector<C, GM, METER, false, true, true>(*p, rc, radd, kmax, pacc, 8);
+                        const uint4 o = do_vector<C, GM, METER, false, kSat, false, true>(vbuf[u], rc, 0xffffu - step, kmax, pacc, 8);
                         if (a.store)
-                            *p = o;
+                            st_stream(dst + (size_t)step * (kTmaConsumers * 16), o);
+                    } else if (partial && vi == nv - 1) {
+                        const int nvalid = (int)((it.valid_bytes - ((tv0 + vi) << 4)) >> 1);
+                        const uint4 o = do_vector<C, GM, METER, true, kSat, false, true>(vbuf[u], rc, 0xffffu - step, kmax, pacc, nvalid);
+                        if (a.store)
+                            st_stream(dst + (size_t)step * (kTmaConsumers * 16), o);
                     }
                 }
-                if (partial && ((nv - 1) % kTmaConsumers) == tid) {
-                    const uint32_t vi = nv - 1, u = vi / kTmaConsumers;
-                    const uint32_t radd = (0x7fffu - (t * kTmaVecsPerThread + u)) << 1;
-                    const int nvalid = (int)((it.valid_bytes - ((tv0 + vi) << 4)) >> 1);
-                    uint4 *p = reinterpret_cast<uint4 *>(tile + (size_t)vi * 16);
-                    const uint4 o = do_vector<C, GM, METER, true, true, true>(*p, rc, radd, kmax, pacc, nvalid);
-                    if (a.store)
-                        *p = o;
-                }
-                fence_async_proxy();          // generic-proxy writes -> visible to the bulk store
-                mbar_arrive(&consumed[slot]);
             }
-            if (!METER)
-                continue;
-            // ---- item epilogue: lane -> warp (shuffles) -> CTA (shared) -> one atomic per channel
-            const uint64_t pos_base = tick_begin(a);
-            uint64_t kc[P];
+            if (METER) {
+                // ---- item epilogue, per warp: shuffle tree, one lane per channel issues the atomics
+                Item pub;
+                pub.src = nullptr;
+                pub.base = base;
+                pub.tk = 0;
+                pub.s = it.s;
+                pub.first = it.v0 + tid;
+                pub.n_i = 0;
+                pub.tail_vec = pub.tail_step = 0;
+                pub.tail_valid = 0;
+                pub.count_frames = (it.chunk == 0 && tid == 0) ? it.nfr : 0;
+                item_publish<C, 32, true, kTmaConsumers>(a, pub, lane, 0xffffffffu, kmax, pacc);
 #pragma unroll
-            for (int c = 0; c < P; c++) {
-                uint32_t best = kmax[c];
-                uint32_t sub = 0;
+                for (int q = 0; q < 8; q++)
+                    kmax[q] = 0;
 #pragma unroll
-                for (int j = 1; j < 8 / P; j++) {
-                    // compare without the sign bit: an equal key in a later slot must not win
-                    if ((kmax[c + j * P] >> 1) > (best >> 1)) {
-                        best = kmax[c + j * P];
-                        sub = (uint32_t)j;
-                    }
-                }
-                const uint32_t mag = best >> 16;
-                const uint32_t step = 0x7fffu - ((best >> 1) & 0x7fffu);
-                const uint32_t v = it.v0 + (step / kTmaVecsPerThread) * kTmaTileVecs + (step % kTmaVecsPerThread) * kTmaConsumers + tid;
-                const uint32_t frame = v * (uint32_t)Shape<C>::kFramesPerVec8 + sub;
-                kc[c] = mag ? (make_key(mag, pos_base + frame) | (uint64_t)(best & 1u)) : 0ull;
+                for (int c = 0; c < P; c++)
+                    pacc[c] = 0;
             }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-#pragma unroll
-                for (int c = 0; c < P; c++) {
-                    kc[c] = max(kc[c], shfl_xor64(0xffffffffu, kc[c], off));
-                    pacc[c] += shfl_xor64(0xffffffffu, pacc[c], off);
-                }
-            }
-            if (lane == 0) {
-#pragma unroll
-                for (int c = 0; c < P; c++) {
-                    red_key[par][warp][c] = kc[c];
-                    red_pow[par][warp][c] = pacc[c];
-                }
-            }
-            consumer_barrier();
-            if (tid < (uint32_t)C) {
-                unsigned long long key = 0, pw = 0;
-                for (int w = 0; w < kTmaConsumerWarps; w++) {
-                    key = max(key, red_key[par][w][tid]);
-                    pw += red_pow[par][w][tid];
-                }
-                unsigned long long *row = a.meters + (size_t)it.s * a.row_u64;
-                if (key)
-                    atomicMax(row + tid, key);
-                if (pw)
-                    atomicAdd(row + C + tid, pw);
-                if (tid == 0 && it.chunk == 0 && it.nfr)
-                    atomicAdd(row + 2 * C, (unsigned long long)it.nfr);
-            }
-            par ^= 1;                 // the next item writes the other half of the scratch
-#pragma unroll
-            for (int q = 0; q < 8; q++)
-                kmax[q] = 0;
+            item = item_n;
+            it = itn;
 #pragma unroll
             for (int c = 0; c < P; c++)
-                pacc[c] = 0;
+                rc[c] = rcn[c];
         }
     }
     tick_end(a);

@@ -362,25 +362,39 @@ def test_full_size_config2_properties(cm, port):
             assert int(snap[s].frames) == block
 
 
-def test_graph_cycle_equals_individual_ticks(cm, port):
-    """cmgpu_process_cycle replays a ring's ticks as one CUDA graph. Every replay must see a fresh
-    tick number (it lives on the device), otherwise an equal magnitude from a later replay could
-    steal the peak. Same result as issuing the ticks one by one, and as the oracle."""
-    rng = np.random.default_rng(77)
-    channels, n_streams, block, ring, cycles = 1, 301, 320, 5, 3
+@pytest.mark.parametrize("channels,block,ragged,no_span", [
+    (1, 320, False, False), (1, 320, False, True), (1, 320, True, False), (2, 4799, False, False),
+    (2, 20000, True, False), (8, 257, False, False), (16, 100, True, False), (4, 333, False, True), (6, 500, False, False)])
+def test_cycle_equals_individual_ticks(cm, port, monkeypatch, channels, block, ragged, no_span):
+    """cmgpu_process_cycle runs a ring's ticks as ONE launch over all slots (a span: work items
+    numbered (tick, stream, chunk)) or, for the kernels that cannot (6 channels here) and with
+    CMGPU_NO_SPAN, as one CUDA graph of per-tick launches. Either way every tick must get its own
+    place in the position order, and every replay a fresh one (the tick number lives on the device),
+    otherwise an equal magnitude from a later tick could steal the peak. Same result as issuing the
+    ticks one by one, and as the oracle."""
+    rng = np.random.default_rng(77 + channels + block)
+    n_streams, ring, cycles = 301 if block < 1000 else 23, 5, 3
     data = make_pcm(rng, "ties", (ring, n_streams, block * channels))
     # slot 0 opens with +100 everywhere, later slots repeat the magnitude with the other sign
     data[:, :7, :] = 0
     data[0, :7, 0] = 100
-    data[1:, :7, 3] = -100
+    data[1:, :7, 3 * channels] = -100
     scale, gain = make_gains(rng, n_streams, channels)
     scale[:7] = 0
+    frames = np.full((ring, n_streams), block, np.uint32)
+    if ragged:
+        frames = rng.integers(0, block + 1, size=(ring, n_streams)).astype(np.uint32)
+        frames[:, :7] = block
+    if no_span:
+        monkeypatch.setenv("CMGPU_NO_SPAN", "1")
     results = []
     for mode in ("cycle", "single"):
         with cm.Engine(channels, n_streams, block, ring_slots=ring) as eng:
             eng.set_gain_table(scale, gain)
             for slot in range(ring):
                 eng.host_slot(slot)[:, : block * channels] = data[slot]
+                if ragged:
+                    eng.set_frames(slot, frames[slot])
                 eng.submit(slot)
             for _ in range(cycles):
                 if mode == "cycle":
@@ -394,21 +408,22 @@ def test_graph_cycle_equals_individual_ticks(cm, port):
             outs = [eng.host_slot(slot)[:, : block * channels].copy() for slot in range(ring)]
             snap = eng.snapshot()
             results.append((outs, [cm.state_dict(snap[s], channels) for s in range(n_streams)]))
-            assert eng.launch_count() >= ring * cycles
+            spans = mode == "cycle" and not no_span and channels != 6
+            assert eng.launch_count() == (cycles if spans else ring * cycles)
     # oracle: the in-place ring is transformed again on every cycle
     meters = None
     work = data.copy()
-    frames = np.full(n_streams, block, np.uint32)
     for _ in range(cycles):
         for slot in range(ring):
-            meters, _ = port.batch(work[slot], frames, channels, scale, gain, meters=meters)
+            meters, _ = port.batch(work[slot], frames[slot], channels, scale, gain, meters=meters)
     for outs, states in results:
         for slot in range(ring):
             assert np.array_equal(outs[slot], work[slot])
         for s in range(n_streams):
             assert states[s]["frames"] == int(meters[s].frames)
-            assert states[s]["power"][0] == int(meters[s].power[0])
-            assert states[s]["channel_peak"][0] == int(meters[s].channel_peak[0]), f"stream {s}"
+            for c in range(channels):
+                assert states[s]["power"][c] == int(meters[s].power[c])
+                assert states[s]["channel_peak"][c] == int(meters[s].channel_peak[c]), f"stream {s} channel {c}"
             assert states[s]["global_peak"] == int(meters[s].global_peak)
     assert all(results[0][1][s]["channel_peak"][0] == 100 for s in range(7))
 
@@ -458,12 +473,13 @@ def test_opus_sized_blocks(cm, port):
     run_case(cm, port, 1, 64, 2880, None, "gauss", seed=2881)
 
 
-@pytest.mark.parametrize("channels,block", [(2, 65536), (1, 131072 + 5), (2, 40001), (1, 200003)])
+@pytest.mark.parametrize("channels,block", [(2, 65536), (1, 131072 + 5), (2, 40001), (1, 200003), (4, 32768 + 3),
+                                            (8, 16384 + 77), (16, 8192 + 5)])
 @pytest.mark.parametrize("kind", ["ties", "full"])
 def test_tma_staged_kernel(cm, port, channels, block, kind, monkeypatch):
-    """The opt-in TMA-staged kernel (cmgpu_tma.cuh, CMGPU_TMA=1) for long mono / stereo
-    stream-blocks: ragged frame counts, a partial last vector, several ticks onto the same meter
-    window -- same bit-exact bar as the default kernel."""
+    """The TMA-staged kernel (cmgpu_tma.cuh, CMGPU_TMA=1: bulk loads into a shared-memory ring,
+    stores straight from registers) for long stream-blocks: ragged frame counts, a partial last
+    vector, several ticks onto the same meter window -- same bit-exact bar as the default kernel."""
     monkeypatch.setenv("CMGPU_TMA", "1")
     rng = np.random.default_rng(block + channels)
     n_streams = 23

@@ -1,0 +1,8 @@
+#!/bin/bash
+# TMA kernel geometry / mode sweep: tools/sweep_tma.sh "<libs>" "<modes>" <workload>
+libs=${1:-"cur"}; modes=${2:-"fused"}; w=${3:-cfg2}
+export CMGPU_TMA=1
+for lib in $libs; do
+  if [ $lib = cur ]; then unset CMGPU_LIB; else export CMGPU_LIB=$PWD/libcoolmic-dsp_b200/lib/exp/$lib.so; fi
+  for m in $modes; do timeout 120 python bench.py --workload $w --mode $m --steps 40 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$lib', '$w', '$m', round(d['ms_per_step'],4), round(d['roofline']['frac'],4), d['roofline']['kernel'])"; done
+done
