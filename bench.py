@@ -40,14 +40,14 @@ WORKLOADS = {
     # device-timed run: `ticks` ticks of `frames` frames over a ring of `ring` slots per step
     # (graph=True: the ring's ticks replayed as one CUDA graph launch); e2e: `e2e_ticks` ticks of `e2e_frames`
     "cfg2": dict(channels=2, streams=1024, rate=48000, frames=480000, ticks=1, ring=1, graph=False,
-                 e2e_frames=48000, e2e_ticks=10,
+                 e2e_frames=12000, e2e_ticks=40,
                  desc="1,024 x 48 kHz stereo S16 streams x 10 s per GPU, one device ring, one fused tick per step"),
     "cfg3": dict(channels=1, streams=16384, rate=16000, frames=320, ticks=50, ring=50, graph=True,
                  e2e_frames=320, e2e_ticks=50,
                  desc="16,384 x 16 kHz mono streams, 20 ms (320-frame, 640-byte) stream-blocks; step = one cycle of 50 "
                       "ticks over a 50-slot ring (1.05 GB in+out) issued as ONE span launch (cmgpu_process_cycle)"),
     "cfg4a": dict(channels=8, streams=4096, rate=48000, frames=96000, ticks=1, ring=1, graph=False,
-                  e2e_frames=9600, e2e_ticks=10,
+                  e2e_frames=2400, e2e_ticks=40,
                   desc="4,096 x 48 kHz 8-channel S16 streams x 2 s per GPU, per-channel gain + 8-channel meter (parity mode)"),
     "cfg5x": dict(channels=2, streams=65536, rate=48000, frames=49152, ticks=1, ring=1, graph=False,
                   e2e_frames=4800, e2e_ticks=10, strong=True,
@@ -431,26 +431,32 @@ def main():
         gather_s = [0.0]
 
         def e2e_step():
+            # Upload, tick and download of every tick are queued on the engine's three streams; the
+            # step's meter state is read as soon as its last tick has run (the snapshot waits for the
+            # compute stream only), so the downloads of this step's last ticks overlap the uploads of
+            # the next step's first ones. Everything is drained (eng.sync) before the clock stops.
             nonlocal meter_rows, gathered
             for t in range(n_ticks):
                 slot = t % 4
                 eng.submit(slot, pin_in.array[t])
                 eng.process(slot)
                 eng.fetch(slot, pin_out.array[t])
-            eng.sync()
+            meter_rows = eng.snapshot(reset=dist is None)       # D2H of the integer meter state (+ reset)
             if dist is not None:
                 tg = time.perf_counter()
                 gathered = gather_meters(cm, eng, dist, rank, world)
                 gather_s[0] += time.perf_counter() - tg
-            meter_rows = eng.snapshot(reset=True)      # D2H of the integer meter state, then reset
+                eng.reset_meters()
 
         for _ in range(2):
             e2e_step()
+        eng.sync()
         gather_s[0] = 0.0
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             e2e_step()
+        eng.sync()
         barrier()
         wall = max_over_ranks(time.perf_counter() - t0)
         assert int(meter_rows[0].frames) == tick_frames * n_ticks
@@ -467,7 +473,8 @@ def main():
                "steps": e2e_steps, "ms_per_step": 1e3 * wall / e2e_steps,
                "nccl_gather_ms_per_step": (1e3 * gather_s[0] / e2e_steps) if dist is not None else None,
                "how": f"{n_ticks} ticks of {tick_frames} frames per step through a 4-slot ring, pinned host buffers, "
-                      "upload/compute/download on three CUDA streams, meter snapshot (+ NCCL gather to rank 0 when N>1) per step"}
+                      "upload/compute/download on three CUDA streams, meter snapshot (+ NCCL gather to rank 0 when N>1) per step; "
+                      "steps are queued back to back and drained before the clock stops"}
         eng.close()
         pin_in.free(); pin_out.free()
 
@@ -563,7 +570,7 @@ def gather_meters(cm, eng, dist, rank, world):
     import torch
     mine = cm.sharding.wrap_device_rows(eng.device_meters(), eng.max_streams * eng.meter_row_u64())
     out = cm.sharding.gather_rows(mine, dist, rank, world)
-    torch.cuda.synchronize()
+    torch.cuda.current_stream().synchronize()       # the gather only: the engine's copy streams keep running
     return out
 
 

@@ -127,6 +127,11 @@ struct cmgpu_ctx {
 
     cudaStream_t s_up = nullptr, s_cmp = nullptr, s_down = nullptr;
     std::vector<cudaEvent_t> ev_up, ev_cmp, ev_down;
+    // Cross-stream ordering is queued only where it orders something: a tick waits for a slot's upload /
+    // download only if one was issued since the slot's last tick, and a slot's "ticks done" event is
+    // recorded when an upload or download first asks for it. Back-to-back ticks on resident data are
+    // then back-to-back kernel launches, which is what lets them overlap (launch_begin).
+    std::vector<uint8_t> up_pending, down_pending, cmp_unrecorded;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     std::mutex mu;
 
@@ -139,6 +144,11 @@ struct cmgpu_ctx {
     unsigned graph_first = 0, graph_n = 0, graph_flags = 0;
     uint64_t graph_launches = 0;                   // kernel nodes in the cached graph
     uint64_t config_gen = 0, graph_gen = ~0ull;    // bumped whenever launch arguments may change
+    // tick numbering: ticks issued by plain / span launches since the device counter was last bumped
+    uint32_t pending_ticks = 0;
+    // slots of the previous tick launch on s_cmp (~0u: something else was queued since), for the
+    // overlap rule of programmatic dependent launch
+    unsigned last_first = ~0u, last_n = 0;
 
     // how many active streams need which gain mode; the tick runs in the cheapest common one
     unsigned n_mode[3] = {0, 0, 0};                // GM_IDENTITY / GM_MASKED / GM_ADDALL
@@ -264,7 +274,24 @@ int resident_ctas(cmgpu_ctx *c, int gm, bool meter)
     return cap;
 }
 
-cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter, cudaStream_t st)
+// `pdl`: the launch may start while the previous launch of the stream is still draining
+// (programmatic dependent launch; the kernels' launch_begin / launch_end are the device side).
+cudaError_t launch_fast(TickKernel k, unsigned grid, cudaStream_t st, const TickArgs &a, bool pdl)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k, a);
+}
+
+cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter, cudaStream_t st, bool pdl)
 {
     if (c->tma && !a.planar) {
         TickKernel k = tma_kernel(c, gm, meter);
@@ -298,7 +325,7 @@ cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter, cud
     else if (c->plan_g == 0)
         generic_kernel(gm, meter)<<<(unsigned)grid, 128, 0, st>>>(a, (int)c->channels);
     else
-        pick_fast(c, gm, meter, a.planar != nullptr)<<<(unsigned)grid, 256, 0, st>>>(a);
+        return launch_fast(pick_fast(c, gm, meter, a.planar != nullptr), (unsigned)grid, st, a, pdl);
     return cudaGetLastError();
 }
 
@@ -448,11 +475,16 @@ int rebuild_classes_locked(cmgpu_ctx *c)
 // One tick on stream `st`. In a cycle (cmgpu_process_cycle) the ticks run concurrently: each gets
 // its place in the sequence as `tick_offset` and leaves advancing the counter to the cycle's end.
 // n_ticks > 1: a span -- ONE launch over the consecutive slots [slot, slot + n_ticks) (span_ok() says when).
+// `captured`: the launch is being recorded into a cycle's graph; its tick number is then relative to
+// the device counter (tick_offset = place in the cycle) and the graph's own bump_tick advances it.
+// Otherwise the host numbers the tick(s): offset = ticks issued since the last bump.
 int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st = nullptr, unsigned tick_offset = 0,
-                  unsigned tick_bump = 1, unsigned n_ticks = 1)
+                  bool captured = false, unsigned n_ticks = 1)
 {
     if (!st)
         st = c->s_cmp;
+    if (!captured)
+        tick_offset = c->pending_ticks;
     int rc = upload_gains_locked(c);
     if (rc)
         return rc;
@@ -477,7 +509,6 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
         m.tick = c->d_tick;
         m.pbits = c->pbits;
         m.tick_offset = tick_offset;
-        m.tick_bump = tick_bump;
         m.n_streams = c->active;
         m.block_frames = c->block_frames;
         m.stride_in = (uint32_t)c->stride;
@@ -506,6 +537,10 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
             cmgpu::mix_tick<false><<<(unsigned)grid, 128, 0, st>>>(m);
         CU(cudaGetLastError());
         c->launches++;
+        if (!captured) {
+            c->pending_ticks += 1;
+            c->last_first = ~0u;
+        }
         return CMGPU_OK;
     }
     if (c->classes_dirty && (rc = rebuild_classes_locked(c)))
@@ -534,7 +569,6 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
     a.tick = c->d_tick;
     a.pbits = c->pbits;
     a.tick_offset = tick_offset;
-    a.tick_bump = tick_bump;
     a.n_streams = c->active;
     a.block_frames = c->block_frames;
     a.stride_bytes = (uint32_t)c->stride;
@@ -547,8 +581,24 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
     a.n_ticks = n_ticks;
     a.frames_stride = c->max_streams;
     a.slot_bytes = c->slot_bytes;
-    CU(launch_tick(c, a, gm, meter, st));
+    // Overlap with the previous tick launch of the compute stream is safe when this launch reads
+    // nothing that one writes: other ring slots, or a separate output ring (the input ring is then
+    // read-only for ticks). Anything else queued on the stream in between (uploads of gains or
+    // frames, snapshots, event waits on a slot's upload) is an ordinary full dependency anyway.
+    bool pdl = false;
+    if (!captured && st == c->s_cmp && c->last_first != ~0u && !getenv("CMGPU_NO_PDL")) {
+        const bool disjoint = slot >= c->last_first + c->last_n || slot + n_ticks <= c->last_first;
+        pdl = separate || disjoint;
+    }
+    CU(launch_tick(c, a, gm, meter, st, pdl));
     c->launches++;
+    if (!captured) {
+        c->pending_ticks += n_ticks;
+        if (st == c->s_cmp) {
+            c->last_first = slot;
+            c->last_n = n_ticks;
+        }
+    }
     return CMGPU_OK;
 }
 
@@ -586,6 +636,31 @@ double power_db(double mean_square)
 }
 
 bool slot_ok(const cmgpu_ctx *c, unsigned slot) { return c && slot < c->slots; }
+
+// "every tick queued on this slot so far": recorded on demand (a superset -- everything queued on the
+// compute stream so far -- which is what the next upload / download of the slot has to wait for).
+int ticks_done_event_locked(cmgpu_ctx *c, unsigned slot)
+{
+    if (c->cmp_unrecorded[slot]) {
+        CU(cudaEventRecord(c->ev_cmp[slot], c->s_cmp));
+        c->cmp_unrecorded[slot] = 0;
+        c->last_first = ~0u;
+    }
+    return CMGPU_OK;
+}
+
+int tick_waits_locked(cmgpu_ctx *c, unsigned slot)
+{
+    if (c->up_pending[slot]) {
+        CU(cudaStreamWaitEvent(c->s_cmp, c->ev_up[slot], 0));
+        c->up_pending[slot] = 0;
+    }
+    if (c->down_pending[slot]) {
+        CU(cudaStreamWaitEvent(c->s_cmp, c->ev_down[slot], 0));
+        c->down_pending[slot] = 0;
+    }
+    return CMGPU_OK;
+}
 
 }  // namespace
 
@@ -737,6 +812,9 @@ static cmgpu_ctx_t *ctx_create_impl(int device, unsigned channels, unsigned out_
     c->ev_up.assign(ring_slots, nullptr);
     c->ev_cmp.assign(ring_slots, nullptr);
     c->ev_down.assign(ring_slots, nullptr);
+    c->up_pending.assign(ring_slots, 0);
+    c->down_pending.assign(ring_slots, 0);
+    c->cmp_unrecorded.assign(ring_slots, 0);
     for (unsigned i = 0; i < ring_slots; i++) {
         if ((e = cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&c->ev_cmp[i], cudaEventDisableTiming)) != cudaSuccess ||
@@ -956,11 +1034,14 @@ int cmgpu_submit(cmgpu_ctx_t *c, unsigned slot, const void *host)
         return fail(CMGPU_ERR_FAULT, "no host buffer and no pinned staging");
     CU(cudaSetDevice(c->device));
     // the slot must not be overwritten while its previous tick or download is in flight
+    if (int erc = ticks_done_event_locked(c, slot))
+        return erc;
     CU(cudaStreamWaitEvent(c->s_up, c->ev_cmp[slot], 0));
     CU(cudaStreamWaitEvent(c->s_up, c->ev_down[slot], 0));
     CU(cudaMemcpyAsync(c->d_in + (size_t)slot * c->slot_bytes, host, c->stride * c->active, cudaMemcpyHostToDevice,
                        c->s_up));
     CU(cudaEventRecord(c->ev_up[slot], c->s_up));
+    c->up_pending[slot] = 1;
     return CMGPU_OK;
 }
 
@@ -970,13 +1051,17 @@ int cmgpu_process(cmgpu_ctx_t *c, unsigned slot, unsigned flags)
         return fail(c ? CMGPU_ERR_INVAL : CMGPU_ERR_FAULT, "bad context or slot");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
-    CU(cudaStreamWaitEvent(c->s_cmp, c->ev_up[slot], 0));
-    CU(cudaStreamWaitEvent(c->s_cmp, c->ev_down[slot], 0));
-    int rc = launch_locked(c, slot, flags);
-    if (rc)
+    // a tick that consumes a fresh upload (or follows a download) is part of a streaming pipeline: the
+    // slot's next upload will want to know exactly when THIS tick is done, so say so now; a tick on
+    // resident data records nothing and stays a bare kernel launch
+    const bool streaming = c->up_pending[slot] || c->down_pending[slot];
+    int rc = tick_waits_locked(c, slot);
+    if (rc || (rc = launch_locked(c, slot, flags)))
         return rc;
-    CU(cudaEventRecord(c->ev_cmp[slot], c->s_cmp));
-    return CMGPU_OK;
+    c->cmp_unrecorded[slot] = 1;
+    if (streaming)
+        rc = ticks_done_event_locked(c, slot);
+    return rc;
 }
 
 int cmgpu_fetch(cmgpu_ctx_t *c, unsigned slot, void *host)
@@ -992,11 +1077,14 @@ int cmgpu_fetch(cmgpu_ctx_t *c, unsigned slot, void *host)
     if (!host)
         return fail(CMGPU_ERR_FAULT, "no host buffer and no pinned staging");
     CU(cudaSetDevice(c->device));
+    if (int erc = ticks_done_event_locked(c, slot))
+        return erc;
     CU(cudaStreamWaitEvent(c->s_down, c->ev_cmp[slot], 0));
     CU(cudaStreamWaitEvent(c->s_down, c->ev_up[slot], 0));
     const uint8_t *src = (c->d_out ? c->d_out : c->d_in) + (size_t)slot * out_slot;
     CU(cudaMemcpyAsync(host, src, out_stride * c->active, cudaMemcpyDeviceToHost, c->s_down));
     CU(cudaEventRecord(c->ev_down[slot], c->s_down));
+    c->down_pending[slot] = 1;
     return CMGPU_OK;
 }
 
@@ -1020,6 +1108,7 @@ int cmgpu_fetch_planar(cmgpu_ctx_t *c, unsigned slot, float *host)
     CU(cudaMemcpyAsync(host, c->d_planar + (size_t)slot * c->planar_slot_floats,
                        c->plane_stride * c->channels * c->active * sizeof(float), cudaMemcpyDeviceToHost, c->s_down));
     CU(cudaEventRecord(c->ev_down[slot], c->s_down));
+    c->down_pending[slot] = 1;
     return CMGPU_OK;
 }
 
@@ -1039,6 +1128,8 @@ int cmgpu_slot_wait(cmgpu_ctx_t *c, unsigned slot)
     if (!slot_ok(c, slot))
         return fail(c ? CMGPU_ERR_INVAL : CMGPU_ERR_FAULT, "bad context or slot");
     CU(cudaSetDevice(c->device));
+    if (int erc = ticks_done_event_locked(c, slot))
+        return erc;
     CU(cudaEventSynchronize(c->ev_up[slot]));
     CU(cudaEventSynchronize(c->ev_cmp[slot]));
     CU(cudaEventSynchronize(c->ev_down[slot]));
@@ -1218,6 +1309,19 @@ int cmgpu_time_process(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, un
 // tick). That turns the launch-bound small-buffer regime into the same software-pipelined stream of
 // items as a large tick. Needs the fast kernels, no float planes, and per-slot frame counts given
 // for all of the span's slots or for none.
+// Brings the device's tick counter up to date with the ticks the host has numbered itself; needed
+// before a captured cycle, whose launches count from the device counter.
+static int flush_ticks_locked(cmgpu_ctx *c)
+{
+    c->last_first = ~0u;
+    if (!c->pending_ticks)
+        return CMGPU_OK;
+    cmgpu::bump_tick<<<1, 32, 0, c->s_cmp>>>(c->d_tick, c->pending_ticks);
+    CU(cudaGetLastError());
+    c->pending_ticks = 0;
+    return CMGPU_OK;
+}
+
 static bool span_ok(const cmgpu_ctx *c, unsigned first_slot, unsigned n_slots, unsigned flags)
 {
     if (n_slots < 2 || c->plan_g <= 0 || c->tma || c->out_channels || (flags & CMGPU_PLANAR) || getenv("CMGPU_NO_SPAN"))
@@ -1261,7 +1365,7 @@ static int build_cycle_locked(cmgpu_ctx *c, unsigned first_slot, unsigned n_slot
     for (unsigned i = 0; i < lanes && ce == cudaSuccess; i++)
         ce = cudaStreamWaitEvent(c->s_fork[i], c->ev_fork, 0);
     for (unsigned i = 0; i < n_slots && rc == CMGPU_OK && ce == cudaSuccess; i++)
-        rc = launch_locked(c, first_slot + i, flags, c->s_fork[i % lanes], i, 0);
+        rc = launch_locked(c, first_slot + i, flags, c->s_fork[i % lanes], i, true);
     for (unsigned i = 0; i < lanes && ce == cudaSuccess; i++) {
         ce = cudaEventRecord(c->ev_join[i], c->s_fork[i]);
         if (ce == cudaSuccess)
@@ -1306,19 +1410,26 @@ int cmgpu_process_cycle(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, u
     if (rc)
         return rc;
     // order the cycle after the uploads of its slots and before their next download
+    bool streaming = false;
     for (unsigned i = 0; i < n_slots; i++) {
-        CU(cudaStreamWaitEvent(c->s_cmp, c->ev_up[first_slot + i], 0));
-        CU(cudaStreamWaitEvent(c->s_cmp, c->ev_down[first_slot + i], 0));
+        streaming = streaming || c->up_pending[first_slot + i] || c->down_pending[first_slot + i];
+        if ((rc = tick_waits_locked(c, first_slot + i)))
+            return rc;
     }
     if (span) {
-        if ((rc = launch_locked(c, first_slot, flags, c->s_cmp, 0, n_slots, n_slots)))
+        if ((rc = launch_locked(c, first_slot, flags, c->s_cmp, 0, false, n_slots)))
             return rc;
     } else {
+        if ((rc = flush_ticks_locked(c)))
+            return rc;
         CU(cudaGraphLaunch(c->graph, c->s_cmp));
         c->launches += c->graph_launches;
     }
-    for (unsigned i = 0; i < n_slots; i++)
-        CU(cudaEventRecord(c->ev_cmp[first_slot + i], c->s_cmp));
+    for (unsigned i = 0; i < n_slots; i++) {
+        c->cmp_unrecorded[first_slot + i] = 1;
+        if (streaming && (rc = ticks_done_event_locked(c, first_slot + i)))
+            return rc;
+    }
     return CMGPU_OK;
 }
 
@@ -1339,9 +1450,11 @@ int cmgpu_time_cycles(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, uns
     CU(cudaEventRecord(c->ev_t0, c->s_cmp));
     for (unsigned r = 0; r < cycles; r++) {
         if (span) {
-            if ((rc = launch_locked(c, first_slot, flags, c->s_cmp, 0, n_slots, n_slots)))
+            if ((rc = launch_locked(c, first_slot, flags, c->s_cmp, 0, false, n_slots)))
                 return rc;
         } else {
+            if ((rc = flush_ticks_locked(c)))
+                return rc;
             CU(cudaGraphLaunch(c->graph, c->s_cmp));
             c->launches += c->graph_launches;
         }

@@ -87,10 +87,10 @@ struct TickArgs {
     const uint32_t *frames;     // valid frames per stream, or nullptr = block_frames each
     const GainRow *gains;
     unsigned long long *meters;
-    unsigned long long *tick;   // [0] tick sequence number, [1] CTAs of this launch that are done
+    unsigned long long *tick;   // [0] tick sequence number as of the last bump_tick
     uint32_t pbits;             // position = (tick[0] + tick_offset) << pbits | frame
-    uint32_t tick_offset;       // which tick of a concurrently running cycle this launch is
-    uint32_t tick_bump;         // what the last CTA adds to tick[0] (0: a later launch does it)
+    uint32_t tick_offset;       // the launch's tick number relative to tick[0]
+    uint32_t reserved0;
     uint32_t n_streams;
     uint32_t block_frames;
     uint32_t stride_bytes;      // bytes between stream-blocks (multiple of 16)
@@ -159,31 +159,29 @@ __device__ __forceinline__ uint64_t make_key(uint32_t mag, uint64_t pos)
     return mag ? (((uint64_t)mag << kKeyMagShift) | (((~pos) & kKeyPosMask) << 1)) : 0ull;
 }
 
-// The tick sequence number lives on the device so that a launch captured in a CUDA graph still
-// sees a fresh position base at every replay. Every thread reads it on entry; the CTA that
-// finishes last (all CTAs of a launch are co-resident, so by then all have read it) advances it.
+// Which tick a launch is decides where its samples sit in the position order of the meter keys:
+//     tick = tick[0] + tick_offset (+ the tick's index inside a span).
+// tick[0] lives on the device and is advanced only by bump_tick (once per replay of a captured cycle,
+// and before one when plain ticks were issued since); plain and span launches get their place from
+// the host as tick_offset = ticks issued since the last bump. No launch modifies tick[0] itself, so
+// consecutive launches may overlap (see launch_begin).
 __device__ __forceinline__ uint64_t tick_pos_base(const unsigned long long *tick, uint32_t offset, uint32_t pbits)
 {
     const unsigned long long t = *reinterpret_cast<const volatile unsigned long long *>(tick) + offset;
     return ((uint64_t)t << pbits) & kKeyPosMask;
 }
-__device__ __forceinline__ void tick_finish(unsigned long long *tick, uint32_t bump)
-{
-    if (!bump)
-        return;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned long long done = atomicAdd(tick + 1, 1ull);
-        if (done == (unsigned long long)gridDim.x - 1ull) {
-            tick[1] = 0ull;
-            __threadfence();
-            atomicAdd(tick, (unsigned long long)bump);
-        }
-    }
-}
 __device__ __forceinline__ uint64_t tick_begin(const TickArgs &a) { return tick_pos_base(a.tick, a.tick_offset, a.pbits); }
-__device__ __forceinline__ void tick_end(const TickArgs &a) { tick_finish(a.tick, a.tick_bump); }
+
+// Programmatic dependent launch: every tick kernel lets the NEXT launch of its stream start as soon
+// as its own CTAs have all started (they are all resident at once), so the next tick's CTAs take
+// over SM by SM while this tick's last work items drain -- no idle tail, no launch gap, no ramp
+// between ticks. Only launches the host marked as independent of their predecessor use it
+// (different ring slots, or a read-only input ring); meter updates are atomics on order-free
+// position keys. launch_end keeps completion in stream order: a launch does not finish before the
+// one it overlapped.
+__device__ __forceinline__ void launch_begin() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void launch_end() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void tick_end(const TickArgs &) { launch_end(); }
 
 // One sample through the gain recipe (see GainRow).
 struct Recipe {
@@ -563,6 +561,7 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
     constexpr int P = Shape<C>::kPerLane;
     constexpr int UNROLL = Tune<C, G>::kUnroll;
     constexpr size_t kStep = (size_t)G * 16;              // bytes between a lane's consecutive vectors
+    launch_begin();
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gl = threadIdx.x & (G - 1);
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(uint32_t)(G - 1)));
@@ -900,8 +899,8 @@ __global__ void __launch_bounds__(256, 2) any_tick(const __grid_constant__ TickA
     tick_end(a);
 }
 
-// Closes a cycle of concurrently running ticks: advances the tick sequence number once all of
-// them are done (the graph orders it after every tick node).
+// Advances the tick sequence number: at the end of a captured cycle (the graph orders it after
+// every tick node) and, from the host, before a cycle when plain ticks were issued since the last one.
 __global__ void bump_tick(unsigned long long *tick, unsigned n)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0)

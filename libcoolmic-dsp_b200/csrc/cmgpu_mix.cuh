@@ -39,7 +39,7 @@ struct MixArgs {
     unsigned long long *meters_in;    // rows of (2*CIN+2) uint64
     unsigned long long *meters_out;   // rows of (2*COUT+2) uint64
     unsigned long long *tick;
-    uint32_t pbits, tick_offset, tick_bump;
+    uint32_t pbits, tick_offset, reserved0;
     uint32_t n_streams, block_frames;
     uint32_t stride_in, stride_out;
     uint32_t items_per_block, per_item;   // frames per item
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(128) mix_tick(const __grid_constant__ MixArgs 
         mix_publish<16>(a.meters_in + (size_t)s * (2 * cin + 2), cin, in, pos_base, f0, lane, kin, pin);
         mix_publish<16>(a.meters_out + (size_t)s * (2 * cout + 2), cout, out, pos_base, f0, lane, kout, pout);
     }
-    tick_finish(a.tick, a.tick_bump);
+    launch_end();
 }
 
 __device__ __forceinline__ int dp2a_lo_su(uint32_t a_s16x2, uint32_t b_u8x4, int c)
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(256, 2) mix8to2_tick(const __grid_constant__ M
         mix_publish<2>(a.meters_out + (size_t)s * 6, 2, reinterpret_cast<const volatile int16_t *>(a.out + (size_t)s * a.stride_out),
                        pos_base, f0, lane, kout, pout);
     }
-    tick_finish(a.tick, a.tick_bump);
+    launch_end();
 }
 
 }  // namespace cmgpu

@@ -362,6 +362,48 @@ def test_full_size_config2_properties(cm, port):
             assert int(snap[s].frames) == block
 
 
+@pytest.mark.parametrize("channels,block,n_streams", [(2, 60000, 40), (8, 9000, 64), (1, 320, 3000), (2, 4800, 700)])
+@pytest.mark.parametrize("no_pdl", [False, True])
+def test_overlapping_ticks_on_resident_data(cm, port, monkeypatch, channels, block, n_streams, no_pdl):
+    """Back-to-back ticks on data that is already on the device are bare kernel launches, each marked
+    as a programmatic dependent launch of the one before when it reads nothing that one writes (other
+    ring slots, or a separate output ring): the next tick's CTAs start while the previous tick's last
+    work items drain. The meter must not notice: ticks are numbered by the host, keys carry (tick,
+    frame), so a tie between ticks still goes to the earlier tick. Checked against the oracle run
+    tick after tick, with the overlap on and off (CMGPU_NO_PDL)."""
+    if no_pdl:
+        monkeypatch.setenv("CMGPU_NO_PDL", "1")
+    rng = np.random.default_rng(900 + channels + block)
+    ring, rounds = 3, 4
+    data = make_pcm(rng, "ties", (ring, n_streams, block * channels))
+    scale, gain = make_gains(rng, n_streams, channels)
+    with cm.Engine(channels, n_streams, block, ring_slots=ring, flags=cm.SEPARATE_OUT) as eng:
+        eng.set_gain_table(scale, gain)
+        for slot in range(ring):
+            eng.host_slot(slot)[:, : block * channels] = data[slot]
+            eng.submit(slot)
+        eng.sync()
+        order = []
+        for r in range(rounds):
+            for slot in ([0, 0, 1, 2, 2, 1] if r % 2 else [2, 1, 0]):
+                eng.process(slot)               # the same slot twice in a row is fine too: the input ring is read-only
+                order.append(slot)
+        for slot in range(ring):
+            eng.fetch(slot)
+        eng.sync()
+        assert eng.launch_count() == len(order)
+        meters = None
+        frames = np.full(n_streams, block, np.uint32)
+        outs = {}
+        for slot in order:
+            work = data[slot].copy()
+            meters, _ = port.batch(work, frames, channels, scale, gain, meters=meters)
+            outs[slot] = work
+        for slot in range(ring):
+            assert np.array_equal(eng.host_slot(slot)[:, : block * channels], outs[slot])
+        check_meters(cm, port, eng, meters, n_streams, channels)
+
+
 @pytest.mark.parametrize("channels,block,ragged,no_span", [
     (1, 320, False, False), (1, 320, False, True), (1, 320, True, False), (2, 4799, False, False),
     (2, 20000, True, False), (8, 257, False, False), (16, 100, True, False), (4, 333, False, True), (6, 500, False, False)])
