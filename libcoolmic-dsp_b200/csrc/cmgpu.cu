@@ -276,19 +276,22 @@ int resident_ctas(cmgpu_ctx *c, int gm, bool meter)
 
 // `pdl`: the launch may start while the previous launch of the stream is still draining
 // (programmatic dependent launch; the kernels' launch_begin / launch_end are the device side).
-cudaError_t launch_fast(TickKernel k, unsigned grid, cudaStream_t st, const TickArgs &a, bool pdl)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*k)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool pdl,
+                          Args... args)
 {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, k, a);
+    return cudaLaunchKernelEx(&cfg, k, KArgs(args)...);
 }
 
 cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter, cudaStream_t st, bool pdl)
@@ -311,8 +314,7 @@ cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter, cud
         uint64_t grid = (uint64_t)t.n_streams * t.items_per_block;
         if (grid > (uint64_t)cap)
             grid = (uint64_t)cap;
-        k<<<(unsigned)grid, cmgpu::kTmaThreads, cmgpu::kTmaSmemBytes, st>>>(t);
-        return cudaGetLastError();
+        return launch_kernel(k, (unsigned)grid, cmgpu::kTmaThreads, cmgpu::kTmaSmemBytes, st, pdl, t);
     }
     const uint64_t items = (uint64_t)a.n_streams * a.items_per_block * (a.n_ticks > 1 ? a.n_ticks : 1u);
     const uint64_t per_cta = c->plan_g > 0 ? 256u / (unsigned)c->plan_g : (c->plan_g < 0 ? 8u : 4u);
@@ -321,12 +323,10 @@ cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter, cud
     if (grid > cap)
         grid = cap;
     if (c->plan_g < 0)
-        any_kernel(gm, meter)<<<(unsigned)grid, 256, 0, st>>>(a, (int)c->channels, c->plan_lanes);
-    else if (c->plan_g == 0)
-        generic_kernel(gm, meter)<<<(unsigned)grid, 128, 0, st>>>(a, (int)c->channels);
-    else
-        return launch_fast(pick_fast(c, gm, meter, a.planar != nullptr), (unsigned)grid, st, a, pdl);
-    return cudaGetLastError();
+        return launch_kernel(any_kernel(gm, meter), (unsigned)grid, 256, 0, st, pdl, a, (int)c->channels, c->plan_lanes);
+    if (c->plan_g == 0)
+        return launch_kernel(generic_kernel(gm, meter), (unsigned)grid, 128, 0, st, pdl, a, (int)c->channels);
+    return launch_kernel(pick_fast(c, gm, meter, a.planar != nullptr), (unsigned)grid, 256, 0, st, pdl, a);
 }
 
 // Decide how a tick is cut into work items. Shape-only, so done once per context.
@@ -531,15 +531,19 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
             occ = 1;
         if (grid > (uint64_t)occ * c->num_sms)
             grid = (uint64_t)occ * c->num_sms;
+        // a downmix context always has its own output ring: consecutive ticks never conflict
+        const bool mpdl = !captured && st == c->s_cmp && c->last_first != ~0u && !getenv("CMGPU_NO_PDL");
         if (vec8)
-            cmgpu::mix8to2_tick<<<(unsigned)grid, 256, 0, st>>>(m);
+            CU(launch_kernel(cmgpu::mix8to2_tick, (unsigned)grid, 256, 0, st, mpdl, m));
         else
-            cmgpu::mix_tick<false><<<(unsigned)grid, 128, 0, st>>>(m);
-        CU(cudaGetLastError());
+            CU(launch_kernel(cmgpu::mix_tick<false>, (unsigned)grid, 128, 0, st, mpdl, m));
         c->launches++;
         if (!captured) {
             c->pending_ticks += 1;
-            c->last_first = ~0u;
+            if (st == c->s_cmp) {
+                c->last_first = slot;
+                c->last_n = 1;
+            }
         }
         return CMGPU_OK;
     }

@@ -746,6 +746,7 @@ __device__ __noinline__ void store_planar_any(float *planar, uint32_t plane_stri
 template <int GM, bool METER>
 __global__ void __launch_bounds__(256, 2) any_tick(const __grid_constant__ TickArgs a, const int C, const int L)
 {
+    launch_begin();
     constexpr int UNROLL = 4;
     const uint32_t lane = threadIdx.x & 31u;
     const bool active = (int)lane < L;
@@ -1001,6 +1002,7 @@ __device__ __forceinline__ void run_item_generic(const TickArgs &a, int C, uint3
 template <int GM, bool METER>
 __global__ void __launch_bounds__(128) generic_tick(const __grid_constant__ TickArgs a, const int C)
 {
+    launch_begin();
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_per_cta = 128 / 32;
     const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block;

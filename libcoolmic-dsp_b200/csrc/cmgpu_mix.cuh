@@ -98,6 +98,7 @@ __device__ __forceinline__ void mix_publish(unsigned long long *row, int nch, co
 template <bool VEC8>
 __global__ void __launch_bounds__(128) mix_tick(const __grid_constant__ MixArgs a)
 {
+    launch_begin();
     __shared__ uint16_t s_w[4][16 * 16];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = threadIdx.x >> 5;
@@ -210,6 +211,7 @@ __device__ __forceinline__ int dp2a_hi_su(uint32_t a_s16x2, uint32_t b_u8x4, int
 // low and high bytes) + one 64-bit recombination per output instead of 8 half-rate IMAD.WIDE.
 __global__ void __launch_bounds__(256, 2) mix8to2_tick(const __grid_constant__ MixArgs a)
 {
+    launch_begin();
     constexpr int UNROLL = 4;
     constexpr size_t kStep = 32 * 16;
     const uint32_t lane = threadIdx.x & 31u;

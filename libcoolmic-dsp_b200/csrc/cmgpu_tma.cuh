@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(kTmaThreads, CMGPU_TMA_CTAS) tma_tick(const __
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = tid >> 5, lane = tid & 31u;
     const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block;
+    launch_begin();
 
     if (tid == 0) {
         for (int s = 0; s < kTmaStages; s++) {
