@@ -238,9 +238,15 @@ TickKernel tma_kernel(const cmgpu_ctx *c, int gm, bool meter)
 
 using AnyKernel = void (*)(const TickArgs, const int, const int);
 
-AnyKernel any_kernel(int gm, bool meter)
+AnyKernel any_kernel(int gm, bool meter, bool nc)
 {
     using namespace cmgpu;
+    if (nc) {               // separate output ring: loads through the read-only path
+        switch (gm) {
+        case GM_IDENTITY: return meter ? any_tick<GM_IDENTITY, true, true> : any_tick<GM_IDENTITY, false, true>;
+        default:          return meter ? any_tick<GM_MASKED, true, true> : any_tick<GM_MASKED, false, true>;
+        }
+    }
     switch (gm) {
     case GM_IDENTITY: return meter ? any_tick<GM_IDENTITY, true> : any_tick<GM_IDENTITY, false>;
     default:          return meter ? any_tick<GM_MASKED, true> : any_tick<GM_MASKED, false>;
@@ -266,7 +272,7 @@ int resident_ctas(cmgpu_ctx *c, int gm, bool meter)
         return cap;
     int n = 0;
     cudaError_t e = c->plan_g > 0   ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pick_fast(c, gm, meter), 256, 0)
-                    : c->plan_g < 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, any_kernel(gm, meter), 256, 0)
+                    : c->plan_g < 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, any_kernel(gm, meter, c->d_out != nullptr), 256, 0)
                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, generic_kernel(gm, meter), 128, 0);
     if (e != cudaSuccess || n < 1)
         n = 1;
@@ -323,7 +329,7 @@ cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter, cud
     if (grid > cap)
         grid = cap;
     if (c->plan_g < 0)
-        return launch_kernel(any_kernel(gm, meter), (unsigned)grid, 256, 0, st, pdl, a, (int)c->channels, c->plan_lanes);
+        return launch_kernel(any_kernel(gm, meter, c->d_out != nullptr), (unsigned)grid, 256, 0, st, pdl, a, (int)c->channels, c->plan_lanes);
     if (c->plan_g == 0)
         return launch_kernel(generic_kernel(gm, meter), (unsigned)grid, 128, 0, st, pdl, a, (int)c->channels);
     return launch_kernel(pick_fast(c, gm, meter, a.planar != nullptr), (unsigned)grid, 256, 0, st, pdl, a);
@@ -374,6 +380,8 @@ void make_plan(cmgpu_ctx *c)
     uint32_t target = 2048;
     if (const char *e = getenv("CMGPU_ITEM_VECS"))          // tuning hook
         target = (uint32_t)strtoul(e, nullptr, 10) ? (uint32_t)strtoul(e, nullptr, 10) : target;
+    if (target > 32768)                                       // item_publish: vector indices of an item fit 16 bits
+        target = 32768;
     uint32_t items = (nvec + target - 1) / target;
     uint32_t per = (nvec + items - 1) / items;
     const uint32_t quantum = (uint32_t)g * 4u;
@@ -390,6 +398,8 @@ void make_plan(cmgpu_ctx *c)
         uint32_t tile_target = 8 * cmgpu::kTmaTileVecs;
         if (const char *e = getenv("CMGPU_TMA_ITEM_TILES"))         // tuning hook
             tile_target = (uint32_t)(strtoul(e, nullptr, 10) ? strtoul(e, nullptr, 10) : 8) * cmgpu::kTmaTileVecs;
+        if (tile_target > 32768)                                    // item_publish: vector indices of an item fit 16 bits
+            tile_target = 32768;
         uint32_t n = (nvec + tile_target - 1) / tile_target;
         uint32_t tper = (nvec + n - 1) / n;
         tper = (tper + cmgpu::kTmaTileVecs - 1) / cmgpu::kTmaTileVecs * cmgpu::kTmaTileVecs;

@@ -448,55 +448,52 @@ __device__ __forceinline__ void load_recipes(const TickArgs &a, uint32_t s, uint
     }
 }
 
-// Meter epilogue of one item: widen the lane's in-loop keys to position keys, fold slots of the
-// same channel, combine the group's lanes with shuffles, publish one channel per lane.
+// Meter epilogue of one item: combine the group's lanes with shuffles, publish one channel per lane.
+// The lanes' keys are combined while they are still 32 bits wide -- magnitude << 16 | ~(index of the
+// vector among the group's vectors of this item), one SHFL and one max per round instead of two and
+// a 64-bit compare -- and only the winner is widened to a position key. For frames narrower than a
+// vector (C < 8) that key names the winning VECTOR; the publishing lane looks at it again and takes
+// the channel's first sample with the winning magnitude (and, always, the sample's sign).
 // STRIDE: vectors between a lane's consecutive steps (G in fused_tick; the consumer count in tma_tick,
-// where G is only the width of the shuffle tree).
+// where G is only the width of the shuffle tree). Needs per_item + STRIDE <= 65,536 vectors.
 template <int C, int G, bool MERGE = false, int STRIDE = G>
 __device__ __forceinline__ void item_publish(const TickArgs &a, const Item &it, uint32_t gl, unsigned gmask,
                                              const uint32_t (&kmax)[8], uint64_t (&pacc)[Shape<C>::kPerLane])
 {
+    static_assert(MERGE || C >= 8, "narrow frames keep one running key per channel (do_vector<MERGE>)");
     constexpr int P = Shape<C>::kPerLane;
     constexpr int S = (C <= 8) ? 8 / P : 1;      // slots of one channel in a vector (= frames per vector)
-    const uint64_t pos_base = tick_pos_base(a.tick, a.tick_offset + it.tk, a.pbits);
-    uint64_t kc[P];
+    // Where the tick number is read is measured, not guessed (A/B on B200): warps that walk long
+    // items want it requested first, so that its latency hides behind the shuffle rounds instead of
+    // adding to the re-read's (cfg5: 3 %); the 8-lane groups of the small-buffer regime, where the
+    // epilogue is a third of all instructions, are 6 % faster reading it only in the publishing lanes.
+    constexpr bool kEarlyTick = G > 8;
+    uint64_t pos_base = 0;
+    if (kEarlyTick)
+        pos_base = tick_pos_base(a.tick, a.tick_offset + it.tk, a.pbits);
+    uint32_t k32[P];
 #pragma unroll
     for (int c = 0; c < P; c++) {
-        // a channel's slots c, c+P, c+2P, ... are in time order inside a vector: fold them in the
-        // cheap 32-bit domain first (strict '>' keeps the earlier slot), widen only the winner
-        uint32_t best = kmax[c];
-        uint32_t sub = 0;          // MERGE: the key is per vector; the slot is found after the reduction
-        if (!MERGE) {
-#pragma unroll
-            for (int j = 1; j < 8 / P; j++) {
-                if (kmax[c + j * P] > best) {
-                    best = kmax[c + j * P];
-                    sub = (uint32_t)j;
-                }
-            }
-        }
-        const uint32_t mag = best >> 16;
-        const uint32_t step = 0xffffu - (best & 0xffffu);
-        const uint32_t v = it.first + step * STRIDE;
-        // frame index of that slot of vector v inside the stream-block
-        const uint32_t frame = (C <= 8) ? (v * (uint32_t)Shape<C>::kFramesPerVec8 + sub) : (v >> 1);
-        kc[c] = make_key(mag, pos_base + frame);
+        const uint32_t best = kmax[c];
+        const uint32_t idx = (0xffffu - (best & 0xffffu)) * (uint32_t)STRIDE + gl;
+        k32[c] = (best >> 16) ? ((best & 0xffff0000u) | (0xffffu - idx)) : 0u;
     }
 #pragma unroll
     for (int off = G / 2; off >= Shape<C>::kLanesPerFrame; off >>= 1) {
 #pragma unroll
         for (int c = 0; c < P; c++) {
-            kc[c] = max(kc[c], shfl_xor64(gmask, kc[c], off));
+            k32[c] = max(k32[c], __shfl_xor_sync(gmask, k32[c], off));
             pacc[c] += shfl_xor64(gmask, pacc[c], off);
         }
     }
     // lane L publishes one channel: C <= 8 -> channel L; C == 16 -> channel 8*(L&1) + (L>>1)
-    uint64_t key = 0, pw = 0;
+    uint32_t key32 = 0;
+    uint64_t pw = 0;
     const int sel = (C == 16) ? (int)(gl >> 1) : (int)gl;
 #pragma unroll
     for (int c = 0; c < P; c++) {
         if (sel == c) {
-            key = kc[c];
+            key32 = k32[c];
             pw = pacc[c];
         }
     }
@@ -504,34 +501,32 @@ __device__ __forceinline__ void item_publish(const TickArgs &a, const Item &it, 
     __syncwarp(gmask);       // make the item's stores visible to the lane that re-reads a sample
     if ((int)gl < C) {
         unsigned long long *row = a.meters + (size_t)it.s * a.row_u64;
-        if (key) {
-            // the sign of the winning sample: re-read it from where it was written
-            const uint64_t pos = (~(key >> 1)) & kKeyPosMask;
-            const uint32_t frame = (uint32_t)(pos - pos_base);
-            const volatile int16_t *y =
-                reinterpret_cast<const volatile int16_t *>(a.out + it.base);
-            if (MERGE && S > 1) {
-                // `frame` is the first frame of the winning vector: the channel's first sample in it
-                // that has the winning magnitude is the peak (slots past the valid frames of a tail
-                // vector come after every valid one, so they can only match after it)
-                const uint32_t mag = (uint32_t)(key >> kKeyMagShift);
-                uint32_t j = 0;
-                int yv = 0;
-                bool found = false;
+        if (key32) {
+            const uint32_t mag = key32 >> 16;
+            const uint32_t v = (it.first - gl) + (0xffffu - (key32 & 0xffffu));       // the winning vector
+            const uint32_t frame = (C <= 8) ? v * (uint32_t)Shape<C>::kFramesPerVec8 : (v >> 1);
+            if (!kEarlyTick)
+                pos_base = tick_pos_base(a.tick, a.tick_offset + it.tk, a.pbits);
+            const uint64_t pos = pos_base + frame;
+            // the winning sample, re-read from where it was written: its sign, and for narrow frames
+            // which of the vector's frames it is (slots past the valid frames of a tail vector come
+            // after every valid one, so they can only match after the real winner)
+            const volatile int16_t *y = reinterpret_cast<const volatile int16_t *>(a.out + it.base);
+            uint32_t j = 0;
+            int yv = y[(size_t)frame * C + ch];
+            if (S > 1) {
+                bool found = (uint32_t)abs(yv) == mag;
 #pragma unroll
-                for (int q = 0; q < S; q++) {
-                    const int v = y[((size_t)frame + q) * C + ch];
-                    if (!found && (uint32_t)abs(v) == mag) {
+                for (int q = 1; q < S; q++) {
+                    const int cand = y[((size_t)frame + q) * C + ch];
+                    if (!found && (uint32_t)abs(cand) == mag) {
                         found = true;
                         j = (uint32_t)q;
-                        yv = v;
+                        yv = cand;
                     }
                 }
-                atomicMax(row + ch, (unsigned long long)(make_key(mag, pos + j) | (yv < 0 ? 1ull : 0ull)));
-            } else {
-                const int yv = y[(size_t)frame * C + ch];
-                atomicMax(row + ch, (unsigned long long)(key | (yv < 0 ? 1ull : 0ull)));
             }
+            atomicMax(row + ch, (unsigned long long)(make_key(mag, pos + j) | (yv < 0 ? 1ull : 0ull)));
         }
         if (pw)
             atomicAdd(row + C + ch, (unsigned long long)pw);
@@ -743,7 +738,7 @@ __device__ __noinline__ void store_planar_any(float *planar, uint32_t plane_stri
 // C, so each of the lane's 8 sample slots keeps ONE channel for the whole item -- the hot loop is
 // the 8-channel one (do_vector<8>: a recipe, a peak key and a power sum per slot), only the
 // recipes are gathered per lane and the epilogue folds slots into channels by a per-lane map.
-template <int GM, bool METER>
+template <int GM, bool METER, bool NC = false>
 __global__ void __launch_bounds__(256, 2) any_tick(const __grid_constant__ TickArgs a, const int C, const int L)
 {
     launch_begin();
@@ -805,7 +800,7 @@ __global__ void __launch_bounds__(256, 2) any_tick(const __grid_constant__ TickA
         const uint32_t nb = n_i / UNROLL;
 #define CMGPU_LOAD_BATCH(buf, b)                                                        \
     _Pragma("unroll") for (int u = 0; u < UNROLL; u++)                                  \
-        buf[u] = ld_stream(src + (size_t)((b) * UNROLL + u) * kStep);
+        buf[u] = ld_stream(src + (size_t)((b) * UNROLL + u) * kStep, NC);
 #define CMGPU_DO_BATCH(buf, b)                                                          \
     _Pragma("unroll") for (int u = 0; u < UNROLL; u++) {                                \
         const uint32_t iu = (b) * UNROLL + u;                                           \
@@ -833,7 +828,7 @@ __global__ void __launch_bounds__(256, 2) any_tick(const __grid_constant__ TickA
 #undef CMGPU_LOAD_BATCH
 #undef CMGPU_DO_BATCH
         for (uint32_t i = nb * UNROLL; i < n_i; i++) {
-            const uint4 w = ld_stream(src + (size_t)i * kStep);
+            const uint4 w = ld_stream(src + (size_t)i * kStep, NC);
             const uint4 o = do_vector<8, GM, METER, false, true>(w, rc, 0xffffu - i, kmax, pacc, 8);
             if (a.store)
                 st_stream(dst + (size_t)i * kStep, o);
@@ -843,7 +838,7 @@ __global__ void __launch_bounds__(256, 2) any_tick(const __grid_constant__ TickA
         if (active && vfull < v1 && (vfull << 4) < valid_bytes && ((vfull - v0) % (uint32_t)L) == lane) {
             const uint32_t step = (vfull - v0) / (uint32_t)L;
             const int nvalid = (int)((valid_bytes - (vfull << 4)) >> 1);
-            const uint4 w = ld_stream(a.in + base + (size_t)vfull * 16);
+            const uint4 w = ld_stream(a.in + base + (size_t)vfull * 16, NC);
             const uint4 o = do_vector<8, GM, METER, true, true>(w, rc, 0xffffu - step, kmax, pacc, nvalid);
             if (a.store)
                 st_stream(a.out + base + (size_t)vfull * 16, o);
