@@ -359,19 +359,30 @@ def main():
         return eng.time_process(steps * ticks, 0, ring, flags=pflags)
 
     pflags = {"fused": cm.FUSED, "transform": cm.TRANSFORM, "meter": cm.METER, "copy": 0}[args.mode]
-    clocks = ClockSampler(local)
-    clocks.start()
-    timed(args.warmup)
-    eng.reset_meters()
-    launches0 = eng.launch_count()
-    barrier()
-    clocks.mark_begin()
-    ms_total = timed(args.steps)
-    clocks.mark_end()
-    barrier()
-    clk = clocks.stop()
-    launches = eng.launch_count() - launches0
-    ms_total = max_over_ranks(ms_total)
+    # A run that saw a hardware or thermal slowdown is re-measured once (sw_power_cap is kept and noted).
+    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    remeasured = False
+    for attempt in range(2):
+        clocks = ClockSampler(local)
+        clocks.start()
+        timed(args.warmup)
+        eng.reset_meters()
+        launches0 = eng.launch_count()
+        barrier()
+        clocks.mark_begin()
+        ms_total = timed(args.steps)
+        clocks.mark_end()
+        barrier()
+        clk = clocks.stop()
+        launches = eng.launch_count() - launches0
+        ms_total = max_over_ranks(ms_total)
+        throttled = max_over_ranks(1.0 if bad & set(clk.get("reasons") or []) else 0.0) > 0
+        if not throttled or attempt == 1:
+            break
+        remeasured = True
+        time.sleep(2.0)
+    if remeasured:
+        clk["remeasured_after_slowdown"] = True
     ms_step = ms_total / args.steps
     value = samples_per_step_rank * world / (ms_step * 1e-3) / 1e6
 

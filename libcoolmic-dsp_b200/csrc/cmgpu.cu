@@ -244,11 +244,13 @@ AnyKernel any_kernel(int gm, bool meter, bool nc)
     if (nc) {               // separate output ring: loads through the read-only path
         switch (gm) {
         case GM_IDENTITY: return meter ? any_tick<GM_IDENTITY, true, true> : any_tick<GM_IDENTITY, false, true>;
+        case GM_ADDALL:   return meter ? any_tick<GM_ADDALL, true, true> : any_tick<GM_ADDALL, false, true>;
         default:          return meter ? any_tick<GM_MASKED, true, true> : any_tick<GM_MASKED, false, true>;
         }
     }
     switch (gm) {
     case GM_IDENTITY: return meter ? any_tick<GM_IDENTITY, true> : any_tick<GM_IDENTITY, false>;
+    case GM_ADDALL:   return meter ? any_tick<GM_ADDALL, true> : any_tick<GM_ADDALL, false>;
     default:          return meter ? any_tick<GM_MASKED, true> : any_tick<GM_MASKED, false>;
     }
 }
@@ -565,7 +567,7 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
     if (transform && c->n_mode[cmgpu::GM_MASKED])
         gm = cmgpu::GM_MASKED;
     else if (transform && c->n_mode[cmgpu::GM_ADDALL])
-        gm = (c->plan_g <= 0) ? cmgpu::GM_MASKED : cmgpu::GM_ADDALL;   // generic / any kernels: masked covers it
+        gm = (c->plan_g == 0) ? cmgpu::GM_MASKED : cmgpu::GM_ADDALL;   // generic kernel: masked covers it
     const bool store = gm != cmgpu::GM_IDENTITY || separate;
     const bool planar = (flags & CMGPU_PLANAR) != 0;
     if (planar && (!c->d_planar || !meter))

@@ -783,7 +783,8 @@ __global__ void __launch_bounds__(256, 2) any_tick(const __grid_constant__ TickA
                 if (GM != GM_IDENTITY) {
                     rc[k].mw = (int)__ldg(&g->mw[ch]);
                     rc[k].mul = (int)__ldg(&g->mul[ch]);
-                    rc[k].addm = (int)__ldg(&g->addm[ch]);
+                    if (GM == GM_MASKED)
+                        rc[k].addm = (int)__ldg(&g->addm[ch]);
                 }
                 ch = ch + 1 == C ? 0 : ch + 1;
             }
@@ -848,19 +849,22 @@ __global__ void __launch_bounds__(256, 2) any_tick(const __grid_constant__ TickA
         if (!METER)
             continue;
 
-        // ---- epilogue: slots -> position keys, fold by the lane's channel map, combine lanes ----
+        // ---- epilogue: fold the lane's slots by its channel map, combine lanes, publish ----
+        // Keys stay 32 bits wide until a channel's winner is known: magnitude << 16 | ~(index of the
+        // sample's vector among the item's vectors * 8 + slot) -- one SHFL + max per round, and ONE
+        // division by C (sample index -> frame) per channel instead of one per slot.
         const uint64_t pos_base = tick_begin(a);
-        uint64_t key8[8];
+        uint32_t key8[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const uint32_t mag = kmax[k] >> 16;
-            const uint32_t step = 0xffffu - (kmax[k] & 0xffffu);
-            const uint64_t sample = ((uint64_t)first + (uint64_t)step * (uint32_t)L) * 8u + (uint32_t)k;
-            key8[k] = make_key(mag, pos_base + (uint32_t)(sample / (uint32_t)C));
+            const uint32_t idx = ((0xffffu - (kmax[k] & 0xffffu)) * (uint32_t)L + lane) * 8u + (uint32_t)k;
+            key8[k] = (kmax[k] >> 16) ? ((kmax[k] & 0xffff0000u) | (0xffffu - idx)) : 0u;
         }
-        uint64_t key = 0, pw = 0;
+        uint32_t key32 = 0;
+        uint64_t pw = 0;
         for (int c = 0; c < C; c++) {
-            uint64_t kc = 0, pc = 0;
+            uint32_t kc = 0;
+            uint64_t pc = 0;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 if (chan[k] == c) {
@@ -870,23 +874,24 @@ __global__ void __launch_bounds__(256, 2) any_tick(const __grid_constant__ TickA
             }
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) {
-                kc = max(kc, shfl_xor64(0xffffffffu, kc, off));
+                kc = max(kc, __shfl_xor_sync(0xffffffffu, kc, off));
                 pc += shfl_xor64(0xffffffffu, pc, off);
             }
             if ((int)lane == c) {
-                key = kc;
+                key32 = kc;
                 pw = pc;
             }
         }
         __syncwarp();
         if ((int)lane < C) {
             unsigned long long *row = a.meters + (size_t)s * a.row_u64;
-            if (key) {
-                const uint64_t pos = (~(key >> 1)) & kKeyPosMask;
-                const uint32_t frame = (uint32_t)(pos - pos_base);
+            if (key32) {
+                const uint32_t mag = key32 >> 16;
+                const uint64_t sample = (uint64_t)v0 * 8u + (0xffffu - (key32 & 0xffffu));
+                const uint32_t frame = (uint32_t)(sample / (uint32_t)C);
                 const volatile int16_t *y = reinterpret_cast<const volatile int16_t *>(a.out + base);
                 const int yv = y[(size_t)frame * C + lane];
-                atomicMax(row + lane, (unsigned long long)(key | (yv < 0 ? 1ull : 0ull)));
+                atomicMax(row + lane, (unsigned long long)(make_key(mag, pos_base + frame) | (yv < 0 ? 1ull : 0ull)));
             }
             if (pw)
                 atomicAdd(row + C + lane, (unsigned long long)pw);
