@@ -46,15 +46,23 @@ struct MixArgs {
     uint32_t cin, cout;
 };
 
+// exact trunc(n / scale) wherever the quotient is inside the clamp range; returns the
+// UNSATURATED quotient (callers saturate to 16 bits, two results with one cvt.pack.sat where they can).
+// The 64-bit sum is first saturated to +-(2^31 - 1): everything beyond that saturates in the result
+// anyway (2^31 - 1 >= 32768 * 65535), and the magnitude then fits the 32 x 32 -> 64 bit multiply.
+__device__ __forceinline__ int mix_divide_raw(long long n, uint32_t magic, uint32_t shift)
+{
+    int ns;
+    asm("cvt.sat.s32.s64 %0, %1;" : "=r"(ns) : "l"(n));
+    ns = max(ns, -0x7fffffff);
+    const uint32_t a = (uint32_t)abs(ns);
+    const uint32_t q = (uint32_t)(((unsigned long long)a * magic) >> shift);      // < 2^31
+    const int sgn = ns >> 31;
+    return ((int)q ^ sgn) - sgn;
+}
 __device__ __forceinline__ int mix_divide(long long n, uint32_t magic, uint32_t shift)
 {
-    // exact trunc(n / scale) wherever the quotient is inside the clamp range
-    const long long lim = 0x7fffffffll;
-    const long long c = n > lim ? lim : (n < -lim ? -lim : n);
-    const uint32_t a = (uint32_t)(c < 0 ? -c : c);
-    const uint32_t q = (uint32_t)(((unsigned long long)a * magic) >> shift);
-    const int y = c < 0 ? -(int)q : (int)q;
-    return max(min(y, 32767), -32768);
+    return max(min(mix_divide_raw(n, magic, shift), 32767), -32768);
 }
 
 template <int NCH>
@@ -278,19 +286,22 @@ __global__ void __launch_bounds__(256, 2) mix8to2_tick(const __grid_constant__ M
         const uint32_t radd = 0xffffu - (iu);                                               \
         do_vector<8, GM_IDENTITY, true, false, false>(vec_, none, radd, kin, pin, 8);       \
         const uint32_t xw[4] = {(vec_).x, (vec_).y, (vec_).z, (vec_).w};                    \
-        int y[2];                                                                           \
+        int r[2];                                                                           \
         _Pragma("unroll") for (int m = 0; m < 2; m++) {                                     \
             int lo = 0, hi = 0;                                                             \
             _Pragma("unroll") for (int p = 0; p < 4; p++) {                                 \
                 lo = dp2a_lo_su(xw[p], B[m][p], lo);                                        \
                 hi = dp2a_hi_su(xw[p], B[m][p], hi);                                        \
             }                                                                               \
-            y[m] = mix_divide((long long)hi * 256 + lo, magic, shift);                      \
-            const uint32_t mg = (uint32_t)abs(y[m]);                                        \
-            kout[m] = max(kout[m], (mg << 16) + radd);                                      \
-            pout[m] += (uint64_t)((int64_t)y[m] * y[m]);                                    \
+            r[m] = mix_divide_raw((long long)hi * 256 + lo, magic, shift);                  \
         }                                                                                   \
-        dst[(size_t)(iu) * 32] = ((uint32_t)y[0] & 0xffffu) | ((uint32_t)y[1] << 16);       \
+        const uint32_t ow = pack_sat16(r[1], r[0]);      /* saturate both, pack: one instruction */ \
+        const int y0 = (int)(short)(ow & 0xffffu), y1 = (int)ow >> 16;                      \
+        kout[0] = max(kout[0], ((uint32_t)abs(y0) << 16) + radd);                           \
+        kout[1] = max(kout[1], ((uint32_t)abs(y1) << 16) + radd);                           \
+        pout[0] += (uint64_t)((int64_t)y0 * y0);                                            \
+        pout[1] += (uint64_t)((int64_t)y1 * y1);                                            \
+        dst[(size_t)(iu) * 32] = ow;                                                        \
     }
 #define CMGPU_MIX_LOAD(buf, b)                                                              \
     _Pragma("unroll") for (int u = 0; u < UNROLL; u++)                                      \
