@@ -43,7 +43,7 @@
 #define CMGPU_VEC_FENCE_STMT
 #endif
 #ifndef CMGPU_G8_CTAS
-#define CMGPU_G8_CTAS 3
+#define CMGPU_G8_CTAS 4
 #endif
 #ifndef CMGPU_G8_CTAS_WIDE
 #define CMGPU_G8_CTAS_WIDE 2
