@@ -45,6 +45,7 @@ extern "C" {
 #include <coolmic-dsp/iohandle.h>
 #include <coolmic-dsp/transform.h>
 #include <coolmic-dsp/vumeter.h>
+#include <coolmic-dsp/util.h>
 typedef igloo_ro_t coolmic_b200_ro_t;
 #define COOLMIC_B200_MAX_CHANNELS COOLMIC_DSP_TRANSFORM_MAX_CHANNELS
 #else
@@ -98,6 +99,14 @@ int                coolmic_vumeter_reset(coolmic_vumeter_t *self);
 int                coolmic_vumeter_attach_iohandle(coolmic_vumeter_t *self, coolmic_iohandle_t *handle);
 ssize_t            coolmic_vumeter_read(coolmic_vumeter_t *self, ssize_t maxlen);
 int                coolmic_vumeter_result(coolmic_vumeter_t *self, coolmic_vumeter_result_t *result);
+
+/* Meter results -> colours (reference include/coolmic-dsp/util.h:40-47, src/util.c:59-139). Host-side
+ * double arithmetic with the reference's expressions and libm: identical doubles and ARGB words. */
+#define COOLMIC_UTIL_PROFILE_DEFAULT "default"
+typedef uint32_t coolmic_argb_t;
+coolmic_argb_t coolmic_util_ahsv2argb(double alpha, double hue, double saturation, double value);
+double         coolmic_util_power2hue(double power, const char *profile);
+double         coolmic_util_peak2hue(int16_t peak, const char *profile);
 #endif /* COOLMIC_B200_WITH_IGLOO */
 
 /* ---- batch mode: the same objects, many streams per GPU tick ---------------
