@@ -157,7 +157,7 @@ struct cmgpu_ctx {
     // launch plan (depends on shape only)
     int plan_g = 32;              // lanes per item (fast kernels); 0 = frame-per-lane generic kernel; -1 = any_tick
     int plan_lanes = 32;          // any_tick: lanes of a warp that take part
-    // long mono / stereo stream-blocks: TMA-staged kernel (cmgpu_tma.cuh) with its own item geometry
+    // long stream-blocks, opt-in: TMA-staged kernel (cmgpu_tma.cuh) with its own item geometry
     bool tma = false;
     uint32_t tma_items = 1, tma_per_item = 0;
     int tma_grid_cap[3][2] = {{0, 0}, {0, 0}, {0, 0}};
@@ -392,10 +392,10 @@ void make_plan(cmgpu_ctx *c)
     c->plan_g = g;
     c->plan_items = items;
     c->plan_per_item = per;
-    // Opt-in (CMGPU_TMA=1): stream-blocks of >= 128 KiB with 1 or 2 channels staged through shared
-    // memory with TMA bulk copies. Measured on B200: as a pure copy it beats the LDG
-    // pattern (0.632 vs 0.650 ms on cfg2), fused it does not (0.684 vs 0.650 ms) -- the fused tick is
-    // instruction-bound by then -- so the LDG kernel stays the default.
+    // Opt-in (CMGPU_TMA=1): stream-blocks of >= 128 KiB with their loads staged through shared memory
+    // by TMA bulk copies (cmgpu_tma.cuh). Measured on B200: as a pure copy it equals the
+    // LDG kernel (0.650 ms on cfg2), with gain + meter it is slower (0.71 vs 0.62-0.65), so the LDG
+    // kernel stays the default.
     if (nvec >= 8192 && getenv("CMGPU_TMA")) {
         uint32_t tile_target = 8 * cmgpu::kTmaTileVecs;
         if (const char *e = getenv("CMGPU_TMA_ITEM_TILES"))         // tuning hook

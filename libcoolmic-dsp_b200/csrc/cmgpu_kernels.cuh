@@ -18,7 +18,7 @@
 #include <cuda_runtime.h>
 
 #ifndef CMGPU_UNROLL
-#define CMGPU_UNROLL 4      // register slots of the rolling prefetch ring per lane
+#define CMGPU_UNROLL 4      // vectors per load batch of a lane (two batches are held in registers)
 #endif
 #ifndef CMGPU_MIN_CTAS
 #define CMGPU_MIN_CTAS 3    // resident 256-thread CTAs per SM the fast kernels are compiled for
@@ -30,18 +30,10 @@
 #ifndef CMGPU_MIN_CTAS_WIDE
 #define CMGPU_MIN_CTAS_WIDE 2
 #endif
-// 8-lane-group kernels (stream-blocks of <= 1 KiB)
 #ifndef CMGPU_SATPACK_ALL
 #define CMGPU_SATPACK_ALL 1   // 0: the 80-register 1- and 2-channel kernels clamp with two VIMNMX and pack with PRMT instead of I2IP
 #endif
-#ifndef CMGPU_VEC_FENCE
-#define CMGPU_VEC_FENCE 0
-#endif
-#if CMGPU_VEC_FENCE
-#define CMGPU_VEC_FENCE_STMT asm volatile("" ::: "memory");
-#else
-#define CMGPU_VEC_FENCE_STMT
-#endif
+// 8-lane-group kernels (stream-blocks of <= 1 KiB)
 #ifndef CMGPU_G8_CTAS
 #define CMGPU_G8_CTAS 4
 #endif
@@ -588,7 +580,6 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
             st_stream(dstp + (size_t)iu * kStep, o);                                    \
         if (PLANAR)                                                                     \
             store_planar<C>(a.planar, a.plane_stride, (it).s, (it).first + iu * G, o, 8); \
-        CMGPU_VEC_FENCE_STMT                                                            \
     }
 
     uint64_t item = (uint64_t)blockIdx.x * groups_per_cta + threadIdx.x / G;
