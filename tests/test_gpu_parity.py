@@ -404,6 +404,71 @@ def test_overlapping_ticks_on_resident_data(cm, port, monkeypatch, channels, blo
         check_meters(cm, port, eng, meters, n_streams, channels)
 
 
+def test_tick_numbering_across_plain_ticks_and_captured_cycles(cm, port, monkeypatch):
+    """Plain ticks are numbered by the host (an offset from the device's tick counter), the ticks of a
+    captured cycle count from the device counter itself, which is brought up to date before every
+    replay. Mixed freely, later ticks must still lose ties against earlier ones."""
+    monkeypatch.setenv("CMGPU_NO_SPAN", "1")          # force the CUDA-graph form of the cycle
+    rng = np.random.default_rng(4242)
+    channels, n_streams, block, ring = 2, 97, 640, 3
+    data = make_pcm(rng, "ties", (ring, n_streams, block * channels))
+    scale, gain = make_gains(rng, n_streams, channels)
+    scale[:] = 0                                       # pass-through: the ring can be re-read as is
+    plan = [("tick", 2), ("tick", 0), ("cycle", None), ("tick", 1), ("cycle", None), ("cycle", None), ("tick", 0)]
+    with cm.Engine(channels, n_streams, block, ring_slots=ring) as eng:
+        eng.set_gain_table(scale, gain)
+        for slot in range(ring):
+            eng.host_slot(slot)[:, : block * channels] = data[slot]
+            eng.submit(slot)
+        order = []
+        for kind, slot in plan:
+            if kind == "tick":
+                eng.process(slot)
+                order.append(slot)
+            else:
+                eng.process_cycle(0, ring)
+                order += list(range(ring))
+        eng.sync()
+        meters = None
+        frames = np.full(n_streams, block, np.uint32)
+        for slot in order:
+            meters, _ = port.batch(data[slot].copy(), frames, channels, scale, gain, meters=meters)
+        check_meters(cm, port, eng, meters, n_streams, channels)
+
+
+def test_upload_waits_for_ticks_on_resident_data(cm, port):
+    """A tick on resident data records no event of its own; the slot's next upload asks for one. The
+    upload must still not overwrite the slot while such a tick is reading it (in place)."""
+    rng = np.random.default_rng(99)
+    channels, n_streams, block = 2, 64, 200000                   # 51 MB per slot: ticks that take a while
+    a_data = make_pcm(rng, "gauss", (n_streams, block * channels))
+    b_data = make_pcm(rng, "full", (n_streams, block * channels))
+    scale, gain = make_gains(rng, n_streams, channels)
+    frames = np.full(n_streams, block, np.uint32)
+    staging = cm.PinnedArray((n_streams, block * channels))
+    with cm.Engine(channels, n_streams, block) as eng:
+        eng.set_gain_table(scale, gain)
+        eng.host_slot(0)[:, : block * channels] = a_data
+        eng.submit(0)
+        eng.process(0)                  # consumes the upload
+        eng.process(0)                  # resident data, in place: transforms the transformed block again
+        eng.process(0)
+        staging.array[:] = b_data
+        eng.submit(0, staging.array)    # must wait for all three ticks
+        eng.process(0)
+        eng.fetch(0)
+        eng.sync()
+        work = a_data.copy()
+        meters = None
+        for _ in range(3):
+            meters, _ = port.batch(work, frames, channels, scale, gain, meters=meters)
+        want = b_data.copy()
+        meters, _ = port.batch(want, frames, channels, scale, gain, meters=meters)
+        assert np.array_equal(eng.host_slot(0)[:, : block * channels], want)
+        check_meters(cm, port, eng, meters, n_streams, channels)
+    staging.free()
+
+
 @pytest.mark.parametrize("channels,block,ragged,no_span", [
     (1, 320, False, False), (1, 320, False, True), (1, 320, True, False), (2, 4799, False, False),
     (2, 20000, True, False), (8, 257, False, False), (16, 100, True, False), (4, 333, False, True), (6, 500, False, False)])
