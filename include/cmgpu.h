@@ -132,12 +132,18 @@ int cmgpu_slot_set_frames(cmgpu_ctx_t *ctx, unsigned slot, const uint32_t *frame
  * Asynchronous when the source is page-locked. */
 int cmgpu_submit(cmgpu_ctx_t *ctx, unsigned slot, const void *host);
 /* One tick: ONE fused kernel launch over all active streams of the slot, on the compute
- * stream, ordered after the slot's last submit. Asynchronous. */
+ * stream, ordered after the slot's last submit. Asynchronous. Ticks on data that is already on
+ * the device (no submit / fetch of the slot since its last tick) are bare kernel launches, and
+ * consecutive ones overlap at their edges when they cannot conflict (different slots, or a
+ * CMGPU_SEPARATE_OUT context): the meters do not depend on completion order. */
 int cmgpu_process(cmgpu_ctx_t *ctx, unsigned slot, unsigned flags);
-/* Small-buffer regime: `n_slots` consecutive ticks (slots first_slot ..) replayed as ONE cached
- * CUDA graph launch, so that per-tick launch latency does not dominate 20 ms blocks. Ordered
- * after the slots' last submits; the graph is rebuilt when gains, frames or the active stream
- * count change. Asynchronous. */
+/* Small-buffer regime: `n_slots` consecutive ticks (slots first_slot ..) issued as ONE launch that
+ * walks all of them (the ring is one allocation), so that per-tick launch latency does not
+ * dominate 20 ms blocks; contexts whose kernels cannot do that (channel counts that do not tile 16
+ * bytes, downmix, float planes, frame counts set for only some of the slots) get ONE cached CUDA
+ * graph of per-tick launches instead, rebuilt when gains, frames or the active stream count
+ * change. Either way the ticks count as slots first_slot, first_slot + 1, ... in time order.
+ * Ordered after the slots' last submits. Asynchronous. */
 int cmgpu_process_cycle(cmgpu_ctx_t *ctx, unsigned first_slot, unsigned n_slots, unsigned flags);
 /* Device -> host copy of the slot's (transformed) PCM on the download stream, ordered after
  * the slot's last tick. `host` NULL = the pinned staging slot. Asynchronous if page-locked. */
