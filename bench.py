@@ -252,6 +252,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    ap.add_argument("--e2e-no-gather", action="store_true", help="diagnostic: skip the NCCL meter gather in the end-to-end steps")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -452,8 +453,9 @@ def main():
                 eng.submit(slot, pin_in.array[t])
                 eng.process(slot)
                 eng.fetch(slot, pin_out.array[t])
-            meter_rows = eng.snapshot(reset=dist is None)       # D2H of the integer meter state (+ reset)
-            if dist is not None:
+            gather = dist is not None and not args.e2e_no_gather
+            meter_rows = eng.snapshot(reset=not gather)         # D2H of the integer meter state (+ reset)
+            if gather:
                 tg = time.perf_counter()
                 gathered = gather_meters(cm, eng, dist, rank, world)
                 gather_s[0] += time.perf_counter() - tg
