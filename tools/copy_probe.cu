@@ -39,6 +39,61 @@ __global__ void __launch_bounds__(256, 3) copy_warp_chunks(const uint4 *__restri
     }
 }
 
+
+// (1b) the same loads, but the stores go through a per-warp shared-memory staging tile and leave as
+//      ONE bulk store (cp.async.bulk shared -> global) of BATCHES x 2 KiB per warp: does the write side
+//      of the pattern get cheaper when it arrives in bulk?
+template <int BATCHES>
+__global__ void __launch_bounds__(256, 3) copy_warp_chunks_bulk_store(const uint4 *__restrict__ in, uint4 *__restrict__ out, size_t nvec, uint32_t per_item)
+{
+    extern __shared__ __align__(128) uint8_t stage[];       // [warp][2 tiles][BATCHES * 2048]
+    constexpr uint32_t kTile = BATCHES * 2048;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *mine = stage + (size_t)warp * 2 * kTile;
+    const size_t n_items = (nvec + per_item - 1) / per_item;
+    const size_t stride = (size_t)gridDim.x * 8;
+    uint32_t t = 0;
+    for (size_t item = (size_t)blockIdx.x * 8 + warp; item < n_items; item += stride) {
+        const size_t v0 = item * per_item;
+        const uint4 *src = in + v0 + lane;
+        const uint32_t n_b = per_item / 128;               // batches of 4 vectors per lane
+        uint4 a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) a[u] = __ldg(src + (size_t)u * 32);
+        for (uint32_t bi = 0; bi < n_b; bi++) {
+            if (bi + 1 < n_b) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) b[u] = __ldg(src + (size_t)((bi + 1) * 4 + u) * 32);
+            }
+            const uint32_t sub = bi % BATCHES;
+            uint8_t *tile = mine + (size_t)(t & 1u) * kTile;
+            if (sub == 0) {
+                // the tile is free again once the bulk store issued two tiles ago has read it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                *reinterpret_cast<uint4 *>(tile + (size_t)sub * 2048 + (size_t)u * 512 + lane * 16) = a[u];
+            if (sub == BATCHES - 1 || bi + 1 == n_b) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    const uint32_t bytes = (sub + 1) * 2048;
+                    uint8_t *dst = reinterpret_cast<uint8_t *>(out + v0) + (size_t)(bi - sub) * 2048;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                                 "r"((uint32_t)__cvta_generic_to_shared(tile)), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                t++;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) a[u] = b[u];
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // (2) classic grid-stride elementwise copy, 4 x 128-bit per thread per step, whole grid sweeps memory in lockstep
 __global__ void __launch_bounds__(256) copy_grid_stride(const uint4 *__restrict__ in, uint4 *__restrict__ out, size_t nvec)
 {
@@ -159,6 +214,30 @@ int main()
         char name[64];
         snprintf(name, sizeof(name), "warp chunks, %u vectors per item", per);
         report(name, best);
+    }
+
+    {
+        auto run_bulk = [&](auto kern, int batches, const char *label) {
+            const int smem = 8 * 2 * batches * 2048;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            int occ = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem);
+            float b2 = 1e9, m2;
+            for (int r = 0; r < 6; r++) {
+                cudaEventRecord(e0);
+                kern<<<sms * occ, 256, smem>>>((const uint4 *)in, (uint4 *)out, nvec, 2048u);
+                cudaEventRecord(e1);
+                cudaEventSynchronize(e1);
+                cudaEventElapsedTime(&m2, e0, e1);
+                if (r && m2 < b2) b2 = m2;
+            }
+            char name[96];
+            snprintf(name, sizeof(name), "warp chunks, LDG + %s bulk stores, %d CTA/SM", label, occ);
+            report(name, b2);
+        };
+        run_bulk(copy_warp_chunks_bulk_store<1>, 1, "2 KiB");
+        run_bulk(copy_warp_chunks_bulk_store<2>, 2, "4 KiB");
+        run_bulk(copy_warp_chunks_bulk_store<4>, 4, "8 KiB");
     }
     for (int mult : {4, 8, 16}) {
         best = 1e9;
