@@ -378,8 +378,12 @@ void make_plan(cmgpu_ctx *c)
     const uint32_t nvec = (uint32_t)(c->stride / 16);
     // stream-blocks of up to 1 KiB are walked by 8-lane groups so that no lane idles
     const int g = (nvec <= 64 && C != 16) ? 8 : 32;
-    // aim for ~32 KiB (2048 vectors) per item, a multiple of 4 steps of the group
-    uint32_t target = 2048;
+    // Aim for 24 KiB (1,536 vectors) per item for mono / stereo and 32 KiB (2,048) for wider frames, a
+    // multiple of 4 steps of the group. Measured, not derived (tools/sweep_item.sh on two boxes, with
+    // overlapping launches): stereo cfg2 0.620 ms at 2,048, 0.598-0.601 at 1,536, 0.607 at 1,280, 0.604 at
+    // 4,096; cfg5 4.11 / 4.01 / 4.04 ms at 2,048 / 1,536 / 1,280; 8-channel cfg4a 1.98 at 1,536, 1.93 at
+    // 2,048, 1.92 at 4,096.
+    uint32_t target = C <= 2 ? 1536 : 2048;
     if (const char *e = getenv("CMGPU_ITEM_VECS"))          // tuning hook
         target = (uint32_t)strtoul(e, nullptr, 10) ? (uint32_t)strtoul(e, nullptr, 10) : target;
     if (target > 32768)                                       // item_publish: vector indices of an item fit 16 bits
