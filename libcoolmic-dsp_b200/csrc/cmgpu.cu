@@ -17,6 +17,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <algorithm>
 #include <vector>
 
 using cmgpu::GainRow;
@@ -146,9 +147,13 @@ struct cmgpu_ctx {
     uint64_t config_gen = 0, graph_gen = ~0ull;    // bumped whenever launch arguments may change
     // tick numbering: ticks issued by plain / span launches since the device counter was last bumped
     uint32_t pending_ticks = 0;
-    // slots of the previous tick launch on s_cmp (~0u: something else was queued since), for the
-    // overlap rule of programmatic dependent launch
-    unsigned last_first = ~0u, last_n = 0;
+    // Overlap rule of programmatic dependent launch. A chain of overlapping launches is open on s_cmp
+    // while every launch since the last full dependency was marked dependent-launchable; in_chain[slot]
+    // says which slots those launches touch. A small grid does not fill the GPU, so ANY launch of the
+    // chain may still be running when the next one starts -- not just the previous one.
+    bool chain_open = false;
+    std::vector<uint8_t> in_chain;
+    unsigned last_first = ~0u, last_n = 0;         // ~0u: something other than a tick was queued last
 
     // how many active streams need which gain mode; the tick runs in the cheapest common one
     unsigned n_mode[3] = {0, 0, 0};                // GM_IDENTITY / GM_MASKED / GM_ADDALL
@@ -548,7 +553,9 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
         if (grid > (uint64_t)occ * c->num_sms)
             grid = (uint64_t)occ * c->num_sms;
         // a downmix context always has its own output ring: consecutive ticks never conflict
-        const bool mpdl = !captured && st == c->s_cmp && c->last_first != ~0u && !getenv("CMGPU_NO_PDL");
+        const bool mpdl = !captured && st == c->s_cmp && c->chain_open && c->last_first != ~0u && !getenv("CMGPU_NO_PDL");
+        if (!captured && st == c->s_cmp)
+            c->chain_open = true;
         if (vec8)
             CU(launch_kernel(cmgpu::mix8to2_tick, (unsigned)grid, 256, 0, st, mpdl, m));
         else
@@ -601,14 +608,23 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
     a.n_ticks = n_ticks;
     a.frames_stride = c->max_streams;
     a.slot_bytes = c->slot_bytes;
-    // Overlap with the previous tick launch of the compute stream is safe when this launch reads
-    // nothing that one writes: other ring slots, or a separate output ring (the input ring is then
-    // read-only for ticks). Anything else queued on the stream in between (uploads of gains or
-    // frames, snapshots, event waits on a slot's upload) is an ordinary full dependency anyway.
+    // A launch may start while earlier tick launches of the compute stream are still running when it
+    // reads nothing any of them writes: slots none of the still-open chain touches, or a separate
+    // output ring (the input ring is then read-only for ticks). Anything else queued on the stream
+    // in between (uploads of gains or frames, snapshots, event waits on a slot's upload) is an
+    // ordinary full dependency anyway and closes the chain.
     bool pdl = false;
-    if (!captured && st == c->s_cmp && c->last_first != ~0u && !getenv("CMGPU_NO_PDL")) {
-        const bool disjoint = slot >= c->last_first + c->last_n || slot + n_ticks <= c->last_first;
-        pdl = separate || disjoint;
+    if (!captured && st == c->s_cmp) {
+        bool conflict = false;
+        if (!separate)
+            for (unsigned i = slot; i < slot + n_ticks && i < c->slots; i++)
+                conflict = conflict || c->in_chain[i];
+        pdl = c->chain_open && c->last_first != ~0u && !conflict && !getenv("CMGPU_NO_PDL");
+        if (!pdl)
+            std::fill(c->in_chain.begin(), c->in_chain.end(), 0);      // a full dependency: everything before is done
+        for (unsigned i = slot; i < slot + n_ticks && i < c->slots; i++)
+            c->in_chain[i] = 1;
+        c->chain_open = true;
     }
     CU(launch_tick(c, a, gm, meter, st, pdl));
     c->launches++;
@@ -665,6 +681,7 @@ int ticks_done_event_locked(cmgpu_ctx *c, unsigned slot)
         CU(cudaEventRecord(c->ev_cmp[slot], c->s_cmp));
         c->cmp_unrecorded[slot] = 0;
         c->last_first = ~0u;
+        c->chain_open = false;
     }
     return CMGPU_OK;
 }
@@ -835,6 +852,7 @@ static cmgpu_ctx_t *ctx_create_impl(int device, unsigned channels, unsigned out_
     c->up_pending.assign(ring_slots, 0);
     c->down_pending.assign(ring_slots, 0);
     c->cmp_unrecorded.assign(ring_slots, 0);
+    c->in_chain.assign(ring_slots, 0);
     for (unsigned i = 0; i < ring_slots; i++) {
         if ((e = cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&c->ev_cmp[i], cudaEventDisableTiming)) != cudaSuccess ||
@@ -1334,6 +1352,7 @@ int cmgpu_time_process(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, un
 static int flush_ticks_locked(cmgpu_ctx *c)
 {
     c->last_first = ~0u;
+    c->chain_open = false;
     if (!c->pending_ticks)
         return CMGPU_OK;
     cmgpu::bump_tick<<<1, 32, 0, c->s_cmp>>>(c->d_tick, c->pending_ticks);

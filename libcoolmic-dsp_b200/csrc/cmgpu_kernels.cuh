@@ -165,12 +165,13 @@ __device__ __forceinline__ uint64_t tick_pos_base(const unsigned long long *tick
 __device__ __forceinline__ uint64_t tick_begin(const TickArgs &a) { return tick_pos_base(a.tick, a.tick_offset, a.pbits); }
 
 // Programmatic dependent launch: every tick kernel lets the NEXT launch of its stream start as soon
-// as its own CTAs have all started (they are all resident at once), so the next tick's CTAs take
-// over SM by SM while this tick's last work items drain -- no idle tail, no launch gap, no ramp
-// between ticks. Only launches the host marked as independent of their predecessor use it
-// (different ring slots, or a read-only input ring); meter updates are atomics on order-free
-// position keys. launch_end keeps completion in stream order: a launch does not finish before the
-// one it overlapped.
+// as its own CTAs have all started, so the next tick's CTAs take over SM by SM while this tick's last
+// work items drain -- no idle tail, no launch gap, no ramp between ticks. A grid that does not fill
+// the GPU lets the launch after the next start too, and so on: any number of consecutive launches
+// may be in flight at once. Only launches the host marked as independent of EVERY launch that may
+// still be running use it (slots that none of them touches, or a read-only input ring); meter
+// updates are atomics on order-free position keys. launch_end keeps completion in stream order: a
+// launch does not finish before the one before it.
 __device__ __forceinline__ void launch_begin() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void launch_end() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tick_end(const TickArgs &) { launch_end(); }
