@@ -153,7 +153,7 @@ struct cmgpu_ctx {
     // chain may still be running when the next one starts -- not just the previous one.
     bool chain_open = false;
     std::vector<uint8_t> in_chain;
-    unsigned last_first = ~0u, last_n = 0;         // ~0u: something other than a tick was queued last
+    unsigned last_first = ~0u;                     // slot of the last tick launch; ~0u: something else was queued last
 
     // how many active streams need which gain mode; the tick runs in the cheapest common one
     unsigned n_mode[3] = {0, 0, 0};                // GM_IDENTITY / GM_MASKED / GM_ADDALL
@@ -563,10 +563,8 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
         c->launches++;
         if (!captured) {
             c->pending_ticks += 1;
-            if (st == c->s_cmp) {
+            if (st == c->s_cmp)
                 c->last_first = slot;
-                c->last_n = 1;
-            }
         }
         return CMGPU_OK;
     }
@@ -630,10 +628,8 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
     c->launches++;
     if (!captured) {
         c->pending_ticks += n_ticks;
-        if (st == c->s_cmp) {
+        if (st == c->s_cmp)
             c->last_first = slot;
-            c->last_n = n_ticks;
-        }
     }
     return CMGPU_OK;
 }
