@@ -3,18 +3,24 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-Workload (default `cfg2`, BASELINE.json configs[1]): per GPU 1,024 independent 48 kHz stereo S16
-streams x 10 s, resident in one device ring; one step = one fused tick (ONE kernel launch) over the
-whole ring = 9.8304e8 samples, 3.93 GB of algorithmic traffic (2 B read + 2 B written per sample),
-far larger than the 126 MB L2. With N > 1 every rank holds its own 1,024 streams (streams shard
-trivially; no data-path collective) -> weak scaling; the per-stream meter rows are gathered to
-rank 0 over NCCL outside the kernel-timed region and inside the end-to-end one.
+Workload (default `cfg5`, BASELINE.json configs[4], the configuration north_star states both targets
+on): 65,536 independent 48 kHz stereo S16 streams x 1 s IN TOTAL, sharded by contiguous stream range
+across the N GPUs (strong scaling; all of it fits one GPU: 12.6 GB in + 12.6 GB out), resident in one
+device ring per GPU; one step = one fused tick (ONE kernel launch per GPU) over the rank's share =
+6.29e9 samples and 25.2 GB of algorithmic traffic in total (2 B read + 2 B written per sample), far
+larger than the 126 MB L2. No data-path collective; the per-stream meter results are gathered to rank
+0 over NCCL by the C library (cmgpu_gather_results) outside the kernel-timed region and inside the
+end-to-end one. No PyTorch anywhere: under torchrun this script only reads RANK / LOCAL_RANK /
+WORLD_SIZE; the communicator, barriers and max-over-ranks are the library's own NCCL calls.
 
 `value`  device-timed (CUDA events on the engine's compute stream, max over ranks), inputs in HBM.
-`e2e`    the same work through the C ABI with pinned HOST buffers: per step every 1 s tick of the
-         10 s is uploaded, processed and downloaded through a 4-slot ring on three CUDA streams,
-         then the meter state is read back; wall clock, max over ranks.
-`roofline` algorithmic bytes / measured kernel time against MEASURED_PEAKS.json's HBM copy rate.
+`e2e`    the same work through the C ABI with pinned HOST buffers: per step every tick is uploaded,
+         processed and downloaded through a 4-slot ring on three CUDA streams, then the meter results
+         are gathered (NCCL at N>1) and finalised; wall clock, max over ranks. A second leg runs the
+         reference-named object API (coolmic_b200_batch_tick over member transforms fed by memory
+         iohandles) on the cfg2 shape; `link` is what the host link gives when every rank drives it.
+`roofline` algorithmic bytes / measured kernel time against MEASURED_PEAKS.json's HBM copy rate: the
+         burst figure of the timed steps, a >= 2 s sustained run, and one slot in place without overlap.
 `cpu_baseline` the reference's own transform.c/tee.c/vumeter.c object code (oracle/_ref) on this
          box's host cores over a bounded sample of the same workload.
 
@@ -23,6 +29,7 @@ rank 0 over NCCL outside the kernel-timed region and inside the end-to-end one.
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -38,33 +45,39 @@ sys.path.insert(0, str(ROOT))
 
 WORKLOADS = {
     # device-timed run: `ticks` ticks of `frames` frames over a ring of `ring` slots per step
-    # (graph=True: the ring's ticks replayed as one CUDA graph launch); e2e: `e2e_ticks` ticks of `e2e_frames`
+    # (graph=True: the ring's ticks issued as one cycle); e2e: `e2e_ticks` ticks of `e2e_frames`;
+    # tone: period[(f + sstep*s + cstep*c) mod n] of the reference's snddev_sine period at `rate`
     "cfg2": dict(channels=2, streams=1024, rate=48000, frames=480000, ticks=1, ring=1, graph=False,
-                 e2e_frames=12000, e2e_ticks=40,
+                 e2e_frames=12000, e2e_ticks=40, sstep=7, cstep=3,
                  desc="1,024 x 48 kHz stereo S16 streams x 10 s per GPU, one device ring, one fused tick per step"),
     "cfg3": dict(channels=1, streams=16384, rate=16000, frames=320, ticks=50, ring=50, graph=True,
-                 e2e_frames=320, e2e_ticks=50,
+                 e2e_frames=320, e2e_ticks=50, sstep=5, cstep=0,
                  desc="16,384 x 16 kHz mono streams, 20 ms (320-frame, 640-byte) stream-blocks; step = one cycle of 50 "
                       "ticks over a 50-slot ring (1.05 GB in+out) issued as ONE span launch (cmgpu_process_cycle)"),
     "cfg4a": dict(channels=8, streams=4096, rate=48000, frames=96000, ticks=1, ring=1, graph=False,
-                  e2e_frames=2400, e2e_ticks=40,
+                  e2e_frames=2400, e2e_ticks=40, sstep=7, cstep=5,
                   desc="4,096 x 48 kHz 8-channel S16 streams x 2 s per GPU, per-channel gain + 8-channel meter (parity mode)"),
     "cfg5x": dict(channels=2, streams=65536, rate=48000, frames=49152, ticks=1, ring=1, graph=False,
-                  e2e_frames=4800, e2e_ticks=10, strong=True,
+                  e2e_frames=4800, e2e_ticks=10, strong=True, sstep=7, cstep=3,
                   desc="DIAGNOSTIC: cfg5 with 49,152 frames per stream (stream-blocks that divide into equal work items)"),
     "cfg6ch": dict(channels=6, streams=4096, rate=48000, frames=48000, ticks=1, ring=1, graph=False,
-                   e2e_frames=4800, e2e_ticks=10,
+                   e2e_frames=4800, e2e_ticks=10, sstep=7, cstep=3,
                    desc="DIAGNOSTIC: 4,096 x 48 kHz 6-channel (5.1) streams x 1 s per GPU -- a channel count that does not tile a "
                         "16-byte vector (any-channel kernel)"),
     "cfg4b": dict(channels=8, streams=4096, rate=48000, frames=96000, ticks=1, ring=1, graph=False,
-                  e2e_frames=9600, e2e_ticks=10, mix_out=2, bytes_per_sample=2.5,
+                  e2e_frames=9600, e2e_ticks=10, mix_out=2, bytes_per_sample=2.5, sstep=7, cstep=5,
                   desc="EXTENSION, PARITY UNPINNED (the reference has no downmix): 4,096 x 48 kHz 8-channel streams x 2 s "
                        "per GPU, 8->2 integer downmix + metering of the 8 input and 2 output channels; 16 B read + 4 B "
                        "written per frame; checked against our own CPU restatement only"),
+    "cfg2p": dict(channels=2, streams=1024, rate=48000, frames=240000, ticks=1, ring=1, graph=False, planar=True,
+                  bytes_per_sample=8.0, e2e_frames=12000, e2e_ticks=20, sstep=7, cstep=3,
+                  desc="DIAGNOSTIC (SURVEY 8f N2): cfg2 x 5 s with the float-plane second output (S16 -> planar float "
+                       "/32768.f, enc_vorbis.c:108-117): 2 B read + 2 B + 4 B written per sample"),
     "cfg5": dict(channels=2, streams=65536, rate=48000, frames=48000, ticks=1, ring=1, graph=False,
-                 e2e_frames=4800, e2e_ticks=10, strong=True,
+                 e2e_frames=4800, e2e_ticks=10, strong=True, sstep=7, cstep=3,
                  desc="65,536 x 48 kHz stereo S16 streams x 1 s in total, sharded by stream across the GPUs"),
 }
+NOISE_EVERY, NOISE_PHASE = 16, 5
 
 
 def gain_table(first_stream: int, n: int, channels: int):
@@ -85,23 +98,6 @@ def mix_table(first_stream: int, n: int, cin: int, cout: int):
     c = np.arange(cin)[None, None, :]
     w = (scale[:, None, None].astype(np.int64) // cin + 11 * ((s[:, None, None] + c + 3 * m) % 32)).astype(np.uint16)
     return scale, w
-
-
-def synth_block(first_stream: int, n: int, channels: int, frames: int, out: np.ndarray, first_frame: int = 0):
-    """Synthetic 1 kHz tone at 48 kHz (48-sample period), phase-shifted per stream and channel, with
-    every 16th stream replaced by full-range hash noise to exercise the clamp and the tie-breaks."""
-    period = np.round(32766 * np.sin(2 * np.pi * np.arange(48) / 48)).astype(np.int16)
-    tiled = np.tile(period, frames // 48 + 3)
-    for i in range(n):
-        s = first_stream + i
-        row = out[i]
-        if s % 16 == 5:
-            rng = np.random.default_rng(s * 1000003 + first_frame)
-            row[: frames * channels] = rng.integers(-32768, 32768, size=frames * channels).astype(np.int16)
-            continue
-        for c in range(channels):
-            off = (first_frame + 7 * s + 3 * c) % 48
-            row[c: frames * channels: channels] = tiled[off: off + frames]
 
 
 class ClockSampler:
@@ -177,11 +173,13 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
 
 
-def cpu_reference_run(channels, rate, frames, budget_s=12.0, threads=None, streams=None):
+def cpu_reference_run(wl, budget_s=12.0, threads=None, streams=None):
     """The reference's own CPU path (oracle/_ref: mem -> transform -> tee -> {consumer, vumeter},
     1,024-byte pulls, result every 20 reads) over `streams` streams of the workload on `threads`
     pthreads, repeated until ~budget_s seconds have been spent. Falls back to the oracle port."""
     from oracle import pyoracle
+    from libcoolmic_dsp_b200 import synth
+    channels, rate, frames = wl["channels"], wl["rate"], wl["frames"] * wl["ticks"]
     threads = threads or os.cpu_count() or 1
     ref = pyoracle.ref()
     streams = streams or max(threads, min(4 * threads, 256))
@@ -190,8 +188,9 @@ def cpu_reference_run(channels, rate, frames, budget_s=12.0, threads=None, strea
         frames //= 2
     while streams * frames * channels < 4_000_000:      # tiny blocks: more streams, same shape
         streams *= 2
-    pcm = np.empty((streams, frames * channels), dtype=np.int16)
-    synth_block(0, streams, channels, frames, pcm)
+    period = synth.load_period(rate)
+    pcm = np.ascontiguousarray(synth.synth_rows(period, 0, streams, channels, frames, 0, wl["sstep"], wl["cstep"],
+                                                NOISE_EVERY, NOISE_PHASE))
     scale, gain = gain_table(0, streams, channels)
     samples_per_pass = streams * frames * channels
     passes, spent = 0, 0.0
@@ -224,6 +223,18 @@ def dist_env():
     return rank, world, local
 
 
+def rendezvous_path() -> str:
+    """Where rank 0 publishes the NCCL unique id: unique per launcher (its pid and start time) and per
+    MASTER_PORT, so that neither a concurrent job nor a stale file of a dead one can be picked up."""
+    ppid = os.getppid()
+    try:
+        start = Path(f"/proc/{ppid}/stat").read_text().rsplit(")", 1)[1].split()[19]
+    except Exception:
+        start = "0"
+    port = os.environ.get("MASTER_PORT", "0")
+    return f"/tmp/cmgpu_nccl_{ppid}_{start}_{port}.id"
+
+
 def emit(line: dict):
     """The ONE JSON line, on the real stdout (libraries such as NCCL print to fd 1 too)."""
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
@@ -243,16 +254,20 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="fused", choices=["fused", "transform", "meter", "copy"],
                     help="diagnostic: which parts of the tick run in the device-timed loop (default: fused = the product)")
-    ap.add_argument("--verify", action="store_true",
-                    help="after the timed end-to-end steps, have rank 0 re-derive a few streams of every rank with the "
-                         "oracle (checker only, outside every timed region) and compare PCM + gathered meter rows")
+    ap.add_argument("--no-verify", action="store_true",
+                    help="skip the parity spot check (rank 0 re-derives a few streams of every rank with the oracle after "
+                         "the timed end-to-end steps -- checker only, outside every timed region)")
+    ap.add_argument("--verify", action="store_true", help="(default; kept for older command lines)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sustained / in-place roofline figures, the link probe and the object-API end-to-end leg")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
-    ap.add_argument("--e2e-no-gather", action="store_true", help="diagnostic: skip the NCCL meter gather in the end-to-end steps")
+    ap.add_argument("--e2e-no-gather", action="store_true", help="diagnostic: skip the NCCL result gather in the end-to-end steps")
+    ap.add_argument("--e2e-wc", action="store_true", help="diagnostic: write-combined pinned upload buffers")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -265,14 +280,16 @@ def main():
     if wl.get("strong"):
         streams_per_gpu //= max(world, 1)
         scaling = "strong"
-    seconds = frames * ticks / rate
     samples_per_step_rank = streams_per_gpu * frames * ticks * channels
     ring_bytes = 2 * ring * streams_per_gpu * frames * channels * 2
     config = {"workload": f"{args.workload}: {desc}", "streams_per_gpu": streams_per_gpu, "channels": channels,
               "rate_hz": rate, "frames_per_tick": frames, "ticks_per_step": ticks, "ring_slots": ring,
               "cycle_api": bool(wl["graph"]), "gains": "every stream active, scale 1000+s%9000, gain ~0.75..3.1",
+              "input": f"one period of the reference's snddev_sine driver at {rate} Hz (tests/golden/sine.json), "
+                       f"sample = period[(f + {wl['sstep']}s + {wl['cstep']}c) mod n]; every {NOISE_EVERY}th stream full-range "
+                       "splitmix64 noise; written by the on-device generator (cmgpu_tone_fill / cmgpu_noise_fill)",
               "l2": f"in+out rings of {ring_bytes / 1e9:.2f} GB per GPU cycled every step: far larger than the 126 MB L2, no flush needed",
-              "sharding": "by stream, one process per GPU, no data-path collective"}
+              "sharding": "by stream, one process per GPU, no data-path collective; NCCL from the C library, no PyTorch"}
     if args.mode != "fused":
         config["diagnostic_mode"] = args.mode
 
@@ -280,12 +297,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        from __graft_entry__ import load_package
+        load_package()
         runs = []
-        for _ in range(args.warmup if args.warmup < 2 else 1):
-            cpu_reference_run(channels, rate, frames * ticks, budget_s=1.0)
+        cpu_reference_run(wl, budget_s=1.0)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            runs.append(cpu_reference_run(channels, rate, frames * ticks, budget_s=max(0.25, 45.0 / max(args.steps, 1))))
+            runs.append(cpu_reference_run(wl, budget_s=max(0.25, 45.0 / max(args.steps, 1))))
         wall = time.perf_counter() - t0
         value = float(np.mean([r["value"] for r in runs]))
         base = dict(runs[-1]); base["value"] = value
@@ -302,36 +320,33 @@ def main():
     # ---------------------------------------------------------------- our arm
     from __graft_entry__ import load_package
     cm = load_package()
+    from libcoolmic_dsp_b200 import synth
     if cm.lib().cmgpu_device_count() < 1:
         raise SystemExit("bench.py: no CUDA device visible; the hot path has no CPU fallback")
 
-    dist = None
+    comm = None
     if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        comm = cm.Comm(local, rank, world, path=rendezvous_path())
 
     def barrier():
-        if dist is not None:
-            import torch
-            dist.barrier()
-            torch.cuda.synchronize()
+        if comm is not None:
+            comm.barrier()
 
     def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return x if comm is None else float(comm.max(x))
+
+    def sum_over_ranks(x: float) -> float:
+        return x if comm is None else float(comm.sum(x))
 
     first_stream = rank * streams_per_gpu      # == sharding.stream_range(world * streams_per_gpu, world, rank)[0]
     scale, gain = gain_table(first_stream, streams_per_gpu, channels)
+    period = synth.load_period(rate)
+    fill = dict(stream_step=wl["sstep"], channel_step=wl["cstep"], noise_every=NOISE_EVERY, noise_phase=NOISE_PHASE)
 
     # ---- device-resident run: the step's ticks live in a ring of `ring` slots, out of place so
     #      that the input stays pristine across steps
     mix_out = wl.get("mix_out", 0)
+    planar = bool(wl.get("planar"))
     bytes_per_sample = wl.get("bytes_per_sample", 4.0)
 
     def configure(e):
@@ -343,35 +358,35 @@ def main():
             e.set_gain_table(scale, gain)
 
     eng = cm.Engine(channels, streams_per_gpu, frames, ring_slots=ring, device=local,
-                    flags=cm.NO_PINNED | (0 if mix_out else cm.SEPARATE_OUT), out_channels=mix_out)
+                    flags=cm.NO_PINNED | (0 if mix_out else cm.SEPARATE_OUT) | (cm.PLANAR_F32 if planar else 0),
+                    out_channels=mix_out)
     configure(eng)
-    chunk = max(1, (256 << 20) // (frames * channels * 2))
-    stage = np.zeros((streams_per_gpu, eng.stride // 2), dtype=np.int16)
+    eng.tone_table(period)
     for slot in range(ring):
-        for lo in range(0, streams_per_gpu, chunk):
-            hi = min(streams_per_gpu, lo + chunk)
-            synth_block(first_stream + lo, hi - lo, channels, frames, stage[lo:hi], slot * frames)
-        eng.submit(slot, stage)
-        eng.sync()
-
-    def timed(steps):
-        if wl["graph"]:
-            return eng.time_cycles(steps * (ticks // ring), 0, ring, flags=pflags)
-        return eng.time_process(steps * ticks, 0, ring, flags=pflags)
+        synth.device_fill(eng, slot, None, first_stream, slot * frames, **fill)
+    eng.sync()
 
     pflags = {"fused": cm.FUSED, "transform": cm.TRANSFORM, "meter": cm.METER, "copy": 0}[args.mode]
+    if planar:
+        pflags |= cm.PLANAR
+
+    def timed(e, steps):
+        if wl["graph"]:
+            return e.time_cycles(steps * (ticks // ring), 0, ring, flags=pflags)
+        return e.time_process(steps * ticks, 0, ring, flags=pflags)
+
     # A run that saw a hardware or thermal slowdown is re-measured once (sw_power_cap is kept and noted).
     bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     remeasured = False
     for attempt in range(2):
         clocks = ClockSampler(local)
         clocks.start()
-        timed(args.warmup)
+        timed(eng, args.warmup)
         eng.reset_meters()
         launches0 = eng.launch_count()
         barrier()
         clocks.mark_begin()
-        ms_total = timed(args.steps)
+        ms_total = timed(eng, args.steps)
         clocks.mark_end()
         barrier()
         clk = clocks.stop()
@@ -394,13 +409,17 @@ def main():
     if wl["graph"]:
         dev_us = min(eng.time_process(1, 0, 1, flags=pflags) for _ in range(20)) * 1e3
         walls = []
-        for _ in range(20):
+        for _ in range(50):
             eng.sync()
             t0 = time.perf_counter()
             eng.process(0, pflags)
             eng.sync()
             walls.append((time.perf_counter() - t0) * 1e6)
+        tick_ms = 1e3 * frames / rate
         config["single_tick"] = {"device_us": dev_us, "launch_to_complete_us": float(np.median(walls)),
+                                 "launch_to_complete_us_min": float(np.min(walls)),
+                                 "cadence": f"real time needs one tick per {tick_ms:g} ms = {1e3 / tick_ms:g} ticks/s; the span "
+                                            f"figure sustains {1e3 * ticks / ms_step:.0f} ticks/s",
                                  "note": "one tick of the same shape issued alone, outside the timed steps"}
     kernel = eng.kernel_name()
     peak, peak_src = measured_peak()
@@ -412,84 +431,154 @@ def main():
                 "traffic": None, "kernel": kernel, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_launch,
                 "launches_per_step": launches_per_step,
-                "frac_of_nominal_8TBps": achieved / 8000.0}
+                "frac_of_nominal_8TBps": achieved / 8000.0,
+                "how": f"{args.steps} back-to-back launches over the resident ring, separate output ring; consecutive launches "
+                       "overlap at their edges (programmatic dependent launch)"}
     prof = ROOT / "profiles" / "traffic.json"
     if prof.exists():
         try:
             roofline["traffic"] = json.loads(prof.read_text()).get(args.workload, {}).get("dram_bytes_per_launch")
         except Exception:
             pass
-    eng.close()
-    del stage
 
-    # ---- end to end through the C ABI with host buffers: 1 s ticks through a 4-slot ring
+    if not args.no_extras and not wl["graph"] and args.mode == "fused":
+        # (a) sustained: >= 2 s of back-to-back ticks (the part runs into its power cap; clocks recorded)
+        n_sus = max(args.steps, int(2200.0 / max(ms_step, 1e-3)) + 1)
+        clocks = ClockSampler(local)
+        clocks.start()
+        barrier()
+        clocks.mark_begin()
+        ms_sus = timed(eng, n_sus)
+        clocks.mark_end()
+        clk_sus = clocks.stop()
+        ms_sus = max_over_ranks(ms_sus) / n_sus
+        sus = bytes_per_sample * samples_per_step_rank / (ms_sus * 1e-3) / 1e9
+        roofline["sustained"] = {"steps": n_sus, "seconds": ms_sus * n_sus * 1e-3, "ms_per_step": ms_sus, "achieved": sus,
+                                 "frac": sus / peak, "clocks": clk_sus}
+    eng.close()
+
+    if not args.no_extras and not wl["graph"] and args.mode == "fused" and not mix_out and not planar:
+        # (b) the in-place figure: ONE slot transformed in place (what the reference does, transform.c:120),
+        #     where the overlap rule forbids consecutive launches to overlap: each tick is a full dependency
+        e2 = cm.Engine(channels, streams_per_gpu, frames, ring_slots=1, device=local, flags=cm.NO_PINNED)
+        configure(e2)
+        synth.device_fill(e2, 0, period, first_stream, 0, **fill)
+        n_ip = max(20, min(args.steps, 50))
+        e2.time_process(args.warmup, 0, 1, flags=pflags)
+        barrier()
+        ms_ip = max_over_ranks(e2.time_process(n_ip, 0, 1, flags=pflags)) / n_ip
+        ip = bytes_per_sample * samples_per_step_rank / (ms_ip * 1e-3) / 1e9
+        roofline["in_place_no_overlap"] = {"steps": n_ip, "ms_per_step": ms_ip, "achieved": ip, "frac": ip / peak,
+                                           "note": "one ring slot, in place, every launch a full dependency of the previous one"}
+        e2.close()
+
+    # ---- end to end through the C ABI with host buffers: ticks through a 4-slot ring
     e2e = None
     if not args.no_e2e:
         tick_frames = wl["e2e_frames"]
         n_ticks = wl["e2e_ticks"]
         e2e_steps = args.e2e_steps or min(args.steps, 5)
+        # host inputs: written by the same device generator into a scratch (identity, in-place) context
+        # and brought down once -- setup, not measured
+        gen = cm.Engine(channels, streams_per_gpu, tick_frames, ring_slots=2, device=local, flags=cm.NO_PINNED)
+        gen.tone_table(period)
+        shape = (n_ticks, streams_per_gpu, gen.stride // 2)
+        pin_in = cm.PinnedArray(shape, wc=args.e2e_wc)
+        stage = cm.PinnedArray(shape[1:]) if args.e2e_wc else None
+        for t in range(n_ticks):
+            synth.device_fill(gen, t % 2, None, first_stream, t * tick_frames, **fill)
+            if stage is None:
+                gen.fetch(t % 2, pin_in.array[t])
+            else:
+                gen.fetch(t % 2, stage.array)
+                gen.sync()
+                pin_in.array[t] = stage.array
+        gen.sync()
+        gen.close()
+        if stage is not None:
+            stage.free()
+
         eng = cm.Engine(channels, streams_per_gpu, tick_frames, ring_slots=4, device=local, flags=cm.NO_PINNED,
                         out_channels=mix_out)
         configure(eng)
-        shape = (n_ticks, streams_per_gpu, eng.stride // 2)
-        pin_in = cm.PinnedArray(shape)
         pin_out = cm.PinnedArray((n_ticks, streams_per_gpu, eng.out_stride // 2))
-        for t in range(n_ticks):
-            for lo in range(0, streams_per_gpu, 256):
-                hi = min(streams_per_gpu, lo + 256)
-                synth_block(first_stream + lo, hi - lo, channels, tick_frames, pin_in.array[t, lo:hi], t * tick_frames)
-        meter_rows = None
-        gathered = None
-        gather_s = [0.0]
+        total_streams = streams_per_gpu * world
+        gathered = [None]
+        gather = not args.e2e_no_gather
 
         def e2e_step():
             # Upload, tick and download of every tick are queued on the engine's three streams; the
-            # step's meter state is read as soon as its last tick has run (the snapshot waits for the
-            # compute stream only), so the downloads of this step's last ticks overlap the uploads of
-            # the next step's first ones. Everything is drained (eng.sync) before the clock stops.
-            nonlocal meter_rows, gathered
+            # step's meter results are taken as soon as its last tick has run (stream order on the
+            # compute stream), sent to rank 0 over NCCL and finalised there, while the downloads of this
+            # step's last ticks overlap the uploads of the next step's first ones. Everything is drained
+            # (eng.sync) before the clock stops. No barrier between steps: ranks other than the root
+            # never wait on the host for the gather.
             for t in range(n_ticks):
                 slot = t % 4
                 eng.submit(slot, pin_in.array[t])
                 eng.process(slot)
                 eng.fetch(slot, pin_out.array[t])
-            gather = dist is not None and not args.e2e_no_gather
-            meter_rows = eng.snapshot(reset=not gather)         # D2H of the integer meter state (+ reset)
-            if gather:
-                tg = time.perf_counter()
-                gathered = gather_meters(cm, eng, dist, rank, world)
-                gather_s[0] += time.perf_counter() - tg
-                eng.reset_meters()
+            if comm is not None and gather:
+                out = comm.gather_results(eng, rate, total_streams)
+            else:
+                res, st, rcs = eng.results(rate)
+                out = (res, st, rcs, [streams_per_gpu])
+            if out is not None:
+                gathered[0] = out
 
         for _ in range(2):
             e2e_step()
         eng.sync()
-        gather_s[0] = 0.0
         barrier()
+        gather_ms = 0.0
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             e2e_step()
+            if comm is not None:
+                gather_ms += comm.last_gather_ms()
         eng.sync()
+        wall_mine = time.perf_counter() - t0
         barrier()
-        wall = max_over_ranks(time.perf_counter() - t0)
-        assert int(meter_rows[0].frames) == tick_frames * n_ticks
-        spot = "skipped (run with --verify)"
-        if rank == 0 and args.verify:
-            spot = spot_check(cm, wl, streams_per_gpu, world, channels, tick_frames, n_ticks, rate, pin_out.array,
-                              meter_rows, gathered)
+        wall = max_over_ranks(wall_mine)
+        spot = "skipped (--no-verify)"
+        if rank == 0:
+            res, st, rcs, counts = gathered[0]
+            assert int(st[0].frames) == tick_frames * n_ticks and sum(counts) == (total_streams if comm is not None and gather else streams_per_gpu)
+            if not args.no_verify:
+                spot = spot_check(cm, synth, wl, period, streams_per_gpu, world if (comm is not None and gather) else 1,
+                                  channels, tick_frames, n_ticks, rate, pin_out.array, res, st)
         slot_bytes = streams_per_gpu * eng.stride
         out_slot_bytes = streams_per_gpu * eng.out_stride
         meter_bytes = streams_per_gpu * eng.meter_row_u64() * 8
-        e2e = {"parity_spot_check": spot,
-               "value": samples_per_step_rank * world * e2e_steps / wall / 1e6, "unit": "Msamples/s",
+        samples_e2e_rank = streams_per_gpu * tick_frames * n_ticks * channels
+        e2e = {"parity_spot_check": spot, "through": "cmgpu_submit / cmgpu_process / cmgpu_fetch / cmgpu_gather_results (C ABI)",
+               "value": samples_e2e_rank * world * e2e_steps / wall / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": n_ticks * slot_bytes, "d2h_bytes_per_step": n_ticks * out_slot_bytes + meter_bytes,
                "steps": e2e_steps, "ms_per_step": 1e3 * wall / e2e_steps,
-               "nccl_gather_ms_per_step": (1e3 * gather_s[0] / e2e_steps) if dist is not None else None,
+               "gbs_each_way_all_ranks": sum_over_ranks(n_ticks * slot_bytes * e2e_steps / wall_mine / 1e9),
+               "nccl_gather_ms_per_step": (gather_ms / e2e_steps) if comm is not None else None,
                "how": f"{n_ticks} ticks of {tick_frames} frames per step through a 4-slot ring, pinned host buffers, "
-                      "upload/compute/download on three CUDA streams, meter snapshot (+ NCCL gather to rank 0 when N>1) per step; "
-                      "steps are queued back to back and drained before the clock stops"}
+                      "upload/compute/download on three CUDA streams; per step the meter results of all ranks are gathered to "
+                      "rank 0 by cmgpu_gather_results (NCCL send/recv of the raw rows on the compute stream, decode + dB "
+                      "finalise on rank 0); steps are queued back to back and drained before the clock stops"}
         eng.close()
+        if not args.no_extras:
+            # what the host link gives when every rank drives it at once, both directions (the e2e ceiling)
+            probe_bytes = min(256 << 20, max(16 << 20, slot_bytes))
+            barrier()
+            link = cm.link_probe(local, probe_bytes, reps=max(4, (2 << 30) // probe_bytes), both_only=world > 1)
+            link["both_each_way_gbs_all_ranks"] = sum_over_ranks(link["both_each_way_gbs"])
+            link["chunk_bytes"] = probe_bytes
+            e2e["link"] = link
+            e2e["link_ceiling_gbs"] = link["both_each_way_gbs_all_ranks"]
+            e2e["frac_of_link"] = e2e["gbs_each_way_all_ranks"] / max(link["both_each_way_gbs_all_ranks"], 1e-9)
         pin_in.free(); pin_out.free()
+
+        if not args.no_extras and rank == 0 and not mix_out:
+            try:
+                e2e["object_api"] = object_api_leg(cm, synth, local)
+            except Exception as exc:      # the leg is a report, not the metric
+                e2e["object_api"] = {"error": repr(exc)}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline and mix_out:
@@ -497,8 +586,7 @@ def main():
         from oracle import pyoracle
         port = pyoracle.port()
         n = min(frames, 96000)
-        pcm = np.empty((1, n * channels), dtype=np.int16)
-        synth_block(0, 1, channels, n, pcm)
+        pcm = np.ascontiguousarray(synth.synth_rows(period, 0, 1, channels, n, 0, wl["sstep"], wl["cstep"], 0))
         mscale, mw = mix_table(0, 1, channels, mix_out)
         t0 = time.perf_counter(); reps = 0
         while time.perf_counter() - t0 < 5.0:
@@ -507,7 +595,7 @@ def main():
         cpu = {"value": reps * n * channels / (time.perf_counter() - t0) / 1e6, "unit": "Msamples/s", "cores": 1,
                "kind": "port", "sample": f"1 stream x {n} frames x {reps} passes, our own restatement (no reference exists)"}
     elif rank == 0 and not args.no_cpu_baseline:
-        cpu = cpu_reference_run(channels, rate, frames * ticks, budget_s=12.0)
+        cpu = cpu_reference_run(wl, budget_s=12.0)
         cpu.pop("seconds", None)
 
     if rank == 0:
@@ -516,34 +604,42 @@ def main():
                 "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
                 "dtype": "int32 (S16 in/out, int64 power)", "data": "synthetic", "config": config,
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu,
+                "nccl": ({"version": int(cm.lib().cmgpu_comm_nccl_version()), "ranks": world,
+                          "from": "libcoolmic_b200.so (cmgpu_comm_*), id exchanged through a file; no torch.distributed"}
+                         if comm is not None else None)}
         emit(line)
-    if dist is not None:
-        dist.destroy_process_group()
+    if comm is not None:
+        comm.barrier()
+        comm.close()
     return 0
 
 
-def spot_check(cm, wl, streams_per_gpu, world, channels, tick_frames, n_ticks, rate, out0, meter_rows, gathered):
+def spot_check(cm, synth, wl, period, streams_per_gpu, world, channels, tick_frames, n_ticks, rate, out0, results, states):
     """Rank 0 re-derives, with the oracle port, what a few streams of EVERY rank must have produced
-    in the last end-to-end step: transformed PCM (rank 0's own streams) and the integer meter state
-    (all ranks, from the rows that came over NCCL). The oracle is the checker here, nothing it
-    computes is measured or shipped."""
+    in the last end-to-end step: transformed PCM (rank 0's own streams), the integer meter state and the
+    finalised dB values (all ranks, from the rows that came over NCCL). The oracle is the checker here,
+    nothing it computes is measured or shipped."""
     from oracle import pyoracle
     port = pyoracle.port()
     frames = tick_frames * n_ticks
     checked = 0
+    picks = sorted({0, 5, streams_per_gpu // 2, streams_per_gpu - 1})
+
+    def rows(g):
+        return np.ascontiguousarray(synth.synth_rows(period, g, 1, channels, frames, 0, wl["sstep"], wl["cstep"],
+                                                     NOISE_EVERY, NOISE_PHASE))
+
     if wl.get("mix_out"):
         # extension: our own restatement is the only checker there is (parity unpinned)
         cout = wl["mix_out"]
-        for s in sorted({0, 5, streams_per_gpu // 2, streams_per_gpu - 1}):
-            pcm = np.empty((1, frames * channels), dtype=np.int16)
-            for t in range(n_ticks):
-                synth_block(s, 1, channels, tick_frames, pcm[:, t * tick_frames * channels:], t * tick_frames)
+        for s in picks:
+            pcm = rows(s)
             mscale, mw = mix_table(s, 1, channels, cout)
             m_out = pyoracle.Meter()
             want = port.mix(pcm[0], frames, channels, cout, int(mscale[0]), mw[0], None, m_out)
             got = np.concatenate([out0[t, s, : tick_frames * cout] for t in range(n_ticks)])
-            st = meter_rows[s]
+            st = states[s]
             ok = np.array_equal(got, want) and int(st.frames) == frames
             for c in range(cout):
                 ok = ok and int(st.power[c]) == int(m_out.power[c]) and int(st.channel_peak[c]) == int(m_out.channel_peak[c])
@@ -552,39 +648,61 @@ def spot_check(cm, wl, streams_per_gpu, world, channels, tick_frames, n_ticks, r
             checked += 1
         return f"ok: {checked} streams bit-exact vs our own CPU restatement (extension, parity unpinned)"
     for r in range(world):
-        if r == 0:
-            states = meter_rows
-        else:
-            rows = gathered[r].cpu().numpy()
-            states = cm.sharding.decode_rows(cm.lib(), rows, channels)
-        for s in sorted({0, 5, streams_per_gpu // 2, streams_per_gpu - 1}):
+        for s in picks:
             g = r * streams_per_gpu + s
-            pcm = np.empty((1, frames * channels), dtype=np.int16)
-            for t in range(n_ticks):
-                synth_block(g, 1, channels, tick_frames, pcm[:, t * tick_frames * channels:], t * tick_frames)
+            pcm = rows(g)
             scale, gain = gain_table(g, 1, channels)
             meters, _ = port.batch(pcm, np.array([frames], np.uint32), channels, scale, gain)
-            st = states[s]
+            st = states[g]
             ok = int(st.frames) == frames and int(st.global_peak) == int(meters[0].global_peak)
             for c in range(channels):
                 ok = ok and int(st.power[c]) == int(meters[0].power[c])
                 ok = ok and int(st.channel_peak[c]) == int(meters[0].channel_peak[c])
+            want = port.finalise(meters[0], rate, channels)
+            got = results[g].as_dict()
+            ok = ok and np.float64(got["global_power"]).tobytes() == np.float64(want["global_power"]).tobytes()
+            for c in range(channels):
+                ok = ok and np.float64(got["channel_power"][c]).tobytes() == np.float64(want["channel_power"][c]).tobytes()
             if r == 0:
-                got = np.concatenate([out0[t, s, : tick_frames * channels] for t in range(n_ticks)])
-                ok = ok and np.array_equal(got, pcm[0])
+                got_pcm = np.concatenate([out0[t, s, : tick_frames * channels] for t in range(n_ticks)])
+                ok = ok and np.array_equal(got_pcm, pcm[0])
             if not ok:
                 return f"MISMATCH rank {r} stream {s}"
             checked += 1
-    return f"ok: {checked} streams over {world} rank(s) bit-exact vs oracle (PCM on rank 0, meter state on all)"
+    return (f"ok: {checked} streams over {world} rank(s) bit-exact vs oracle (PCM on rank 0; integer meter state and dB "
+            f"doubles on all, as gathered by cmgpu_gather_results)")
 
 
-def gather_meters(cm, eng, dist, rank, world):
-    """Per-stream meter rows of every rank to rank 0 over NCCL (the only collective on the path)."""
-    import torch
-    mine = cm.sharding.wrap_device_rows(eng.device_meters(), eng.max_streams * eng.meter_row_u64())
-    out = cm.sharding.gather_rows(mine, dist, rank, world)
-    torch.cuda.current_stream().synchronize()       # the gather only: the engine's copy streams keep running
-    return out
+def object_api_leg(cm, synth, device):
+    """The path a libcoolmic-dsp maintainer would call (src/simple.c:212-229,445-505 with
+    coolmic_b200_batch_tick in place of the per-stream pull loop): 1,024 member transforms fed by memory
+    iohandles, fused meters, every transform's output read back through its iohandle -- the reference-
+    named object API on a pipelined ring, host buffers on both sides."""
+    lib = cm.lib()
+    if not hasattr(lib, "coolmic_b200_bench_objects"):
+        return {"error": "library built without the object-API bench driver"}
+    fn = lib.coolmic_b200_bench_objects
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_void_p,
+                   C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    streams, channels, block, n_ticks, slots, threads = 1024, 2, 12000, 40, 4, min(16, os.cpu_count() or 1)
+    period = synth.load_period(48000)
+    pcm = np.ascontiguousarray(synth.synth_rows(period, 0, streams, channels, block * 4, 0, 7, 3, NOISE_EVERY, NOISE_PHASE))
+    secs = C.c_double(0)
+    check = C.c_uint64(0)
+    best = None
+    for _ in range(3):
+        rc = fn(device, channels, streams, block, n_ticks, slots, threads, pcm.shape[1] * 2, pcm.ctypes.data,
+                C.byref(secs), C.byref(check))
+        if rc != 0:
+            return {"error": f"coolmic_b200_bench_objects: {rc}"}
+        best = secs.value if best is None else min(best, secs.value)
+    samples = streams * channels * block * n_ticks
+    return {"through": "coolmic_b200_batch_tick + coolmic_iohandle_read on 1,024 member transforms (memory iohandles in, "
+                       "per-transform handles out), fused vumeters, coolmic_vumeter_result per stream at the end",
+            "value": samples / best / 1e6, "unit": "Msamples/s", "ms_per_step": best * 1e3,
+            "shape": f"{streams} x stereo x {block} frames x {n_ticks} ticks, {slots}-slot ring, {threads} host threads",
+            "frames_metered_checksum": int(check.value)}
 
 
 if __name__ == "__main__":

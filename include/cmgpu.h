@@ -89,6 +89,9 @@ const char *cmgpu_last_error(void);                   /* thread-local text of th
 /* Page-locked host memory for callers that stream whole slots from their own buffers
  * (cmgpu_submit / cmgpu_fetch are asynchronous only for page-locked memory). */
 void *cmgpu_host_alloc(size_t bytes);
+/* The same, write-combined: for buffers the host only ever WRITES (capture -> upload); reads by the
+ * host are very slow. */
+void *cmgpu_host_alloc_wc(size_t bytes);
 void  cmgpu_host_free(void *p);
 
 /* ---- context: one per (GPU, channel count) -------------------------------------- */
@@ -180,6 +183,85 @@ unsigned cmgpu_meter_row_u64(const cmgpu_ctx_t *ctx);
 int      cmgpu_meter_decode(const uint64_t *rows, unsigned count, unsigned channels,
                             cmgpu_meter_state_t *out);
 
+/* coolmic_vumeter_result for MANY streams with one device round trip (a caller that reports every
+ * stream each interval, like simple.c:486-491 does for its one stream, would otherwise pay one
+ * blocking copy per stream): the rows of [first, first+count) are taken -- copied and, with `reset`,
+ * cleared where frames != 0, which is what vumeter.c:198-199,214-215 does per object -- in ONE
+ * stream-ordered device step, copied to the host once, and finalised there with the reference's
+ * expression and libm (bit-identical doubles). rcs[i] (optional) = CMGPU_OK or CMGPU_ERR_INVAL (no
+ * frames metered: results[i] zeroed, row untouched). `states` (optional) receives the integer state.
+ * CMGPU_RESULTS_DEVICE_DB: compute the dB values on the device instead (fp64 sqrt/log10 in the take
+ * kernel; agrees with the host finaliser to <= 1e-12 relative, NOT guaranteed bit-identical). */
+#define CMGPU_RESULTS_DEVICE_DB 0x1u
+int cmgpu_meter_results(cmgpu_ctx_t *ctx, unsigned first, unsigned count, uint32_t rate, int reset, unsigned flags,
+                        cmgpu_result_t *results, cmgpu_meter_state_t *states, int *rcs);
+
+/* ---- multi-GPU: the one collective of the path ---------------------------------------
+ * Streams shard by contiguous range across GPUs, one process (or thread) and one context per GPU, no
+ * data-path exchange. Once per reporting interval the per-stream meter rows travel to one rank over
+ * NCCL (NVLink / NVSwitch): grouped ncclSend / ncclRecv of the raw integer rows on the compute stream,
+ * decoded and finalised on the root with the same host code as cmgpu_meter_results. What arrives at
+ * the root is, per stream, exactly what coolmic_vumeter_result() fills (vumeter.h:48-83).
+ *
+ * A communicator is created from a 128-byte NCCL unique id that rank 0 makes and hands to the other
+ * ranks by any means (cmgpu_comm_create), or through a file on a shared file system
+ * (cmgpu_comm_create_file: rank 0 writes `path` atomically and removes it once every rank has joined;
+ * the others wait up to timeout_ms for it) -- no PyTorch, no MPI. An existing ncclComm_t can be
+ * adopted instead (cmgpu_comm_adopt; not destroyed by cmgpu_comm_destroy). */
+typedef struct cmgpu_comm cmgpu_comm_t;
+#define CMGPU_COMM_ID_BYTES 128
+int           cmgpu_comm_unique_id(unsigned char id[CMGPU_COMM_ID_BYTES]);
+cmgpu_comm_t *cmgpu_comm_create(int device, int rank, int nranks, const unsigned char id[CMGPU_COMM_ID_BYTES]);
+cmgpu_comm_t *cmgpu_comm_create_file(int device, int rank, int nranks, const char *path, int timeout_ms);
+cmgpu_comm_t *cmgpu_comm_adopt(void *nccl_comm, int device);
+void          cmgpu_comm_destroy(cmgpu_comm_t *comm);
+int           cmgpu_comm_rank(const cmgpu_comm_t *comm);
+int           cmgpu_comm_size(const cmgpu_comm_t *comm);
+int           cmgpu_comm_nccl_version(void);                       /* e.g. 22703 */
+/* Plumbing for multi-rank measurements: a barrier, and an in-place max / sum over ranks. */
+int           cmgpu_comm_barrier(cmgpu_comm_t *comm);
+int           cmgpu_comm_max(cmgpu_comm_t *comm, double *values, unsigned n);
+int           cmgpu_comm_sum(cmgpu_comm_t *comm, double *values, unsigned n);
+/* Every rank calls it with its own context (collective). Each rank contributes the rows of its
+ * active streams; `reset` as in cmgpu_meter_results. On `root` the outputs (each optional) receive,
+ * rank after rank in stream order: results[total], states[total], rcs[total], and counts[nranks] =
+ * streams per rank; elsewhere they are ignored. The root returns once it has everything; the other
+ * ranks return as soon as their part is queued on their compute stream (they never wait on the host,
+ * so a rank behind a slower host link does not hold the others up). */
+int cmgpu_gather_results(cmgpu_ctx_t *ctx, cmgpu_comm_t *comm, int root, uint32_t rate, int reset,
+                         cmgpu_result_t *results, cmgpu_meter_state_t *states, int *rcs, unsigned *counts);
+/* Device milliseconds the last cmgpu_gather_results spent on the ROOT between its first and last
+ * stream operation (take + NCCL + copy to the host); 0 on the other ranks. */
+float cmgpu_comm_last_gather_ms(const cmgpu_comm_t *comm);
+
+/* ---- adjacent consumers / producers on the device ------------------------------
+ * Meter colours: what the app derives from each result with coolmic_util_power2hue / peak2hue /
+ * ahsv2argb (util.h:40-47, util.c:59-139), for every stream of [first, first+count) in one kernel over
+ * the CURRENT meter rows (no reset): dB on the device, "default" profile hues, packed 0xAARRGGBB.
+ * Host doubles are the reference (csrc/host/shim_util.c is bit-exact with util.c); the device's sin()
+ * may differ in the last place, so hues agree to a few ulp and a colour byte can differ by one only
+ * when x*255 lands within that of an integer. Streams with no frames metered get all-zero colours. */
+typedef struct cmgpu_colors {
+    uint32_t global_power_argb, global_peak_argb;
+    uint32_t channel_power_argb[CMGPU_MAX_CHANNELS];
+    uint32_t channel_peak_argb[CMGPU_MAX_CHANNELS];
+    double   global_power_hue;                      /* for checks: the hue the global power mapped to */
+    double   channel_power_hue[CMGPU_MAX_CHANNELS];
+} cmgpu_colors_t;
+int cmgpu_meter_colors(cmgpu_ctx_t *ctx, unsigned first, unsigned count, double alpha, double saturation,
+                       double value, cmgpu_colors_t *out);
+/* Tone source: fills the valid frames of a slot ON THE DEVICE the way a snddev_sine-fed capture would
+ * (snddev_sine.c:118-150: a cyclic copy of a one-period table), without embedding the driver's data:
+ * the table is given at run time (e.g. one period read from the real driver).
+ *   sample(stream s, frame f, channel c) = period[(first_frame + f + stream_step*s + channel_step*c) mod n]
+ * cmgpu_noise_fill: full-range deterministic noise, sample = (int16) splitmix64(seed ^ s<<40 ^ f<<4 ^ c)
+ * (second data set), for streams s with s % every == phase (every >= 1). */
+int cmgpu_tone_set_table(cmgpu_ctx_t *ctx, const int16_t *period, unsigned n);
+int cmgpu_tone_fill(cmgpu_ctx_t *ctx, unsigned slot, uint64_t first_frame, unsigned first_stream,
+                    unsigned stream_step, unsigned channel_step);
+int cmgpu_noise_fill(cmgpu_ctx_t *ctx, unsigned slot, uint64_t first_frame, unsigned first_stream,
+                     uint64_t seed, unsigned every, unsigned phase);
+
 /* ---- EXTENSION: N -> M integer downmix (no counterpart in libcoolmic-dsp; PARITY UNPINNED) ------
  * BASELINE.json's config 4 names a downmix the reference does not implement.
  * Specified here in the reference's arithmetic style (transform.c:110-123):
@@ -207,6 +289,12 @@ int cmgpu_time_process(cmgpu_ctx_t *ctx, unsigned first_slot, unsigned n_slots, 
 /* The same for `cycles` replays of the cached CUDA graph of n_slots ticks (cmgpu_process_cycle). */
 int cmgpu_time_cycles(cmgpu_ctx_t *ctx, unsigned first_slot, unsigned n_slots, unsigned cycles,
                       unsigned flags, float *ms);
+/* What the host link of `device` gives for page-locked buffers of `bytes` bytes, `reps` times each:
+ * upload alone, download alone, and both at once (GB/s per direction). The end-to-end path moves
+ * every sample across the link twice, so `both` is its ceiling; with several ranks calling this at the
+ * same moment (after a barrier) each sees its share of the links they have in common. */
+int cmgpu_link_probe(int device, size_t bytes, unsigned reps, int write_combined, float *h2d_gbs, float *d2h_gbs,
+                     float *both_gbs);
 /* Number of kernel launches this context has issued so far. */
 uint64_t cmgpu_launch_count(const cmgpu_ctx_t *ctx);
 /* Name of the kernel variant cmgpu_process would pick for the current shape (for logs). */

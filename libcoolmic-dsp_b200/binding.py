@@ -55,6 +55,20 @@ class Result(C.Structure):
         }
 
 
+class Colors(C.Structure):
+    _fields_ = [
+        ("global_power_argb", C.c_uint32),
+        ("global_peak_argb", C.c_uint32),
+        ("channel_power_argb", C.c_uint32 * MAX_CH),
+        ("channel_peak_argb", C.c_uint32 * MAX_CH),
+        ("global_power_hue", C.c_double),
+        ("channel_power_hue", C.c_double * MAX_CH),
+    ]
+
+
+COMM_ID_BYTES = 128
+RESULTS_DEVICE_DB = 0x1
+
 # every symbol include/cmgpu.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _U16P = C.POINTER(C.c_uint16)
@@ -63,6 +77,7 @@ SYMBOLS = {
     "cmgpu_device_count": (C.c_int, []),
     "cmgpu_last_error": (C.c_char_p, []),
     "cmgpu_host_alloc": (_P, [C.c_size_t]),
+    "cmgpu_host_alloc_wc": (_P, [C.c_size_t]),
     "cmgpu_host_free": (None, [_P]),
     "cmgpu_ctx_create": (_P, [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint]),
     "cmgpu_ctx_destroy": (None, [_P]),
@@ -104,8 +119,30 @@ SYMBOLS = {
     "cmgpu_host_out_slot": (_P, [_P, C.c_uint]),
     "cmgpu_time_process": (C.c_int, [_P, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_float)]),
     "cmgpu_time_cycles": (C.c_int, [_P, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_float)]),
+    "cmgpu_link_probe": (C.c_int, [C.c_int, C.c_size_t, C.c_uint, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                   C.POINTER(C.c_float)]),
     "cmgpu_launch_count": (C.c_uint64, [_P]),
     "cmgpu_kernel_name": (C.c_char_p, [_P]),
+    "cmgpu_meter_results": (C.c_int, [_P, C.c_uint, C.c_uint, C.c_uint32, C.c_int, C.c_uint, C.POINTER(Result),
+                                      C.POINTER(MeterState), C.POINTER(C.c_int)]),
+    "cmgpu_comm_unique_id": (C.c_int, [C.POINTER(C.c_ubyte)]),
+    "cmgpu_comm_create": (_P, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]),
+    "cmgpu_comm_create_file": (_P, [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]),
+    "cmgpu_comm_adopt": (_P, [_P, C.c_int]),
+    "cmgpu_comm_destroy": (None, [_P]),
+    "cmgpu_comm_rank": (C.c_int, [_P]),
+    "cmgpu_comm_size": (C.c_int, [_P]),
+    "cmgpu_comm_nccl_version": (C.c_int, []),
+    "cmgpu_comm_barrier": (C.c_int, [_P]),
+    "cmgpu_comm_max": (C.c_int, [_P, C.POINTER(C.c_double), C.c_uint]),
+    "cmgpu_comm_sum": (C.c_int, [_P, C.POINTER(C.c_double), C.c_uint]),
+    "cmgpu_gather_results": (C.c_int, [_P, _P, C.c_int, C.c_uint32, C.c_int, C.POINTER(Result), C.POINTER(MeterState),
+                                       C.POINTER(C.c_int), C.POINTER(C.c_uint)]),
+    "cmgpu_comm_last_gather_ms": (C.c_float, [_P]),
+    "cmgpu_meter_colors": (C.c_int, [_P, C.c_uint, C.c_uint, C.c_double, C.c_double, C.c_double, C.POINTER(Colors)]),
+    "cmgpu_tone_set_table": (C.c_int, [_P, C.POINTER(C.c_int16), C.c_uint]),
+    "cmgpu_tone_fill": (C.c_int, [_P, C.c_uint, C.c_uint64, C.c_uint, C.c_uint, C.c_uint]),
+    "cmgpu_noise_fill": (C.c_int, [_P, C.c_uint, C.c_uint64, C.c_uint, C.c_uint64, C.c_uint, C.c_uint]),
     "cmgpu_recipe_eval": (C.c_int, [C.c_uint16, C.c_uint16, C.c_int16]),
     "cmgpu_recipe_table": (C.c_int, [C.c_uint16, C.c_uint16, C.POINTER(C.c_int16)]),
 }
@@ -298,6 +335,33 @@ class Engine:
             return {"rc": rc}
         return res.as_dict()
 
+    def results(self, rate: int, first: int = 0, count: int | None = None, reset: bool = True, flags: int = 0):
+        """coolmic_vumeter_result for many streams in one device round trip -> (Result[], MeterState[], rc[])."""
+        count = self.active - first if count is None else count
+        res = (Result * count)()
+        st = (MeterState * count)()
+        rcs = (C.c_int * count)()
+        _check(self.L.cmgpu_meter_results(self.ctx, first, count, rate, int(reset), flags, res, st, rcs),
+               "cmgpu_meter_results")
+        return res, st, rcs
+
+    def colors(self, first: int = 0, count: int | None = None, alpha=1.0, saturation=1.0, value=1.0):
+        count = self.active - first if count is None else count
+        out = (Colors * count)()
+        _check(self.L.cmgpu_meter_colors(self.ctx, first, count, alpha, saturation, value, out), "cmgpu_meter_colors")
+        return out
+
+    def tone_table(self, period):
+        t = np.ascontiguousarray(period, dtype=np.int16)
+        _check(self.L.cmgpu_tone_set_table(self.ctx, t.ctypes.data_as(C.POINTER(C.c_int16)), t.size), "cmgpu_tone_set_table")
+
+    def tone_fill(self, slot: int, first_frame: int = 0, first_stream: int = 0, stream_step: int = 7, channel_step: int = 3):
+        _check(self.L.cmgpu_tone_fill(self.ctx, slot, first_frame, first_stream, stream_step, channel_step), "cmgpu_tone_fill")
+
+    def noise_fill(self, slot: int, first_frame: int = 0, first_stream: int = 0, seed: int = 0xC0011DC5,
+                   every: int = 1, phase: int = 0):
+        _check(self.L.cmgpu_noise_fill(self.ctx, slot, first_frame, first_stream, seed, every, phase), "cmgpu_noise_fill")
+
     def finalise(self, state: MeterState, rate: int, channels: int = 0) -> dict:
         res = Result()
         rc = self.L.cmgpu_finalise(C.byref(state), rate, channels or self.out_channels, C.byref(res))
@@ -331,12 +395,67 @@ class Engine:
         return self.L.cmgpu_kernel_name(self.ctx).decode()
 
 
+class Comm:
+    """NCCL communicator owned by the C library (cmgpu_comm_*): no torch, no MPI."""
+
+    def __init__(self, device: int, rank: int, nranks: int, path: str | None = None, uid: bytes | None = None,
+                 timeout_ms: int = 120000):
+        self.L = lib()
+        if uid is not None:
+            buf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(uid)
+            self.comm = self.L.cmgpu_comm_create(device, rank, nranks, buf)
+        else:
+            self.comm = self.L.cmgpu_comm_create_file(device, rank, nranks, str(path).encode(), timeout_ms)
+        if not self.comm:
+            raise CmgpuError(-1, "cmgpu_comm_create")
+        self.rank, self.size = rank, nranks
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_ubyte * COMM_ID_BYTES)()
+        _check(lib().cmgpu_comm_unique_id(buf), "cmgpu_comm_unique_id")
+        return bytes(buf)
+
+    def close(self):
+        if self.comm:
+            self.L.cmgpu_comm_destroy(self.comm)
+            self.comm = None
+
+    def barrier(self):
+        _check(self.L.cmgpu_comm_barrier(self.comm), "cmgpu_comm_barrier")
+
+    def max(self, *values: float):
+        arr = (C.c_double * len(values))(*values)
+        _check(self.L.cmgpu_comm_max(self.comm, arr, len(values)), "cmgpu_comm_max")
+        return list(arr) if len(values) > 1 else arr[0]
+
+    def sum(self, *values: float):
+        arr = (C.c_double * len(values))(*values)
+        _check(self.L.cmgpu_comm_sum(self.comm, arr, len(values)), "cmgpu_comm_sum")
+        return list(arr) if len(values) > 1 else arr[0]
+
+    def gather_results(self, eng: "Engine", rate: int, total_streams: int, root: int = 0, reset: bool = True,
+                       want_results: bool = True, want_states: bool = True):
+        """Collective. On the root: (Result[total], MeterState[total], rc[total], counts[nranks]); else None."""
+        is_root = self.rank == root
+        res = (Result * total_streams)() if is_root and want_results else None
+        st = (MeterState * total_streams)() if is_root and want_states else None
+        rcs = (C.c_int * total_streams)() if is_root else None
+        counts = (C.c_uint * self.size)() if is_root else None
+        _check(self.L.cmgpu_gather_results(eng.ctx, self.comm, root, rate, int(reset), res, st, rcs, counts),
+               "cmgpu_gather_results")
+        return (res, st, rcs, list(counts)) if is_root else None
+
+    def last_gather_ms(self) -> float:
+        return float(self.L.cmgpu_comm_last_gather_ms(self.comm))
+
+
 class PinnedArray:
     """int16 numpy view over page-locked host memory from cmgpu_host_alloc()."""
 
-    def __init__(self, shape):
+    def __init__(self, shape, wc: bool = False):
         n = int(np.prod(shape))
-        self.ptr = lib().cmgpu_host_alloc(n * 2)
+        self.ptr = (lib().cmgpu_host_alloc_wc if wc else lib().cmgpu_host_alloc)(n * 2)
         if not self.ptr:
             raise CmgpuError(-11, "cmgpu_host_alloc")
         buf = (C.c_int16 * n).from_address(self.ptr)
@@ -347,6 +466,17 @@ class PinnedArray:
             self.array = None
             lib().cmgpu_host_free(self.ptr)
             self.ptr = None
+
+
+def link_probe(device: int = 0, nbytes: int = 256 << 20, reps: int = 8, both_only: bool = False, wc: bool = False) -> dict:
+    """Host-link rates for pinned buffers (GB/s per direction): upload, download, both at once."""
+    up, down, both = C.c_float(0), C.c_float(0), C.c_float(0)
+    _check(lib().cmgpu_link_probe(device, nbytes, reps, int(wc), None if both_only else C.byref(up),
+                                  None if both_only else C.byref(down), C.byref(both)), "cmgpu_link_probe")
+    out = {"both_each_way_gbs": float(both.value)}
+    if not both_only:
+        out.update(h2d_gbs=float(up.value), d2h_gbs=float(down.value))
+    return out
 
 
 def state_dict(st: MeterState, channels: int) -> dict:

@@ -8,7 +8,7 @@
 #include "cmgpu_mix.cuh"
 #include "cmgpu_tma.cuh"
 
-#include "../../include/cmgpu.h"
+#include "cmgpu_ctx.h"
 
 #include <cmath>
 #include <cstdarg>
@@ -20,14 +20,13 @@
 #include <algorithm>
 #include <vector>
 
-using cmgpu::GainRow;
 using cmgpu::MixArgs;
-using cmgpu::MixRow;
 using cmgpu::TickArgs;
+using cmgpu::fail;
 
-namespace {
+namespace cmgpu {
 
-thread_local char g_err[512] = "";
+static thread_local char g_err[512] = "";
 
 int fail(int code, const char *fmt, ...)
 {
@@ -38,12 +37,9 @@ int fail(int code, const char *fmt, ...)
     return code;
 }
 
-#define CU(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e__ = (call);                                                                  \
-        if (e__ != cudaSuccess)                                                                    \
-            return fail(CMGPU_ERR_GENERIC, "%s failed: %s", #call, cudaGetErrorString(e__));       \
-    } while (0)
+}  // namespace cmgpu
+
+namespace {
 
 // ---- the gain recipe (see GainRow in cmgpu_kernels.cuh, proof in DESIGN.md) ---------------
 struct RecipeHost {
@@ -93,83 +89,6 @@ unsigned ceil_log2(uint32_t v)
 }
 
 }  // namespace
-
-struct cmgpu_ctx {
-    int device = 0;
-    unsigned channels = 0, max_streams = 0, active = 0, slots = 0, block_frames = 0, flags = 0;
-    size_t stride = 0, slot_bytes = 0;
-    unsigned row_u64 = 0, pbits = 0;
-    uint64_t launches = 0;
-    int num_sms = 0;
-
-    uint8_t *d_in = nullptr, *d_out = nullptr;     // rings
-    uint8_t *h_ring = nullptr;                     // pinned staging ring
-    float *d_planar = nullptr;                     // optional [slot][stream][channel][plane_stride] float
-    size_t plane_stride = 0, planar_slot_floats = 0;
-
-    // EXTENSION (downmix contexts only): N -> M mix, separate output geometry, input-side meters
-    unsigned out_channels = 0;                     // 0: ordinary gain context
-    size_t stride_out = 0, slot_bytes_out = 0;
-    uint8_t *h_ring_out = nullptr;
-    MixRow *d_mix = nullptr;
-    std::vector<MixRow> h_mix;
-    bool mix_dirty = false;
-    unsigned long long *d_meters_in = nullptr;
-    unsigned row_in_u64 = 0;
-    GainRow *d_gains = nullptr;
-    std::vector<GainRow> h_gains;
-    std::vector<uint16_t> h_scale, h_gain;         // adapted settings, [stream], [stream][channels]
-    unsigned dirty_lo = 0, dirty_hi = 0;           // gain rows to upload: [lo, hi)
-    unsigned long long *d_meters = nullptr;
-    unsigned long long *d_tick = nullptr;          // [0] tick sequence number, [1] CTA completion ticket
-    uint32_t *d_frames = nullptr;                  // [slots][max_streams]
-    std::vector<char> has_frames;
-    std::vector<uint64_t> scratch;                 // snapshot staging
-
-    cudaStream_t s_up = nullptr, s_cmp = nullptr, s_down = nullptr;
-    std::vector<cudaEvent_t> ev_up, ev_cmp, ev_down;
-    // Cross-stream ordering is queued only where it orders something: a tick waits for a slot's upload /
-    // download only if one was issued since the slot's last tick, and a slot's "ticks done" event is
-    // recorded when an upload or download first asks for it. Back-to-back ticks on resident data are
-    // then back-to-back kernel launches, which is what lets them overlap (launch_begin).
-    std::vector<uint8_t> up_pending, down_pending, cmp_unrecorded;
-    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
-    std::mutex mu;
-
-    // cached CUDA graph of a cycle of ticks (launch-bound small-buffer regime): the ticks are
-    // independent nodes spread over a few side streams, so their latencies overlap
-    std::vector<cudaStream_t> s_fork;
-    cudaEvent_t ev_fork = nullptr;
-    std::vector<cudaEvent_t> ev_join;
-    cudaGraphExec_t graph = nullptr;
-    unsigned graph_first = 0, graph_n = 0, graph_flags = 0;
-    uint64_t graph_launches = 0;                   // kernel nodes in the cached graph
-    uint64_t config_gen = 0, graph_gen = ~0ull;    // bumped whenever launch arguments may change
-    // tick numbering: ticks issued by plain / span launches since the device counter was last bumped
-    uint32_t pending_ticks = 0;
-    // Overlap rule of programmatic dependent launch. A chain of overlapping launches is open on s_cmp
-    // while every launch since the last full dependency was marked dependent-launchable; in_chain[slot]
-    // says which slots those launches touch. A small grid does not fill the GPU, so ANY launch of the
-    // chain may still be running when the next one starts -- not just the previous one.
-    bool chain_open = false;
-    std::vector<uint8_t> in_chain;
-    unsigned last_first = ~0u;                     // slot of the last tick launch; ~0u: something else was queued last
-
-    // how many active streams need which gain mode; the tick runs in the cheapest common one
-    unsigned n_mode[3] = {0, 0, 0};                // GM_IDENTITY / GM_MASKED / GM_ADDALL
-    bool classes_dirty = true;
-
-    // launch plan (depends on shape only)
-    int plan_g = 32;              // lanes per item (fast kernels); 0 = frame-per-lane generic kernel; -1 = any_tick
-    int plan_lanes = 32;          // any_tick: lanes of a warp that take part
-    // long stream-blocks, opt-in: TMA-staged kernel (cmgpu_tma.cuh) with its own item geometry
-    bool tma = false;
-    uint32_t tma_items = 1, tma_per_item = 0;
-    int tma_grid_cap[3][2] = {{0, 0}, {0, 0}, {0, 0}};
-    uint32_t plan_items = 1, plan_per_item = 0;
-    int grid_cap[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // resident CTAs per (gain mode, meter) kernel
-    char kname[64] = "";
-};
 
 namespace {
 
@@ -493,6 +412,8 @@ int rebuild_classes_locked(cmgpu_ctx *c)
     return CMGPU_OK;
 }
 
+int flush_ticks_locked(cmgpu_ctx *c);
+
 // One tick on stream `st`. In a cycle (cmgpu_process_cycle) the ticks run concurrently: each gets
 // its place in the sequence as `tick_offset` and leaves advancing the counter to the cycle's end.
 // n_ticks > 1: a span -- ONE launch over the consecutive slots [slot, slot + n_ticks) (span_ok() says when).
@@ -504,11 +425,16 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
 {
     if (!st)
         st = c->s_cmp;
-    if (!captured)
-        tick_offset = c->pending_ticks;
     int rc = upload_gains_locked(c);
     if (rc)
         return rc;
+    if (!captured) {
+        // the host numbers ticks in 32 bits on top of the device's 64-bit counter: fold them in long
+        // before the offset can wrap (a full dependency once every 2^31 ticks)
+        if (c->pending_ticks >= 0x80000000u && (rc = flush_ticks_locked(c)))
+            return rc;
+        tick_offset = c->pending_ticks;
+    }
     const bool meter = (flags & CMGPU_METER) != 0;
     const bool transform = (flags & CMGPU_TRANSFORM) != 0;
     if (!c->active)
@@ -553,7 +479,7 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
         if (grid > (uint64_t)occ * c->num_sms)
             grid = (uint64_t)occ * c->num_sms;
         // a downmix context always has its own output ring: consecutive ticks never conflict
-        const bool mpdl = !captured && st == c->s_cmp && c->chain_open && c->last_first != ~0u && !getenv("CMGPU_NO_PDL");
+        const bool mpdl = !captured && st == c->s_cmp && c->chain_open && c->last_first != ~0u && !c->env_no_pdl;
         if (!captured && st == c->s_cmp)
             c->chain_open = true;
         if (vec8)
@@ -608,16 +534,19 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
     a.slot_bytes = c->slot_bytes;
     // A launch may start while earlier tick launches of the compute stream are still running when it
     // reads nothing any of them writes: slots none of the still-open chain touches, or a separate
-    // output ring (the input ring is then read-only for ticks). Anything else queued on the stream
-    // in between (uploads of gains or frames, snapshots, event waits on a slot's upload) is an
-    // ordinary full dependency anyway and closes the chain.
+    // output ring (the input ring is then read-only for ticks). The host's model is never less strict
+    // than the hardware: in_chain[] is cleared ONLY by a launch issued WITHOUT the overlap attribute
+    // (which the stream orders after everything before it), so whatever else was queued in between
+    // (uploads of gains or frame counts, snapshots, fills, event waits -- each an ordinary full
+    // dependency on the device) can only make the real overlap smaller than the assumed one. Entry
+    // points that queue a non-tick kernel also clear chain_open, so the next tick carries no attribute.
     bool pdl = false;
     if (!captured && st == c->s_cmp) {
         bool conflict = false;
         if (!separate)
             for (unsigned i = slot; i < slot + n_ticks && i < c->slots; i++)
                 conflict = conflict || c->in_chain[i];
-        pdl = c->chain_open && c->last_first != ~0u && !conflict && !getenv("CMGPU_NO_PDL");
+        pdl = c->chain_open && c->last_first != ~0u && !conflict && !c->env_no_pdl;
         if (!pdl)
             std::fill(c->in_chain.begin(), c->in_chain.end(), 0);      // a full dependency: everything before is done
         for (unsigned i = slot; i < slot + n_ticks && i < c->slots; i++)
@@ -632,39 +561,6 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
             c->last_first = slot;
     }
     return CMGPU_OK;
-}
-
-void decode_row(const uint64_t *row, unsigned C, cmgpu_meter_state_t *st)
-{
-    memset(st, 0, sizeof(*st));
-    st->frames = row[2 * C];
-    uint32_t best_mag = 0;
-    uint64_t best_order = 0;
-    for (unsigned c = 0; c < C; c++) {
-        const uint64_t key = row[c];
-        const uint32_t mag = (uint32_t)(key >> cmgpu::kKeyMagShift);
-        const uint64_t pos = (~(key >> 1)) & cmgpu::kKeyPosMask;
-        const int v = (key & 1ull) ? -(int)mag : (int)mag;
-        st->channel_peak[c] = (int16_t)v;
-        st->power[c] = (int64_t)row[C + c];
-        // global peak (vumeter.c:163-168): first sample in interleaved order with the overall
-        // largest magnitude = the channel winner with the smallest (frame, channel)
-        if (mag) {
-            const uint64_t order = pos * 16u + c;
-            if (mag > best_mag || (mag == best_mag && order < best_order)) {
-                best_mag = mag;
-                best_order = order;
-                st->global_peak = (int16_t)v;
-            }
-        }
-    }
-}
-
-double power_db(double mean_square)
-{
-    // vumeter.c:204-205: p = 20*log10(sqrt(p)/32768); p = fmin(p, 0)
-    double p = 20. * log10(sqrt(mean_square) / 32768.);
-    return fmin(p, 0.);
 }
 
 bool slot_ok(const cmgpu_ctx *c, unsigned slot) { return c && slot < c->slots; }
@@ -701,7 +597,7 @@ extern "C" {
 
 const char *cmgpu_version(void) { return "coolmic-b200 0.1 (sm_100a)"; }
 
-const char *cmgpu_last_error(void) { return g_err; }
+const char *cmgpu_last_error(void) { return cmgpu::g_err; }
 
 int cmgpu_device_count(void)
 {
@@ -719,6 +615,17 @@ void *cmgpu_host_alloc(size_t bytes)
     cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
     if (e != cudaSuccess) {
         fail(CMGPU_ERR_NOMEM, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+
+void *cmgpu_host_alloc_wc(size_t bytes)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocWriteCombined);
+    if (e != cudaSuccess) {
+        fail(CMGPU_ERR_NOMEM, "cudaHostAlloc(%zu, write-combined): %s", bytes, cudaGetErrorString(e));
         return nullptr;
     }
     return p;
@@ -755,6 +662,8 @@ static cmgpu_ctx_t *ctx_create_impl(int device, unsigned channels, unsigned out_
         return nullptr;
     }
     c->device = device;
+    c->env_no_pdl = getenv("CMGPU_NO_PDL") != nullptr;
+    c->env_no_span = getenv("CMGPU_NO_SPAN") != nullptr;
     c->channels = channels;
     c->max_streams = c->active = max_streams;
     c->slots = ring_slots;
@@ -923,6 +832,15 @@ void cmgpu_ctx_destroy(cmgpu_ctx_t *c)
     cudaFree(c->d_tick);
     if (c->h_ring)
         cudaFreeHost(c->h_ring);
+    cudaFree(c->d_take);
+    cudaFree(c->d_results);
+    cudaFree(c->d_colors);
+    cudaFree(c->d_tone);
+    if (c->h_take)
+        cudaFreeHost(c->h_take);
+    if (c->h_frames)
+        cudaFreeHost(c->h_frames);
+    for (auto ev : c->ev_frames) if (ev) cudaEventDestroy(ev);
     cudaGetLastError();
     delete c;
 }
@@ -1051,8 +969,21 @@ int cmgpu_slot_set_frames(cmgpu_ctx_t *c, unsigned slot, const uint32_t *frames)
         if (frames[s] > c->block_frames)
             return fail(CMGPU_ERR_INVAL, "stream %u: %u frames > block_frames %u", s, frames[s], c->block_frames);
     CU(cudaSetDevice(c->device));
-    CU(cudaMemcpyAsync(c->d_frames + (size_t)slot * c->max_streams, frames, sizeof(uint32_t) * c->active,
+    // "Copied": the counts are staged in a context-owned pinned row of the slot, so the caller's array
+    // is free on return whether or not it is page-locked; the row is reused only after its previous
+    // upload has left it
+    if (!c->h_frames) {
+        CU(cudaMallocHost(&c->h_frames, sizeof(uint32_t) * (size_t)c->max_streams * c->slots));
+        c->ev_frames.assign(c->slots, nullptr);
+        for (unsigned i = 0; i < c->slots; i++)
+            CU(cudaEventCreateWithFlags(&c->ev_frames[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventSynchronize(c->ev_frames[slot]));
+    uint32_t *stage = c->h_frames + (size_t)slot * c->max_streams;
+    memcpy(stage, frames, sizeof(uint32_t) * c->active);
+    CU(cudaMemcpyAsync(c->d_frames + (size_t)slot * c->max_streams, stage, sizeof(uint32_t) * c->active,
                        cudaMemcpyHostToDevice, c->s_cmp));
+    CU(cudaEventRecord(c->ev_frames[slot], c->s_cmp));
     c->has_frames[slot] = 1;
     return CMGPU_OK;
 }
@@ -1138,6 +1069,8 @@ int cmgpu_fetch_planar(cmgpu_ctx_t *c, unsigned slot, float *host)
         return fail(CMGPU_ERR_INVAL, "context has no float planes (CMGPU_PLANAR_F32)");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
+    if (int erc = ticks_done_event_locked(c, slot))      // a tick on resident data has not recorded it yet
+        return erc;
     CU(cudaStreamWaitEvent(c->s_down, c->ev_cmp[slot], 0));
     CU(cudaMemcpyAsync(host, c->d_planar + (size_t)slot * c->planar_slot_floats,
                        c->plane_stride * c->channels * c->active * sizeof(float), cudaMemcpyDeviceToHost, c->s_down));
@@ -1162,8 +1095,11 @@ int cmgpu_slot_wait(cmgpu_ctx_t *c, unsigned slot)
     if (!slot_ok(c, slot))
         return fail(c ? CMGPU_ERR_INVAL : CMGPU_ERR_FAULT, "bad context or slot");
     CU(cudaSetDevice(c->device));
-    if (int erc = ticks_done_event_locked(c, slot))
-        return erc;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);           // chain / event bookkeeping only; the waits run unlocked
+        if (int erc = ticks_done_event_locked(c, slot))
+            return erc;
+    }
     CU(cudaEventSynchronize(c->ev_up[slot]));
     CU(cudaEventSynchronize(c->ev_cmp[slot]));
     CU(cudaEventSynchronize(c->ev_down[slot]));
@@ -1178,7 +1114,7 @@ int cmgpu_meter_decode(const uint64_t *rows, unsigned count, unsigned channels, 
         return fail(CMGPU_ERR_INVAL, "channels out of range");
     const unsigned row = 2 * channels + 2;
     for (unsigned i = 0; i < count; i++)
-        decode_row(rows + (size_t)i * row, channels, out + i);
+        cmgpu::decode_row(rows + (size_t)i * row, channels, out + i);
     return CMGPU_OK;
 }
 
@@ -1196,11 +1132,18 @@ int cmgpu_meter_snapshot(cmgpu_ctx_t *c, unsigned first, unsigned count, cmgpu_m
     c->scratch.resize(n);
     unsigned long long *src = c->d_meters + (size_t)first * c->row_u64;
     CU(cudaMemcpyAsync(c->scratch.data(), src, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->s_cmp));
-    if (reset)
+    if (reset) {
         CU(cudaMemsetAsync(src, 0, n * sizeof(uint64_t), c->s_cmp));
+        if (first == 0 && count == c->max_streams && !c->out_channels) {      // as in cmgpu_meter_reset
+            CU(cudaMemsetAsync(c->d_tick, 0, sizeof(unsigned long long), c->s_cmp));
+            c->pending_ticks = 0;
+        }
+    }
+    c->last_first = ~0u;
+    c->chain_open = false;
     CU(cudaStreamSynchronize(c->s_cmp));
     for (unsigned i = 0; i < count; i++)
-        decode_row(c->scratch.data() + (size_t)i * c->row_u64, c->out_channels ? c->out_channels : c->channels, out + i);
+        cmgpu::decode_row(c->scratch.data() + (size_t)i * c->row_u64, c->out_channels ? c->out_channels : c->channels, out + i);
     return CMGPU_OK;
 }
 
@@ -1224,7 +1167,7 @@ int cmgpu_mix_input_snapshot(cmgpu_ctx_t *c, unsigned first, unsigned count, cmg
         CU(cudaMemsetAsync(src, 0, n * sizeof(uint64_t), c->s_cmp));
     CU(cudaStreamSynchronize(c->s_cmp));
     for (unsigned i = 0; i < count; i++)
-        decode_row(c->scratch.data() + (size_t)i * c->row_in_u64, c->channels, out + i);
+        cmgpu::decode_row(c->scratch.data() + (size_t)i * c->row_in_u64, c->channels, out + i);
     return CMGPU_OK;
 }
 
@@ -1271,6 +1214,14 @@ int cmgpu_meter_reset(cmgpu_ctx_t *c, unsigned first, unsigned count)
     if (c->d_meters_in)
         CU(cudaMemsetAsync(c->d_meters_in + (size_t)first * c->row_in_u64, 0, sizeof(uint64_t) * c->row_in_u64 * count,
                            c->s_cmp));
+    if (first == 0 && count == c->max_streams) {
+        // every meter window starts afresh: rebase the position keys' tick number to zero, so that the
+        // 46 - pbits bits a key keeps of it can only wrap INSIDE one window of that many ticks
+        CU(cudaMemsetAsync(c->d_tick, 0, sizeof(unsigned long long), c->s_cmp));
+        c->pending_ticks = 0;
+    }
+    c->last_first = ~0u;
+    c->chain_open = false;
     return CMGPU_OK;
 }
 
@@ -1280,37 +1231,7 @@ int cmgpu_finalise(const cmgpu_meter_state_t *st, uint32_t rate, unsigned channe
         return fail(CMGPU_ERR_FAULT, "NULL argument");
     if (!channels || channels > CMGPU_MAX_CHANNELS)
         return fail(CMGPU_ERR_INVAL, "channels out of range");
-    if (!st->frames)
-        return CMGPU_ERR_INVAL;                     // vumeter.c:198-199
-    memset(out, 0, sizeof(*out));
-    out->rate = rate;
-    out->channels = channels;
-    out->frames = st->frames;
-    out->global_peak = st->global_peak;
-    int64_t all = 0;
-    for (unsigned ch = 0; ch < channels; ch++) {
-        all += st->power[ch];
-        out->channel_peak[ch] = st->channel_peak[ch];
-        // vumeter.c:203: signed integer division first, then the conversion to double
-        out->channel_power[ch] = power_db((double)(st->power[ch] / (int64_t)st->frames));
-    }
-    // vumeter.c:209: unsigned division by frames * channels
-    out->global_power = power_db((double)((uint64_t)all / (uint64_t)(st->frames * (uint64_t)channels)));
-    return CMGPU_OK;
-}
-
-int cmgpu_meter_result(cmgpu_ctx_t *c, unsigned stream, uint32_t rate, cmgpu_result_t *out)
-{
-    if (!c || !out)
-        return fail(CMGPU_ERR_FAULT, "NULL argument");
-    cmgpu_meter_state_t st;
-    int rc = cmgpu_meter_snapshot(c, stream, 1, &st, 0);
-    if (rc)
-        return rc;
-    rc = cmgpu_finalise(&st, rate, c->out_channels ? c->out_channels : c->channels, out);
-    if (rc)
-        return rc;
-    return cmgpu_meter_reset(c, stream, 1);
+    return cmgpu::finalise_state(st, rate, channels, out);
 }
 
 int cmgpu_time_process(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, unsigned reps, unsigned flags, float *ms)
@@ -1345,7 +1266,10 @@ int cmgpu_time_process(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, un
 // for all of the span's slots or for none.
 // Brings the device's tick counter up to date with the ticks the host has numbered itself; needed
 // before a captured cycle, whose launches count from the device counter.
-static int flush_ticks_locked(cmgpu_ctx *c)
+}  // extern "C"
+
+namespace {
+int flush_ticks_locked(cmgpu_ctx *c)
 {
     c->last_first = ~0u;
     c->chain_open = false;
@@ -1359,7 +1283,7 @@ static int flush_ticks_locked(cmgpu_ctx *c)
 
 static bool span_ok(const cmgpu_ctx *c, unsigned first_slot, unsigned n_slots, unsigned flags)
 {
-    if (n_slots < 2 || c->plan_g <= 0 || c->tma || c->out_channels || (flags & CMGPU_PLANAR) || getenv("CMGPU_NO_SPAN"))
+    if (n_slots < 2 || c->plan_g <= 0 || c->tma || c->out_channels || (flags & CMGPU_PLANAR) || c->env_no_span)
         return false;
     if ((uint64_t)n_slots * c->active * c->plan_items >= (1ull << 32))
         return false;
@@ -1431,6 +1355,10 @@ static int build_cycle_locked(cmgpu_ctx *c, unsigned first_slot, unsigned n_slot
     c->graph_gen = c->config_gen;
     return CMGPU_OK;
 }
+
+}  // namespace
+
+extern "C" {
 
 int cmgpu_process_cycle(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, unsigned flags)
 {

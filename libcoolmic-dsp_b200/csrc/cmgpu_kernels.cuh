@@ -17,6 +17,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "cmgpu_tables.h"
+
 #ifndef CMGPU_UNROLL
 #define CMGPU_UNROLL 4      // vectors per load batch of a lane (two batches are held in registers)
 #endif
@@ -42,64 +44,6 @@
 #endif
 
 namespace cmgpu {
-
-// ---- device tables ---------------------------------------------------------------------
-
-// Per-stream gain recipe, one row per stream (device resident, 16-byte aligned).
-// For channel c:   X  = x * mul[c]                      (mul = 2^pre, pre in 0..16)
-//                  y  = clamp16((X * (int)mw[c] + ((X & addm[c]) << 32) + (X < 0 ? 2^32 - 1 : 0)) >> 32)
-// which equals trunc(x*g/d) for every int16 x wherever the true quotient is inside the clamp
-// range and clamps identically outside (proof: DESIGN.md "Exact division"; exhaustive test:
-// tests/test_recipe.py through cmgpu_recipe_eval()).
-struct GainRow {
-    uint32_t mw[16];     // low 32 bits of M = floor(2^k * g/d) + 1
-    uint32_t addm[16];   // all-ones when M >= 2^31 (then mulhi_s32 misses +X), else 0
-    uint32_t mul[16];    // 2^pre
-    uint32_t flags;      // bit 0: identity (scale == 0, or every gain[c] == scale)
-    uint32_t pad[3];
-};
-static_assert(sizeof(GainRow) == 208, "GainRow layout");
-
-constexpr uint32_t kGainIdentity = 1u;   // flags bit 0: y = x for every channel
-constexpr uint32_t kGainAddAll = 2u;     // flags bit 1: addm is all-ones for every channel
-
-// How a work item applies its stream's recipe (warp-uniform, chosen per item from flags).
-enum GainMode { GM_IDENTITY = 0, GM_MASKED = 1, GM_ADDALL = 2 };
-
-// Meter row per stream: { peak_key[C], power[C], frames, 0 } as uint64.
-// peak_key = mag(17 bits) << 47 | (~position & (2^46-1)) << 1 | negative
-// so that a 64-bit atomicMax keeps the largest magnitude and, among equals, the earliest
-// position -- exactly the strict '>' update of vumeter.c:163. position = tick << pbits | frame.
-constexpr int      kKeyMagShift = 47;
-constexpr uint64_t kKeyPosMask = (1ull << 46) - 1ull;
-
-struct TickArgs {
-    const uint8_t *in;          // slot base (device)
-    uint8_t *out;               // == in when working in place
-    const uint32_t *frames;     // valid frames per stream, or nullptr = block_frames each
-    const GainRow *gains;
-    unsigned long long *meters;
-    unsigned long long *tick;   // [0] tick sequence number as of the last bump_tick
-    uint32_t pbits;             // position = (tick[0] + tick_offset) << pbits | frame
-    uint32_t tick_offset;       // the launch's tick number relative to tick[0]
-    uint32_t reserved0;
-    uint32_t n_streams;
-    uint32_t block_frames;
-    uint32_t stride_bytes;      // bytes between stream-blocks (multiple of 16)
-    uint32_t items_per_block;   // work items (chunks) per stream-block
-    uint32_t per_item;          // vectors (fast kernels) or frames (generic kernel) per item
-    uint32_t row_u64;           // meter row length in uint64
-    uint32_t store;             // write PCM to `out` (0 only for identity streams in place)
-    float *planar;              // optional second output: [stream][channel][plane_stride] float = y / 32768.f
-    uint32_t plane_stride;      // floats per plane (block_frames rounded up to 4)
-    // A span: ONE launch walks n_ticks consecutive ring slots (fused_tick only; 0 or 1 = a plain tick).
-    // Work items then number (tick, stream, chunk); tick t of the span sits slot_bytes * t further
-    // into both rings and frames_stride * t further into `frames`, and takes the position base
-    // tick[0] + tick_offset + t, so the meter keys order its samples after those of tick t - 1.
-    uint32_t n_ticks;
-    uint32_t frames_stride;
-    uint64_t slot_bytes;
-};
 
 // ---- small helpers -----------------------------------------------------------------------
 
@@ -894,7 +838,7 @@ __global__ void __launch_bounds__(256, 2) any_tick(const __grid_constant__ TickA
 
 // Advances the tick sequence number: at the end of a captured cycle (the graph orders it after
 // every tick node) and, from the host, before a cycle when plain ticks were issued since the last one.
-__global__ void bump_tick(unsigned long long *tick, unsigned n)
+static __global__ void bump_tick(unsigned long long *tick, unsigned n)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0)
         atomicAdd(tick, (unsigned long long)n);

@@ -19,33 +19,6 @@
 
 namespace cmgpu {
 
-// Per-stream mix recipe (device table row).
-struct MixRow {
-    uint16_t w[16][16];      // w[m][c]
-    uint32_t magic;          // M = floor(2^(31+l) / scale) + 1, l = ceil(log2(scale))
-    uint32_t shift;          // 31 + l
-    uint32_t pad[2];
-    // 8 -> 2 fast path: for output m and channel pair p the bytes { lo(w[2p]), lo(w[2p+1]), hi(w[2p]), hi(w[2p+1]) },
-    // so that two dp2a per pair give sum(x * lo) and sum(x * hi) straight from the packed input word
-    uint32_t packed[2][4];
-};
-static_assert(sizeof(MixRow) == 560, "MixRow layout");
-
-struct MixArgs {
-    const uint8_t *in;            // [stream][frames*CIN] S16, stride_in bytes apart
-    uint8_t *out;                 // [stream][frames*COUT] S16, stride_out bytes apart
-    const uint32_t *frames;
-    const MixRow *rows;
-    unsigned long long *meters_in;    // rows of (2*CIN+2) uint64
-    unsigned long long *meters_out;   // rows of (2*COUT+2) uint64
-    unsigned long long *tick;
-    uint32_t pbits, tick_offset, reserved0;
-    uint32_t n_streams, block_frames;
-    uint32_t stride_in, stride_out;
-    uint32_t items_per_block, per_item;   // frames per item
-    uint32_t cin, cout;
-};
-
 // exact trunc(n / scale) wherever the quotient is inside the clamp range; returns the
 // UNSATURATED quotient (callers saturate to 16 bits, two results with one cvt.pack.sat where they can).
 // The 64-bit sum is first saturated to +-(2^31 - 1): everything beyond that saturates in the result
