@@ -239,8 +239,8 @@ float cmgpu_comm_last_gather_ms(const cmgpu_comm_t *comm);
  * ahsv2argb (util.h:40-47, util.c:59-139), for every stream of [first, first+count) in one kernel over
  * the CURRENT meter rows (no reset): dB on the device, "default" profile hues, packed 0xAARRGGBB.
  * Host doubles are the reference (csrc/host/shim_util.c is bit-exact with util.c); the device's sin()
- * may differ in the last place, so hues agree to a few ulp and a colour byte can differ by one only
- * when x*255 lands within that of an integer. Streams with no frames metered get all-zero colours. */
+ * and log10() may differ in the last places, so hues agree to ~1e-13 relative and a colour byte can
+ * differ by one only when x*255 lands within that of an integer. Streams with no frames metered get all-zero colours. */
 typedef struct cmgpu_colors {
     uint32_t global_power_argb, global_peak_argb;
     uint32_t channel_power_argb[CMGPU_MAX_CHANNELS];

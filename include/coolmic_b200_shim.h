@@ -127,11 +127,38 @@ coolmic_vumeter_t    *coolmic_b200_batch_vumeter_new(coolmic_b200_batch_t *batch
                                                      const char *name, coolmic_b200_ro_t associated);
 int                   coolmic_b200_batch_tick(coolmic_b200_batch_t *batch);
 size_t                coolmic_b200_batch_pending(coolmic_b200_batch_t *batch);
+/* The same batch on a ring of `ring_slots` (1..64) pinned/device slots: tick() only QUEUES the slot's
+ * upload, fused launch and download and returns, so tick t uploads while t-1 computes and t-2
+ * downloads (simple.c:445-505's loop, `ring_slots` blocks deep). Readers follow tick by tick; the
+ * first read of a tick's output waits for that slot's download alone. tick() is refused with
+ * COOLMIC_ERROR_BUSY while a reader still has unread output in the slot it would reuse, i.e. once
+ * the slowest reader is `ring_slots` ticks behind. `pull_threads` (>= 1) host threads share the
+ * members' input pulls of a tick (each input handle is called from one thread at a time).
+ * coolmic_b200_batch_new() is the ring_slots = 1, pull_threads = 1 case. Readers of DIFFERENT handles
+ * may run on different threads, also while the driver is inside tick() (which never touches a slot
+ * with unread output); one handle, like any coolmic object, belongs to one thread at a time. */
+coolmic_b200_batch_t *coolmic_b200_batch_new_ring(int device, unsigned int channels, unsigned int max_streams,
+                                                  unsigned int block_frames, unsigned int ring_slots,
+                                                  unsigned int pull_threads);
+/* coolmic_vumeter_result() for every member at once, with ONE device round trip: results[s], rcs[s]
+ * for s = 0 .. max_streams-1 (rcs[s] = COOLMIC_ERROR_INVAL where nothing was metered; vumeter.c:198). */
+int                   coolmic_b200_batch_results(coolmic_b200_batch_t *batch, coolmic_vumeter_result_t *results,
+                                                 int *rcs);
 
 /* Which CUDA device the objects created from now on use (default 0, or $COOLMIC_B200_DEVICE). */
 int coolmic_b200_set_device(int device);
 /* Kernel launches issued on behalf of shim objects so far (evidence that reads run on the GPU). */
 uint64_t coolmic_b200_shim_launches(void);
+/* Measurement: the loop a host application runs (simple.c:445-505), through the objects above only.
+ * `streams` member transforms of a ring batch, each fed by a memory iohandle that cycles over its row
+ * of `pcm` ([streams][bytes_per_stream]), gains as in bench.py, fused vumeters; `n_ticks` ticks of
+ * `block_frames`; every transform's output is read back through its own iohandle by `threads`
+ * consumer threads, `ring_slots - 1` ticks behind the producer; one coolmic_b200_batch_results() at
+ * the end. *seconds = wall time of the loop, *frames_metered = sum of result.frames. */
+int coolmic_b200_bench_objects(int device, unsigned int channels, unsigned int streams, unsigned int block_frames,
+                               unsigned int n_ticks, unsigned int ring_slots, unsigned int threads,
+                               unsigned int bytes_per_stream, const void *pcm, double *seconds,
+                               uint64_t *frames_metered);
 
 #ifdef __cplusplus
 }

@@ -331,20 +331,7 @@ int cmgpu_gather_results(cmgpu_ctx_t *c, cmgpu_comm_t *m, int root, uint32_t rat
         if (counts)
             for (int r = 0; r < m->size; r++)
                 counts[r] = m->h_counts[r];
-        for (size_t i = 0; i < total; i++) {
-            cmgpu_meter_state_t stt;
-            cmgpu::decode_row(m->h_gather + i * row, C, &stt);
-            if (states)
-                states[i] = stt;
-            int r = stt.frames ? CMGPU_OK : CMGPU_ERR_INVAL;
-            if (results) {
-                r = cmgpu::finalise_state(&stt, rate, C, results + i);
-                if (r != CMGPU_OK)
-                    memset(results + i, 0, sizeof(*results));
-            }
-            if (rcs)
-                rcs[i] = r;
-        }
+        cmgpu::finalise_rows(m->h_gather, total, row, C, rate, results, states, rcs);
     }
     return CMGPU_OK;
 }

@@ -27,6 +27,10 @@ int fail(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
 
 int take_rows_locked(struct ::cmgpu_ctx *c, unsigned first, unsigned count, int reset, bool device_db, uint32_t rate);
 int ensure_take_buffers_locked(struct ::cmgpu_ctx *c);
+// Host side of a result gather: raw rows -> integer states -> finalised results (each output optional),
+// spread over a few threads when there are many rows (65,536 streams x log10/sqrt is ~20 ms on one).
+void finalise_rows(const uint64_t *rows, size_t count, unsigned row_u64, unsigned channels, uint32_t rate,
+                   cmgpu_result_t *results, cmgpu_meter_state_t *states, int *rcs);
 
 }  // namespace cmgpu
 

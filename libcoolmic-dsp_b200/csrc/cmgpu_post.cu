@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 using cmgpu::fail;
 
@@ -247,6 +248,42 @@ int take_rows_locked(cmgpu_ctx *c, unsigned first, unsigned count, int reset, bo
     return CMGPU_OK;
 }
 
+void finalise_rows(const uint64_t *rows, size_t count, unsigned row_u64, unsigned channels, uint32_t rate,
+                   cmgpu_result_t *results, cmgpu_meter_state_t *states, int *rcs)
+{
+    auto work = [=](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            cmgpu_meter_state_t st;
+            decode_row(rows + i * row_u64, channels, &st);
+            if (states)
+                states[i] = st;
+            int r = st.frames ? CMGPU_OK : CMGPU_ERR_INVAL;
+            if (results) {
+                r = finalise_state(&st, rate, channels, results + i);
+                if (r != CMGPU_OK)
+                    memset(results + i, 0, sizeof(*results));
+            }
+            if (rcs)
+                rcs[i] = r;
+        }
+    };
+    unsigned n_threads = 1;
+    if (count >= 8192 && results) {
+        n_threads = std::thread::hardware_concurrency();
+        n_threads = n_threads > 8 ? 8 : (n_threads ? n_threads : 1);
+    }
+    if (n_threads <= 1) {
+        work(0, count);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < n_threads; t++)
+        pool.emplace_back(work, count * t / n_threads, count * (t + 1) / n_threads);
+    work(0, count / n_threads);
+    for (auto &th : pool)
+        th.join();
+}
+
 }  // namespace cmgpu
 
 extern "C" {
@@ -271,19 +308,11 @@ int cmgpu_meter_results(cmgpu_ctx_t *c, unsigned first, unsigned count, uint32_t
     if (device_db)
         CU(cudaMemcpyAsync(results, c->d_results, sizeof(cmgpu_result_t) * count, cudaMemcpyDeviceToHost, c->s_cmp));
     CU(cudaStreamSynchronize(c->s_cmp));
-    for (unsigned i = 0; i < count; i++) {
-        cmgpu_meter_state_t st;
-        cmgpu::decode_row(c->h_take + (size_t)i * c->row_u64, C, &st);
-        if (states)
-            states[i] = st;
-        int r = st.frames ? CMGPU_OK : CMGPU_ERR_INVAL;
-        if (results && !device_db) {
-            r = cmgpu::finalise_state(&st, rate, C, results + i);
-            if (r != CMGPU_OK)
-                memset(results + i, 0, sizeof(*results));
-        }
-        if (rcs)
-            rcs[i] = r;
+    if (device_db) {
+        // the dB values came from the device; only the integer state and the return codes are derived here
+        cmgpu::finalise_rows(c->h_take, count, c->row_u64, C, rate, nullptr, states, rcs);
+    } else {
+        cmgpu::finalise_rows(c->h_take, count, c->row_u64, C, rate, results, states, rcs);
     }
     return CMGPU_OK;
 }

@@ -314,3 +314,88 @@ long shimh_batch(const void *in, size_t n_streams, size_t bytes_per_stream, unsi
     free(mem); free(tr); free(vu); free(rd0); free(rd1); free(scratch); free(scratch2);
     return ticks;
 }
+
+/* ---- ring batch: the producer runs ahead of the readers by up to `slots` ticks ---------------- */
+long shimh_batch_ring(const void *in, size_t n_streams, size_t bytes_per_stream, unsigned rate, unsigned channels,
+                      const uint16_t *scale, const uint16_t *gain, size_t src_chunk, unsigned block_frames,
+                      unsigned slots, unsigned threads, size_t pull, void *out, size_t *out_bytes,
+                      shimh_result_t *results, int *flags)
+{
+    coolmic_b200_batch_t *batch = coolmic_b200_batch_new_ring(-1, channels, (unsigned)n_streams, block_frames, slots, threads);
+    memsrc_t *mem = calloc(n_streams, sizeof(*mem));
+    coolmic_transform_t **tr = calloc(n_streams, sizeof(*tr));
+    coolmic_vumeter_t **vu = calloc(n_streams, sizeof(*vu));
+    coolmic_iohandle_t **rd = calloc(n_streams, sizeof(*rd));
+    coolmic_vumeter_result_t *res = calloc(n_streams, sizeof(*res));
+    int *rcs = calloc(n_streams, sizeof(*rcs));
+    char *scratch = malloc(pull ? pull : 1024);
+    long ticks = 0;
+    size_t s;
+
+    if (!batch || !mem || !tr || !vu || !rd || !res || !rcs || !scratch)
+        return -1;
+    if (!pull)
+        pull = 1024;
+    *flags = 0;
+    for (s = 0; s < n_streams; s++) {
+        coolmic_iohandle_t *src;
+        mem[s].data = (const char *)in + s * bytes_per_stream;
+        mem[s].len = bytes_per_stream;
+        mem[s].chunk = src_chunk;
+        tr[s] = coolmic_b200_batch_transform_new(batch, "tr", NULL, rate);
+        if (!tr[s])
+            return -2;
+        coolmic_transform_set_master_gain(tr[s], channels, scale[s], gain + s * channels);
+        src = coolmic_iohandle_new("memsrc", NULL, &mem[s], NULL, memsrc_read, memsrc_eof);
+        coolmic_transform_attach_iohandle(tr[s], src);
+        coolmic_b200_unref(src);
+        rd[s] = coolmic_transform_get_iohandle(tr[s]);
+        vu[s] = coolmic_b200_batch_vumeter_new(batch, tr[s], "vu", NULL);
+        out_bytes[s] = 0;
+    }
+    for (;;) {
+        int fr, any = 0;
+        unsigned issued = 0;
+        /* producer: as many ticks as the ring takes; it must refuse once `slots` ticks are unread */
+        while ((fr = coolmic_b200_batch_tick(batch)) > 0) {
+            ticks++;
+            issued++;
+        }
+        if (fr != 0 && fr != -12)
+            return -10 + fr;
+        if (issued > slots)
+            *flags |= 4;
+        if (fr == -12 && coolmic_b200_batch_pending(batch) == 0)
+            *flags |= 8;                /* BUSY without anything pending */
+        /* consumers: everything that is there, in stream order (each read may wait for its slot) */
+        for (s = 0; s < n_streams; s++) {
+            for (;;) {
+                ssize_t r = coolmic_iohandle_read(rd[s], scratch, pull);
+                if (r < 0)
+                    return -5;
+                if (r == 0)
+                    break;
+                any = 1;
+                memcpy((char *)out + s * bytes_per_stream + out_bytes[s], scratch, (size_t)r);
+                out_bytes[s] += (size_t)r;
+            }
+        }
+        if (fr == 0 && !any)
+            break;
+    }
+    if (coolmic_b200_batch_pending(batch) != 0)
+        *flags |= 16;
+    if (coolmic_b200_batch_results(batch, res, rcs) != 0)
+        return -6;
+    for (s = 0; s < n_streams; s++) {
+        flatten(&results[s], rcs[s], &res[s]);
+        if (coolmic_iohandle_eof(rd[s]) != 1)
+            *flags |= 2;
+        coolmic_b200_unref(rd[s]);
+        coolmic_b200_unref(vu[s]);
+        coolmic_b200_unref(tr[s]);
+    }
+    coolmic_b200_unref(batch);
+    free(mem); free(tr); free(vu); free(rd); free(res); free(rcs); free(scratch);
+    return ticks;
+}

@@ -67,6 +67,30 @@ class ShimLib:
         results = [[_res_dict(res[s * cap + i]) for i in range(min(n_results[s], cap))] for s in range(n)]
         return int(ticks), outs, results, int(mism.value)
 
+    def batch_ring(self, pcm2d, channels, scale, gain, rate=48000, src_chunk=0, block_frames=256, slots=3, threads=1,
+                   pull=1024):
+        """The ring batch with the producer running ahead of its readers. Returns (ticks, [out bytes per
+        stream], [final result per stream], flags)."""
+        assert pcm2d.dtype == np.uint8 and pcm2d.ndim == 2 and pcm2d.flags.c_contiguous
+        n, nbytes = pcm2d.shape
+        out = np.zeros((n, nbytes), dtype=np.uint8)
+        out_bytes = (C.c_size_t * n)()
+        res = (Result * n)()
+        flags = C.c_int(0)
+        keep_s, sp = _u16(scale)
+        keep_g, gp = _u16(gain)
+        fn = self.lib.shimh_batch_ring
+        fn.restype = C.c_long
+        fn.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint, C.c_uint, C.POINTER(C.c_uint16),
+                       C.POINTER(C.c_uint16), C.c_size_t, C.c_uint, C.c_uint, C.c_uint, C.c_size_t, C.c_void_p,
+                       C.POINTER(C.c_size_t), C.POINTER(Result), C.POINTER(C.c_int)]
+        ticks = fn(pcm2d.ctypes.data, n, nbytes, rate, channels, sp, gp, src_chunk, block_frames, slots, threads, pull,
+                   out.ctypes.data, out_bytes, res, C.byref(flags))
+        if ticks < 0:
+            raise RuntimeError(f"shim ring batch harness failed: {ticks}")
+        outs = [out[s, : out_bytes[s]].copy() for s in range(n)]
+        return int(ticks), outs, [_res_dict(res[s]) for s in range(n)], int(flags.value)
+
     def transform(self, pcm, channels, gain=None, rate=48000, src_chunk=0, pull=1024):
         src = _bytes(pcm)
         out = np.zeros(src.size + 64, dtype=np.uint8)

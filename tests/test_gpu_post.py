@@ -94,7 +94,8 @@ def test_results_device_db_within_tolerance(cm, port):
 
 def test_meter_colors_match_host_util(cm, port):
     """Device colours vs the host's coolmic_util_* (bit-exact with reference util.c, tests/test_util.py):
-    hues within 4 ulp, ARGB words equal."""
+    hues within 1e-13 relative (the device's dB and sin() each differ from libm in the last places), ARGB
+    words equal."""
     lib = cm.lib()
     lib.coolmic_util_power2hue.restype = C.c_double
     lib.coolmic_util_power2hue.argtypes = [C.c_double, C.c_char_p]
@@ -123,7 +124,7 @@ def test_meter_colors_match_host_util(cm, port):
             pairs += [(r.channel_power[c], cols[s].channel_power_hue[c], cols[s].channel_power_argb[c]) for c in range(channels)]
             for power, hue, argb in pairs:
                 want_hue = lib.coolmic_util_power2hue(power, b"default")
-                assert abs(hue - want_hue) <= 4 * np.spacing(abs(want_hue)) + 1e-300, (s, power, hue, want_hue)
+                assert abs(hue - want_hue) <= 1e-13 * abs(want_hue) + 1e-300, (s, power, hue, want_hue)
                 flips += int(argb != lib.coolmic_util_ahsv2argb(1.0, want_hue, 1.0, 1.0))
             peaks = [(r.global_peak, cols[s].global_peak_argb)] + [(r.channel_peak[c], cols[s].channel_peak_argb[c]) for c in range(channels)]
             for peak, argb in peaks:

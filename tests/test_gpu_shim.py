@@ -127,3 +127,28 @@ def test_batch_mode_objects(shim, port, channels, block_frames, every, chunk):
         assert len(got) == len(want_res), (len(got), len(want_res))
         for a, b in zip(got, want_res):
             assert same_result(a, b), f"stream {s}: {a} != {b}"
+
+
+@pytest.mark.parametrize("channels,block_frames,slots,threads,chunk", [(2, 256, 3, 1, 0), (1, 100, 4, 3, 7), (8, 64, 2, 2, 100),
+                                                                      (5, 333, 3, 4, 0), (2, 1000, 1, 2, 0)])
+def test_ring_batch_producer_runs_ahead(shim, port, channels, block_frames, slots, threads, chunk):
+    """The pipelined form of batch mode (coolmic_b200_batch_new_ring): ticks are only queued, the producer
+    gets `slots` ticks ahead of the readers and is refused (COOLMIC_ERROR_BUSY) beyond that; readers
+    follow tick by tick, each read waiting for its own slot's download only. PCM and the final results
+    (one device round trip for all members) must equal the reference's, as in the synchronous form."""
+    rng = np.random.default_rng(channels * 77 + block_frames + slots)
+    n = 29
+    nbytes = 2 * channels * 2500 + 2 * channels - 1     # ends inside a frame
+    pcm = rng.integers(0, 256, size=(n, nbytes), dtype=np.uint8)
+    scale = rng.integers(0, 65536, size=n).astype(np.uint16)
+    scale[0] = 0
+    gain = rng.integers(0, 65536, size=(n, channels)).astype(np.uint16)
+    ticks, outs, results, flags = shim.batch_ring(pcm, channels, scale, gain, src_chunk=chunk, block_frames=block_frames,
+                                                  slots=slots, threads=threads, pull=777)
+    assert flags == 0, f"ring semantics violated: flags {flags}"
+    frames_total = nbytes // (2 * channels)
+    assert ticks == -(-frames_total // block_frames)
+    for s in range(n):
+        want, rc = port.transform(pcm[s], channels, (channels, int(scale[s]), gain[s].tolist()))
+        assert rc == 0 and np.array_equal(outs[s], want), f"stream {s}"
+        assert same_result(results[s], port.vumeter(want, channels)[-1]), f"stream {s}"

@@ -171,9 +171,12 @@ __global__ void __launch_bounds__(128) copy_tma_bulk(const uint8_t *in, uint8_t 
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-int main()
+int main(int argc, char **argv)
 {
-    const size_t bytes = (size_t)2 << 30;          // 2 GiB in + 2 GiB out
+    // size in GiB of EACH of the two buffers (default 2): the footprint matters -- see DESIGN.md 4.1
+    const double gib = argc > 1 ? atof(argv[1]) : 2.0;
+    const size_t bytes = ((size_t)(gib * (double)((size_t)1 << 30))) & ~(size_t)0xffff;
+    printf("buffers: 2 x %.2f GiB\n", (double)bytes / (double)((size_t)1 << 30));
     uint8_t *in, *out;
     CK(cudaMalloc(&in, bytes));
     CK(cudaMalloc(&out, bytes));
