@@ -553,6 +553,14 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
             c->in_chain[i] = 1;
         c->chain_open = true;
     }
+    // A launch that does not overlap its predecessor hands its work items out dynamically (TickArgs::work):
+    // plain ticks of the warp-per-item kernels on the compute stream. Spans, captured cycles (their
+    // ticks run side by side on forked streams) and overlapping launches keep the static order.
+    a.work = nullptr;
+    if (!pdl && !captured && st == c->s_cmp && n_ticks <= 1 && c->plan_g == 32 && !c->tma && !c->env_static) {
+        CU(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned int), st));
+        a.work = c->d_work;
+    }
     CU(launch_tick(c, a, gm, meter, st, pdl));
     c->launches++;
     if (!captured) {
@@ -664,6 +672,7 @@ static cmgpu_ctx_t *ctx_create_impl(int device, unsigned channels, unsigned out_
     c->device = device;
     c->env_no_pdl = getenv("CMGPU_NO_PDL") != nullptr;
     c->env_no_span = getenv("CMGPU_NO_SPAN") != nullptr;
+    c->env_static = getenv("CMGPU_STATIC_ITEMS") != nullptr;       // A/B hook: never claim work items dynamically
     c->channels = channels;
     c->max_streams = c->active = max_streams;
     c->slots = ring_slots;
@@ -747,6 +756,8 @@ static cmgpu_ctx_t *ctx_create_impl(int device, unsigned channels, unsigned out_
         return bail("cudaMalloc(tick)", e);
     if ((e = cudaMalloc(&c->d_frames, sizeof(uint32_t) * (size_t)max_streams * ring_slots)) != cudaSuccess)
         return bail("cudaMalloc(frames)", e);
+    if ((e = cudaMalloc(&c->d_work, sizeof(unsigned int))) != cudaSuccess)
+        return bail("cudaMalloc(work counter)", e);
     if ((e = cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->s_cmp, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking)) != cudaSuccess)
@@ -824,6 +835,7 @@ void cmgpu_ctx_destroy(cmgpu_ctx_t *c)
     cudaFree(c->d_gains);
     cudaFree(c->d_meters);
     cudaFree(c->d_frames);
+    cudaFree(c->d_work);
     cudaFree(c->d_planar);
     cudaFree(c->d_mix);
     cudaFree(c->d_meters_in);

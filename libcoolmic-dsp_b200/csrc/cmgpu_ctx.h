@@ -52,7 +52,8 @@ struct cmgpu_ctx {
     uint64_t launches = 0;
     int num_sms = 0;
     // environment hooks, read ONCE at cmgpu_ctx_create (never on the launch path)
-    bool env_no_pdl = false, env_no_span = false;
+    bool env_no_pdl = false, env_no_span = false, env_static = false;
+    unsigned int *d_work = nullptr;                // work-claim counter of non-overlapping launches (TickArgs::work)
 
     uint8_t *d_in = nullptr, *d_out = nullptr;     // rings
     uint8_t *h_ring = nullptr;                     // pinned staging ring

@@ -527,6 +527,22 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
             store_planar<C>(a.planar, a.plane_stride, (it).s, (it).first + iu * G, o, 8); \
     }
 
+#define CMGPU_LOAD_REM(buf, it, b)                                                      \
+    _Pragma("unroll") for (int u = 0; u < UNROLL - 1; u++)                              \
+        if ((b) * UNROLL + u < (it).n_i)                                                \
+            buf[u] = ld_stream((it).src + (size_t)((b) * UNROLL + u) * kStep, nc);
+#define CMGPU_DO_REM(buf, it, b)                                                        \
+    _Pragma("unroll") for (int u = 0; u < UNROLL - 1; u++) {                            \
+        const uint32_t iu = (b) * UNROLL + u;                                           \
+        if (iu < (it).n_i) {                                                            \
+            const uint4 o = do_vector<C, GM, METER, false, Tune<C, G>::kSatPack, false, true>(buf[u], rc, 0xffffu - iu, kmax, pacc, 8); \
+            if (a.store)                                                                \
+                st_stream(dstp + (size_t)iu * kStep, o);                                \
+            if (PLANAR)                                                                 \
+                store_planar<C>(a.planar, a.plane_stride, (it).s, (it).first + iu * G, o, 8); \
+        }                                                                               \
+    }
+
     uint64_t item = (uint64_t)blockIdx.x * groups_per_cta + threadIdx.x / G;
     Item cur;
     Recipe rc[P];
@@ -557,12 +573,23 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
             CMGPU_LOAD_ALL(cur)
         } else if (cur.n_i >= (uint32_t)UNROLL) {
             CMGPU_LOAD_BATCH(bufA, cur, 0u)
+        } else if (cur.n_i) {
+            CMGPU_LOAD_REM(bufA, cur, 0u)
         }
     }
     while (have) {
         // (opaque: otherwise ptxas re-derives the address from src at every store, 8 instructions each)
         uint8_t *const dstp = reinterpret_cast<uint8_t *>(opaque(reinterpret_cast<uint64_t>(cur.src) + (uint64_t)out_delta));
         const uint32_t nb = (G == 8) ? 0u : cur.n_i / UNROLL;   // full batches of this lane; batch 0 is in flight
+        // what is left of the lane's vectors after them (< UNROLL) is one more, predicated, batch of the
+        // same pipeline: requested while the last full batch is worked on, into the register set that is
+        // free then (measured on the 48,000-frame stream-blocks of config 5, whose eighth work item ends
+        // in such a remainder: requested only after the loop, its latency was exposed once per item)
+        const bool rem = (G != 8) && nb * UNROLL < cur.n_i;
+        // work distribution, see TickArgs::work: the next item's number is requested now and used after the loops
+        uint32_t claimed = 0;
+        if (G != 8 && a.work != nullptr && lane == 0)
+            claimed = atomicAdd(a.work, 1u);
         if (G == 8) {
             CMGPU_DO_ALL(bufA, cur, 0u)
             CMGPU_DO_ALL(bufB, cur, (uint32_t)UNROLL)
@@ -570,31 +597,24 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
         for (uint32_t b = 0; b < nb; b += 2) {
             if (b + 1 < nb) {
                 CMGPU_LOAD_BATCH(bufB, cur, b + 1)
+            } else if (rem) {
+                CMGPU_LOAD_REM(bufB, cur, b + 1)
             }
             CMGPU_DO_BATCH(bufA, cur, b)
             if (b + 2 < nb) {
                 CMGPU_LOAD_BATCH(bufA, cur, b + 2)
+            } else if (b + 2 == nb && rem) {
+                CMGPU_LOAD_REM(bufA, cur, b + 2)
             }
             if (b + 1 < nb) {
                 CMGPU_DO_BATCH(bufB, cur, b + 1)
             }
         }
-        // what is left of the lane's vectors (< UNROLL): requested together, then worked on
-        const uint32_t rem0 = nb * UNROLL;
-        if (G != 8 && rem0 < cur.n_i) {
-#pragma unroll
-            for (int u = 0; u < UNROLL - 1; u++)
-                if (rem0 + u < cur.n_i)
-                    bufB[u] = ld_stream(cur.src + (size_t)(rem0 + u) * kStep, nc);
-#pragma unroll
-            for (int u = 0; u < UNROLL - 1; u++) {
-                if (rem0 + u < cur.n_i) {
-                    const uint4 o = do_vector<C, GM, METER, false, Tune<C, G>::kSatPack, false, true>(bufB[u], rc, 0xffffu - (rem0 + u), kmax, pacc, 8);
-                    if (a.store)
-                        st_stream(dstp + (size_t)(rem0 + u) * kStep, o);
-                    if (PLANAR)
-                        store_planar<C>(a.planar, a.plane_stride, cur.s, cur.first + (rem0 + u) * G, o, 8);
-                }
+        if (rem) {
+            if (nb & 1u) {
+                CMGPU_DO_REM(bufB, cur, nb)
+            } else {
+                CMGPU_DO_REM(bufA, cur, nb)
             }
         }
         // Everything about the item that the loops above did not need (stream, tail vector, frame
@@ -613,7 +633,10 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
         }
 
         // next item: recipes and first batch go out before this item's epilogue
-        item += stride;
+        if (G != 8 && a.work != nullptr)
+            item = stride + __shfl_sync(0xffffffffu, claimed, 0);      // the first `stride` items were dealt out statically
+        else
+            item += stride;
         Item nxt;
         Recipe rcn[P];
         have = item_setup<C, G>(a, item, n_items, gl, nxt);
@@ -623,6 +646,8 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
                 CMGPU_LOAD_ALL(nxt)
             } else if (nxt.n_i >= (uint32_t)UNROLL) {
                 CMGPU_LOAD_BATCH(bufA, nxt, 0u)
+            } else if (nxt.n_i) {
+                CMGPU_LOAD_REM(bufA, nxt, 0u)
             }
         }
         if (METER) {
@@ -641,6 +666,8 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
     }
 #undef CMGPU_LOAD_BATCH
 #undef CMGPU_DO_BATCH
+#undef CMGPU_LOAD_REM
+#undef CMGPU_DO_REM
 #undef CMGPU_LOAD_ALL
 #undef CMGPU_DO_ALL
     tick_end(a);

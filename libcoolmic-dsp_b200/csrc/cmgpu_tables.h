@@ -62,6 +62,14 @@ struct TickArgs {
     uint32_t n_ticks;
     uint32_t frames_stride;
     uint64_t slot_bytes;
+    // Work distribution (fused_tick, 32-lane groups). nullptr: static -- group g takes items g, g + n,
+    // g + 2n, ... (n = groups of the grid). Otherwise a zeroed counter: the first n items are dealt out
+    // statically, every further one is claimed with an atomicAdd when a group starts on its current
+    // item, so that SMs that run a little faster simply take more items and the launch has no long tail
+    // of stragglers. Launches that overlap the previous one (programmatic dependent launch) keep the
+    // static order: their tail is hidden by the next launch's head, and a counter would have to be
+    // private to each launch in flight.
+    unsigned int *work;
 };
 
 // Per-stream mix recipe (device table row).

@@ -23,11 +23,36 @@ def build() -> Path:
     return SO
 
 
+STUB_SRC = [ROOT / "tests" / "stub" / "cmgpu_stub.c", ROOT / "oracle" / "coolmic_oracle.c",
+            Path(__file__).resolve().parent / "shim_harness.c"]
+HOST_SRC = sorted((ROOT / "libcoolmic-dsp_b200" / "csrc" / "host").glob("*.c"))
+
+
+def build_stub(sanitize: str = "", main: bool = False) -> Path:
+    """The product's host shim (csrc/host/*.c) linked against tests/stub/cmgpu_stub.c -- a CPU stand-in
+    for the cmgpu_* engine built on the oracle port -- so that the shim's HOST LOGIC runs without a GPU.
+    `sanitize`: "", "address,undefined" or "thread"; `main`: the stand-alone scenario runner instead of
+    a shared library (sanitizer runtimes do not like being loaded into python)."""
+    tag = sanitize.replace(",", "_") or "plain"
+    out = SO.parent / (f"shim_stub_{tag}" + ("" if main else ".so"))
+    srcs = HOST_SRC + STUB_SRC + ([ROOT / "tests" / "stub" / "san_main.c"] if main else [])
+    if out.exists() and out.stat().st_mtime > max(s.stat().st_mtime for s in srcs):
+        return out
+    SO.parent.mkdir(exist_ok=True)
+    cmd = ["gcc", "-std=gnu11", "-O1", "-g", "-fPIC", "-Wall", "-Wextra", "-pthread", f"-I{ROOT / 'include'}"]
+    if sanitize:
+        cmd += [f"-fsanitize={sanitize}", "-fno-omit-frame-pointer"]
+    if not main:
+        cmd += ["-shared"]
+    subprocess.run(cmd + ["-o", str(out)] + [str(s) for s in srcs] + ["-lm"], check=True)
+    return out
+
+
 class ShimLib:
     kind = "b200 shim"
 
-    def __init__(self):
-        self.lib = L = C.CDLL(str(build()))
+    def __init__(self, stub: bool = False):
+        self.lib = L = C.CDLL(str(build_stub() if stub else build()))
         L.shimh_sizeof_result.restype = C.c_uint
         L.shimh_null_checks.restype = C.c_int
         L.shimh_transform.restype = C.c_long
