@@ -505,23 +505,34 @@ def main():
         total_streams = streams_per_gpu * world
         gathered = [None]
         gather = not args.e2e_no_gather
+        # result arrays allocated once (65,536 x 192 B of ctypes structures take milliseconds to create)
+        gather_out = cm.Comm.alloc_results(total_streams, world) if (comm is not None and rank == 0) else None
+        results_out = cm.Engine.alloc_results(streams_per_gpu)
+
+        presubmitted = [0]
+        ahead = min(3, n_ticks)
 
         def e2e_step():
             # Upload, tick and download of every tick are queued on the engine's three streams; the
             # step's meter results are taken as soon as its last tick has run (stream order on the
             # compute stream), sent to rank 0 over NCCL and finalised there, while the downloads of this
-            # step's last ticks overlap the uploads of the next step's first ones. Everything is drained
-            # (eng.sync) before the clock stops. No barrier between steps: ranks other than the root
-            # never wait on the host for the gather.
+            # step's last ticks overlap the uploads of the next step's first ones: those are queued
+            # BEFORE the host waits for the results, so the upload stream never idles at a step boundary.
+            # Everything is drained (eng.sync) before the clock stops. No barrier between steps: ranks
+            # other than the root never wait on the host for the gather.
             for t in range(n_ticks):
                 slot = t % 4
-                eng.submit(slot, pin_in.array[t])
+                if t >= presubmitted[0]:
+                    eng.submit(slot, pin_in.array[t])
                 eng.process(slot)
                 eng.fetch(slot, pin_out.array[t])
+            for t in range(ahead):                       # the next step's first uploads
+                eng.submit(t % 4, pin_in.array[t])
+            presubmitted[0] = ahead
             if comm is not None and gather:
-                out = comm.gather_results(eng, rate, total_streams)
+                out = comm.gather_results(eng, rate, total_streams, out=gather_out)
             else:
-                res, st, rcs = eng.results(rate)
+                res, st, rcs = eng.results(rate, out=results_out)
                 out = (res, st, rcs, [streams_per_gpu])
             if out is not None:
                 gathered[0] = out
@@ -558,7 +569,8 @@ def main():
                "gbs_each_way_all_ranks": sum_over_ranks(n_ticks * slot_bytes * e2e_steps / wall_mine / 1e9),
                "nccl_gather_ms_per_step": (gather_ms / e2e_steps) if comm is not None else None,
                "how": f"{n_ticks} ticks of {tick_frames} frames per step through a 4-slot ring, pinned host buffers, "
-                      "upload/compute/download on three CUDA streams; per step the meter results of all ranks are gathered to "
+                      "upload/compute/download on three CUDA streams (the next step's first uploads are queued before the "
+                      "host waits for this step's results); per step the meter results of all ranks are gathered to "
                       "rank 0 by cmgpu_gather_results (NCCL send/recv of the raw rows on the compute stream, decode + dB "
                       "finalise on rank 0); steps are queued back to back and drained before the clock stops"}
         eng.close()

@@ -295,6 +295,11 @@ int cmgpu_time_cycles(cmgpu_ctx_t *ctx, unsigned first_slot, unsigned n_slots, u
  * same moment (after a barrier) each sees its share of the links they have in common. */
 int cmgpu_link_probe(int device, size_t bytes, unsigned reps, int write_combined, float *h2d_gbs, float *d2h_gbs,
                      float *both_gbs);
+/* Bounds-checking build only (make -C csrc debug -> lib/libcoolmic_b200_dbg.so, for pools without
+ * compute-sanitizer): every PCM vector access of the tick kernels is checked against the launching
+ * context's rings; returns the number of stray accesses so far (they are dropped, and cmgpu_sync
+ * fails). -1 in the normal build. */
+int cmgpu_debug_violations(void);
 /* Number of kernel launches this context has issued so far. */
 uint64_t cmgpu_launch_count(const cmgpu_ctx_t *ctx);
 /* Name of the kernel variant cmgpu_process would pick for the current shape (for logs). */

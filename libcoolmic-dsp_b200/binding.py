@@ -121,6 +121,7 @@ SYMBOLS = {
     "cmgpu_time_cycles": (C.c_int, [_P, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_float)]),
     "cmgpu_link_probe": (C.c_int, [C.c_int, C.c_size_t, C.c_uint, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                    C.POINTER(C.c_float)]),
+    "cmgpu_debug_violations": (C.c_int, []),
     "cmgpu_launch_count": (C.c_uint64, [_P]),
     "cmgpu_kernel_name": (C.c_char_p, [_P]),
     "cmgpu_meter_results": (C.c_int, [_P, C.c_uint, C.c_uint, C.c_uint32, C.c_int, C.c_uint, C.POINTER(Result),
@@ -335,12 +336,15 @@ class Engine:
             return {"rc": rc}
         return res.as_dict()
 
-    def results(self, rate: int, first: int = 0, count: int | None = None, reset: bool = True, flags: int = 0):
-        """coolmic_vumeter_result for many streams in one device round trip -> (Result[], MeterState[], rc[])."""
+    @staticmethod
+    def alloc_results(count: int):
+        return (Result * count)(), (MeterState * count)(), (C.c_int * count)()
+
+    def results(self, rate: int, first: int = 0, count: int | None = None, reset: bool = True, flags: int = 0, out=None):
+        """coolmic_vumeter_result for many streams in one device round trip -> (Result[], MeterState[], rc[]).
+        `out`: arrays from alloc_results() to fill instead of new ones."""
         count = self.active - first if count is None else count
-        res = (Result * count)()
-        st = (MeterState * count)()
-        rcs = (C.c_int * count)()
+        res, st, rcs = out if out is not None else self.alloc_results(count)
         _check(self.L.cmgpu_meter_results(self.ctx, first, count, rate, int(reset), flags, res, st, rcs),
                "cmgpu_meter_results")
         return res, st, rcs
@@ -434,14 +438,19 @@ class Comm:
         _check(self.L.cmgpu_comm_sum(self.comm, arr, len(values)), "cmgpu_comm_sum")
         return list(arr) if len(values) > 1 else arr[0]
 
-    def gather_results(self, eng: "Engine", rate: int, total_streams: int, root: int = 0, reset: bool = True,
-                       want_results: bool = True, want_states: bool = True):
-        """Collective. On the root: (Result[total], MeterState[total], rc[total], counts[nranks]); else None."""
+    @staticmethod
+    def alloc_results(total_streams: int, nranks: int):
+        return ((Result * total_streams)(), (MeterState * total_streams)(), (C.c_int * total_streams)(),
+                (C.c_uint * nranks)())
+
+    def gather_results(self, eng: "Engine", rate: int, total_streams: int, root: int = 0, reset: bool = True, out=None):
+        """Collective. On the root: (Result[total], MeterState[total], rc[total], counts[nranks]); else None.
+        `out`: arrays from alloc_results() to fill instead of new ones (root only)."""
         is_root = self.rank == root
-        res = (Result * total_streams)() if is_root and want_results else None
-        st = (MeterState * total_streams)() if is_root and want_states else None
-        rcs = (C.c_int * total_streams)() if is_root else None
-        counts = (C.c_uint * self.size)() if is_root else None
+        if is_root:
+            res, st, rcs, counts = out if out is not None else self.alloc_results(total_streams, self.size)
+        else:
+            res = st = rcs = counts = None
         _check(self.L.cmgpu_gather_results(eng.ctx, self.comm, root, rate, int(reset), res, st, rcs, counts),
                "cmgpu_gather_results")
         return (res, st, rcs, list(counts)) if is_root else None

@@ -7,6 +7,7 @@
 #include "cmgpu_kernels.cuh"
 #include "cmgpu_mix.cuh"
 #include "cmgpu_tma.cuh"
+#include "cmgpu_span.cuh"
 
 #include "cmgpu_ctx.h"
 
@@ -160,6 +161,34 @@ TickKernel tma_kernel(const cmgpu_ctx *c, int gm, bool meter)
     }
 }
 
+template <int C>
+TickKernel span_kernel_c(int gm, bool meter, bool nc)
+{
+    using namespace cmgpu;
+    if (nc) {
+        switch (gm) {
+        case GM_IDENTITY: return meter ? span_tick<C, GM_IDENTITY, true, true> : span_tick<C, GM_IDENTITY, false, true>;
+        case GM_ADDALL:   return meter ? span_tick<C, GM_ADDALL, true, true> : span_tick<C, GM_ADDALL, false, true>;
+        default:          return meter ? span_tick<C, GM_MASKED, true, true> : span_tick<C, GM_MASKED, false, true>;
+        }
+    }
+    switch (gm) {
+    case GM_IDENTITY: return meter ? span_tick<C, GM_IDENTITY, true, false> : span_tick<C, GM_IDENTITY, false, false>;
+    case GM_ADDALL:   return meter ? span_tick<C, GM_ADDALL, true, false> : span_tick<C, GM_ADDALL, false, false>;
+    default:          return meter ? span_tick<C, GM_MASKED, true, false> : span_tick<C, GM_MASKED, false, false>;
+    }
+}
+TickKernel span_kernel(const cmgpu_ctx *c, int gm, bool meter)
+{
+    const bool nc = c->d_out != nullptr;
+    switch (c->channels) {
+    case 1:  return span_kernel_c<1>(gm, meter, nc);
+    case 2:  return span_kernel_c<2>(gm, meter, nc);
+    case 4:  return span_kernel_c<4>(gm, meter, nc);
+    default: return span_kernel_c<8>(gm, meter, nc);
+    }
+}
+
 using AnyKernel = void (*)(const TickArgs, const int, const int);
 
 AnyKernel any_kernel(int gm, bool meter, bool nc)
@@ -247,6 +276,23 @@ cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter, cud
         if (grid > (uint64_t)cap)
             grid = (uint64_t)cap;
         return launch_kernel(k, (unsigned)grid, cmgpu::kTmaThreads, cmgpu::kTmaSmemBytes, st, pdl, t);
+    }
+    // Small-buffer spans with enough streams to fill the machine with 8-lane groups: one group per STREAM
+    // walks all ticks of the span and publishes its meter partials once (cmgpu_span.cuh)
+    if (a.n_ticks > 1 && c->plan_g == 8 && c->channels <= 8 && !a.planar && a.n_ticks <= cmgpu::kSpanMaxTicks &&
+        !c->env_span_by_tick && (c->env_span_by_stream || (uint64_t)a.n_streams * 8u * 2u >= (uint64_t)c->num_sms * 1024u)) {
+        TickKernel k = span_kernel(c, gm, meter);
+        int &cap = c->span_grid_cap[gm][meter ? 1 : 0];
+        if (!cap) {
+            int n = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, 256, 0) != cudaSuccess || n < 1)
+                n = 1;
+            cap = n * c->num_sms;
+        }
+        uint64_t grid = ((uint64_t)a.n_streams + 31u) / 32u;
+        if (grid > (uint64_t)cap)
+            grid = (uint64_t)cap;
+        return launch_kernel(k, (unsigned)grid, 256, 0, st, pdl, a);
     }
     const uint64_t items = (uint64_t)a.n_streams * a.items_per_block * (a.n_ticks > 1 ? a.n_ticks : 1u);
     const uint64_t per_cta = c->plan_g > 0 ? 256u / (unsigned)c->plan_g : (c->plan_g < 0 ? 8u : 4u);
@@ -414,6 +460,22 @@ int rebuild_classes_locked(cmgpu_ctx *c)
 
 int flush_ticks_locked(cmgpu_ctx *c);
 
+#ifdef CMGPU_BOUNDS_CHECK
+int debug_set_bounds(cmgpu_ctx *c, cudaStream_t st)
+{
+    cmgpu::DebugBounds b;
+    const size_t ring = c->slot_bytes * c->slots;
+    const size_t ring_out = c->out_channels ? c->slot_bytes_out * c->slots : ring;
+    b.lo[0] = (unsigned long long)c->d_in;
+    b.hi[0] = b.lo[0] + ring;
+    b.lo[1] = (unsigned long long)(c->d_out ? c->d_out : c->d_in);
+    b.hi[1] = b.lo[1] + (c->d_out ? ring_out : ring);
+    // pageable source: staged by the runtime before the call returns
+    CU(cudaMemcpyToSymbolAsync(cmgpu::g_dbg_bounds, &b, sizeof(b), 0, cudaMemcpyHostToDevice, st));
+    return CMGPU_OK;
+}
+#endif
+
 // One tick on stream `st`. In a cycle (cmgpu_process_cycle) the ticks run concurrently: each gets
 // its place in the sequence as `tick_offset` and leaves advancing the counter to the cycle's end.
 // n_ticks > 1: a span -- ONE launch over the consecutive slots [slot, slot + n_ticks) (span_ok() says when).
@@ -482,6 +544,10 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
         const bool mpdl = !captured && st == c->s_cmp && c->chain_open && c->last_first != ~0u && !c->env_no_pdl;
         if (!captured && st == c->s_cmp)
             c->chain_open = true;
+#ifdef CMGPU_BOUNDS_CHECK
+        if (int brc = debug_set_bounds(c, st))
+            return brc;
+#endif
         if (vec8)
             CU(launch_kernel(cmgpu::mix8to2_tick, (unsigned)grid, 256, 0, st, mpdl, m));
         else
@@ -553,14 +619,27 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
             c->in_chain[i] = 1;
         c->chain_open = true;
     }
-    // A launch that does not overlap its predecessor hands its work items out dynamically (TickArgs::work):
-    // plain ticks of the warp-per-item kernels on the compute stream. Spans, captured cycles (their
-    // ticks run side by side on forked streams) and overlapping launches keep the static order.
+    // Plain ticks of the warp-per-item kernels claim their work items dynamically (TickArgs::work). Every
+    // launch takes the next of kWorkCounters counters, so launches that overlap never share one: with a
+    // grid of at least a quarter of the resident CTAs no more than five launches fit on the GPU at once
+    // (a launch cannot finish before its predecessor has). Smaller grids, spans, captured cycles (their
+    // ticks run side by side on forked streams and are replayed with the same arguments) stay static.
     a.work = nullptr;
-    if (!pdl && !captured && st == c->s_cmp && n_ticks <= 1 && c->plan_g == 32 && !c->tma && !c->env_static) {
-        CU(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned int), st));
-        a.work = c->d_work;
+    a.work_base = 0;
+    if (!captured && st == c->s_cmp && n_ticks <= 1 && c->plan_g == 32 && !c->tma && !c->env_static) {
+        const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block;
+        const uint64_t cap = (uint64_t)resident_ctas(c, gm, meter);
+        if (n_items >= 8u * cap / 4u || !pdl) {
+            const unsigned k = c->work_next++ % cmgpu_ctx::kWorkCounters;
+            a.work = c->d_work + k;
+            a.work_base = c->work_base[k];
+            c->work_base[k] += (uint32_t)n_items;          // one claim per processed item (mod 2^32, like the counter)
+        }
     }
+#ifdef CMGPU_BOUNDS_CHECK
+    if (int brc = debug_set_bounds(c, st))
+        return brc;
+#endif
     CU(launch_tick(c, a, gm, meter, st, pdl));
     c->launches++;
     if (!captured) {
@@ -672,7 +751,9 @@ static cmgpu_ctx_t *ctx_create_impl(int device, unsigned channels, unsigned out_
     c->device = device;
     c->env_no_pdl = getenv("CMGPU_NO_PDL") != nullptr;
     c->env_no_span = getenv("CMGPU_NO_SPAN") != nullptr;
-    c->env_static = getenv("CMGPU_STATIC_ITEMS") != nullptr;       // A/B hook: never claim work items dynamically
+    c->env_static = getenv("CMGPU_STATIC_ITEMS") != nullptr;
+    c->env_span_by_tick = getenv("CMGPU_SPAN_BY_TICK") != nullptr;    // A/B hook: spans as (tick, stream) work items
+    c->env_span_by_stream = getenv("CMGPU_SPAN_BY_STREAM") != nullptr;    // test hook: stream-major spans for any stream count
     c->channels = channels;
     c->max_streams = c->active = max_streams;
     c->slots = ring_slots;
@@ -756,8 +837,9 @@ static cmgpu_ctx_t *ctx_create_impl(int device, unsigned channels, unsigned out_
         return bail("cudaMalloc(tick)", e);
     if ((e = cudaMalloc(&c->d_frames, sizeof(uint32_t) * (size_t)max_streams * ring_slots)) != cudaSuccess)
         return bail("cudaMalloc(frames)", e);
-    if ((e = cudaMalloc(&c->d_work, sizeof(unsigned int))) != cudaSuccess)
-        return bail("cudaMalloc(work counter)", e);
+    if ((e = cudaMalloc(&c->d_work, sizeof(unsigned int) * cmgpu_ctx::kWorkCounters)) != cudaSuccess ||
+        (e = cudaMemset(c->d_work, 0, sizeof(unsigned int) * cmgpu_ctx::kWorkCounters)) != cudaSuccess)
+        return bail("cudaMalloc(work counters)", e);
     if ((e = cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->s_cmp, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking)) != cudaSuccess)
@@ -1091,6 +1173,18 @@ int cmgpu_fetch_planar(cmgpu_ctx_t *c, unsigned slot, float *host)
     return CMGPU_OK;
 }
 
+int cmgpu_debug_violations(void)
+{
+#ifdef CMGPU_BOUNDS_CHECK
+    unsigned int n = 0;
+    if (cudaMemcpyFromSymbol(&n, cmgpu::g_dbg_violations, sizeof(n)) != cudaSuccess)
+        return -1;
+    return (int)(n > 0x7fffffffu ? 0x7fffffffu : n);
+#else
+    return -1;          // not a bounds-checking build
+#endif
+}
+
 int cmgpu_sync(cmgpu_ctx_t *c)
 {
     if (!c)
@@ -1099,6 +1193,10 @@ int cmgpu_sync(cmgpu_ctx_t *c)
     CU(cudaStreamSynchronize(c->s_up));
     CU(cudaStreamSynchronize(c->s_cmp));
     CU(cudaStreamSynchronize(c->s_down));
+#ifdef CMGPU_BOUNDS_CHECK
+    if (const int n = cmgpu_debug_violations())
+        return fail(CMGPU_ERR_GENERIC, "bounds check: %d PCM vector accesses outside the context's rings", n);
+#endif
     return CMGPU_OK;
 }
 

@@ -52,8 +52,13 @@ struct cmgpu_ctx {
     uint64_t launches = 0;
     int num_sms = 0;
     // environment hooks, read ONCE at cmgpu_ctx_create (never on the launch path)
-    bool env_no_pdl = false, env_no_span = false, env_static = false;
-    unsigned int *d_work = nullptr;                // work-claim counter of non-overlapping launches (TickArgs::work)
+    bool env_no_pdl = false, env_no_span = false, env_static = false, env_span_by_tick = false, env_span_by_stream = false;
+    // work-claim counters (TickArgs::work): launch number n uses counter n % kWorkCounters; each only grows,
+    // work_base[] is its value when the next launch that uses it starts (host arithmetic, no resets)
+    static constexpr unsigned kWorkCounters = 8;
+    unsigned int *d_work = nullptr;
+    uint32_t work_base[kWorkCounters] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned work_next = 0;
 
     uint8_t *d_in = nullptr, *d_out = nullptr;     // rings
     uint8_t *h_ring = nullptr;                     // pinned staging ring
@@ -132,6 +137,7 @@ struct cmgpu_ctx {
     int tma_grid_cap[3][2] = {{0, 0}, {0, 0}, {0, 0}};
     uint32_t plan_items = 1, plan_per_item = 0;
     int grid_cap[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // resident CTAs per (gain mode, meter) kernel
+    int span_grid_cap[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // ... of the stream-major span kernel
     char kname[64] = "";
 };
 

@@ -57,9 +57,33 @@ namespace cmgpu {
 // Written as volatile asm with a memory clobber on purpose: where the compiler is free to move
 // them it sinks a batch of loads down to its first use (seen in SASS), which throws away the
 // prefetch distance the kernels are built around and costs up to 8 %.
+#ifdef CMGPU_BOUNDS_CHECK
+// Debug build (make debug -> libcoolmic_b200_dbg.so; compute-sanitizer is not available on every pool):
+// every PCM vector access is checked against the extents of the launching context's rings. A stray
+// access is counted and dropped; cmgpu_sync / cmgpu_debug_violations report the count.
+struct DebugBounds {
+    unsigned long long lo[2], hi[2];
+};
+__device__ DebugBounds g_dbg_bounds;
+__device__ unsigned int g_dbg_violations;
+__device__ __forceinline__ bool dbg_ok(const void *p)
+{
+    const unsigned long long a = (unsigned long long)p;
+    const bool ok = ((a & 15ull) == 0) && ((a >= g_dbg_bounds.lo[0] && a + 16 <= g_dbg_bounds.hi[0]) ||
+                                           (a >= g_dbg_bounds.lo[1] && a + 16 <= g_dbg_bounds.hi[1]));
+    if (!ok)
+        atomicAdd(&g_dbg_violations, 1u);
+    return ok;
+}
+#endif
+
 __device__ __forceinline__ uint4 ld_stream(const uint8_t *p, bool nc = false)
 {
     uint4 v;
+#ifdef CMGPU_BOUNDS_CHECK
+    if (!dbg_ok(p))
+        return make_uint4(0, 0, 0, 0);
+#endif
     if (nc)
         asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     else
@@ -68,6 +92,10 @@ __device__ __forceinline__ uint4 ld_stream(const uint8_t *p, bool nc = false)
 }
 __device__ __forceinline__ void st_stream(uint8_t *p, uint4 v)
 {
+#ifdef CMGPU_BOUNDS_CHECK
+    if (!dbg_ok(p))
+        return;
+#endif
 #if CMGPU_ST_HINT == 0
     asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 #else
@@ -634,7 +662,7 @@ __global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __
 
         // next item: recipes and first batch go out before this item's epilogue
         if (G != 8 && a.work != nullptr)
-            item = stride + __shfl_sync(0xffffffffu, claimed, 0);      // the first `stride` items were dealt out statically
+            item = stride + (uint32_t)(__shfl_sync(0xffffffffu, claimed, 0) - a.work_base);   // the first `stride` items were dealt out statically
         else
             item += stride;
         Item nxt;

@@ -63,13 +63,16 @@ struct TickArgs {
     uint32_t frames_stride;
     uint64_t slot_bytes;
     // Work distribution (fused_tick, 32-lane groups). nullptr: static -- group g takes items g, g + n,
-    // g + 2n, ... (n = groups of the grid). Otherwise a zeroed counter: the first n items are dealt out
-    // statically, every further one is claimed with an atomicAdd when a group starts on its current
-    // item, so that SMs that run a little faster simply take more items and the launch has no long tail
-    // of stragglers. Launches that overlap the previous one (programmatic dependent launch) keep the
-    // static order: their tail is hidden by the next launch's head, and a counter would have to be
-    // private to each launch in flight.
+    // g + 2n, ... (n = groups of the grid). Otherwise a counter that only ever grows: the first n items
+    // are dealt out statically, every further one is claimed with an atomicAdd when a group starts on
+    // its current item (claimed number = stride + counter value - work_base), so SMs that run a little
+    // faster simply take more items and the launch has no tail of stragglers -- measured on config 5,
+    // one slot in place: 4.38 -> 3.87 ms, 0.88 -> 0.99 of the copy rate. Every processed item makes
+    // exactly one claim, so a launch advances the counter by its item count and the host knows the
+    // next launch's base without ever resetting anything (no memset between launches: ticks stay bare
+    // kernel launches and may overlap). Launches that may be in flight together use different counters.
     unsigned int *work;
+    uint32_t work_base;
 };
 
 // Per-stream mix recipe (device table row).

@@ -91,6 +91,8 @@ def main():
     finally:
         eng.close()
         comm.close()
+    if not ok:
+        print(f"gather_worker rank {rank}: {detail}", flush=True)
     if rank == 0:
         Path(out_path).write_text(json.dumps({"ok": ok, "detail": detail, "ranks": nranks, "total_streams": total,
                                               "streams_checked": total if ok else 0,

@@ -535,6 +535,66 @@ def test_cycle_equals_individual_ticks(cm, port, monkeypatch, channels, block, r
     assert all(results[0][1][s]["channel_peak"][0] == 100 for s in range(7))
 
 
+@pytest.mark.parametrize("channels,block,ragged,ring,separate", [
+    (1, 320, False, 5, False), (1, 320, True, 7, False), (1, 320, False, 50, True), (2, 256, True, 4, True), (2, 255, False, 3, False),
+    (4, 128, True, 6, False), (8, 64, True, 5, True), (1, 512, True, 2, False), (1, 5, True, 9, False), (2, 1, False, 4, False)])
+def test_stream_major_span(cm, port, monkeypatch, channels, block, ragged, ring, separate):
+    """The small-buffer span kernel (cmgpu_span.cuh): one 8-lane group owns a STREAM for all ticks of a
+    span and publishes its meter partials once. Forced here for small stream counts
+    (CMGPU_SPAN_BY_STREAM); equal peaks in different ticks and ragged frame counts included. Must equal
+    the oracle run over the ticks in order, for two consecutive spans (the second continues the window)."""
+    monkeypatch.setenv("CMGPU_SPAN_BY_STREAM", "1")
+    rng = np.random.default_rng(500 + channels * 31 + block + ring)
+    n_streams, cycles = 203, 2
+    data = make_pcm(rng, "ties", (ring, n_streams, block * channels))
+    data[:, :5, :] = 0
+    data[1, :5, 0] = 77                       # first occurrence in tick 1 ...
+    data[2:, :5, 0] = -77                     # ... repeated with the other sign later
+    scale, gain = make_gains(rng, n_streams, channels)
+    frames = np.full((ring, n_streams), block, np.uint32)
+    if ragged:
+        frames = rng.integers(0, block + 1, size=(ring, n_streams)).astype(np.uint32)
+        frames[:, :5] = block
+    flags = cm.SEPARATE_OUT if separate else 0
+    with cm.Engine(channels, n_streams, block, ring_slots=ring, flags=flags) as eng:
+        eng.set_gain_table(scale, gain)
+        for slot in range(ring):
+            eng.host_slot(slot)[:, : block * channels] = data[slot]
+            if ragged:
+                eng.set_frames(slot, frames[slot])
+            eng.submit(slot)
+        for _ in range(cycles):
+            eng.process_cycle(0, ring)
+        assert eng.launch_count() == cycles
+        for slot in range(ring):
+            eng.fetch(slot)
+        eng.sync()
+        outs = [eng.host_slot(slot)[:, : block * channels].copy() for slot in range(ring)]
+        snap = eng.snapshot()
+    meters = None
+    work = data.copy()
+    last = None
+    for _ in range(cycles):
+        src = data.copy() if separate else work           # a separate output ring leaves the input pristine
+        for slot in range(ring):
+            meters, _ = port.batch(src[slot], frames[slot], channels, scale, gain, meters=meters)
+        last = src
+        work = src
+    for slot in range(ring):
+        for s in range(n_streams):
+            n = int(frames[slot][s]) * channels
+            if separate:
+                assert np.array_equal(outs[slot][s, :n], last[slot][s, :n]), f"slot {slot} stream {s}"
+            else:
+                assert np.array_equal(outs[slot][s], last[slot][s]), f"slot {slot} stream {s}"
+    for s in range(n_streams):
+        assert int(snap[s].frames) == int(meters[s].frames), f"stream {s}"
+        for c in range(channels):
+            assert int(snap[s].power[c]) == int(meters[s].power[c]), f"stream {s} ch {c}"
+            assert int(snap[s].channel_peak[c]) == int(meters[s].channel_peak[c]), f"stream {s} ch {c}"
+        assert int(snap[s].global_peak) == int(meters[s].global_peak), f"stream {s}"
+
+
 @pytest.mark.parametrize("channels,block", [(1, 320), (2, 1000), (2, 4799), (4, 333), (8, 257), (16, 100), (6, 500), (3, 77)])
 def test_planar_float_second_output(cm, port, channels, block):
     """the encoder-side sample-format stage (enc_vorbis.c:108-117: de-interleave,
