@@ -69,6 +69,10 @@ WORKLOADS = {
                   desc="EXTENSION, PARITY UNPINNED (the reference has no downmix): 4,096 x 48 kHz 8-channel streams x 2 s "
                        "per GPU, 8->2 integer downmix + metering of the 8 input and 2 output channels; 16 B read + 4 B "
                        "written per frame; checked against our own CPU restatement only"),
+    "cfg4c": dict(channels=8, streams=4096, rate=48000, frames=96000, ticks=1, ring=1, graph=False,
+                  e2e_frames=9600, e2e_ticks=10, mix_out=2, bytes_per_sample=2.5, sstep=7, cstep=5, out_meter_only=True,
+                  desc="EXTENSION, PARITY UNPINNED: cfg4b with only the 2 OUTPUT channels metered "
+                       "(CMGPU_MIX_OUTPUT_METER_ONLY), not the 8 inputs"),
     "cfg2p": dict(channels=2, streams=1024, rate=48000, frames=240000, ticks=1, ring=1, graph=False, planar=True,
                   bytes_per_sample=8.0, e2e_frames=12000, e2e_ticks=20, sstep=7, cstep=3,
                   desc="DIAGNOSTIC (SURVEY 8f N2): cfg2 x 5 s with the float-plane second output (S16 -> planar float "
@@ -346,6 +350,7 @@ def main():
     # ---- device-resident run: the step's ticks live in a ring of `ring` slots, out of place so
     #      that the input stays pristine across steps
     mix_out = wl.get("mix_out", 0)
+    mix_flags = cm.MIX_OUTPUT_METER_ONLY if wl.get("out_meter_only") else 0
     planar = bool(wl.get("planar"))
     bytes_per_sample = wl.get("bytes_per_sample", 4.0)
 
@@ -358,7 +363,7 @@ def main():
             e.set_gain_table(scale, gain)
 
     eng = cm.Engine(channels, streams_per_gpu, frames, ring_slots=ring, device=local,
-                    flags=cm.NO_PINNED | (0 if mix_out else cm.SEPARATE_OUT) | (cm.PLANAR_F32 if planar else 0),
+                    flags=cm.NO_PINNED | (0 if mix_out else cm.SEPARATE_OUT) | (cm.PLANAR_F32 if planar else 0) | mix_flags,
                     out_channels=mix_out)
     configure(eng)
     eng.tone_table(period)
@@ -498,7 +503,7 @@ def main():
         if stage is not None:
             stage.free()
 
-        eng = cm.Engine(channels, streams_per_gpu, tick_frames, ring_slots=4, device=local, flags=cm.NO_PINNED,
+        eng = cm.Engine(channels, streams_per_gpu, tick_frames, ring_slots=4, device=local, flags=cm.NO_PINNED | mix_flags,
                         out_channels=mix_out)
         configure(eng)
         pin_out = cm.PinnedArray((n_ticks, streams_per_gpu, eng.out_stride // 2))

@@ -49,6 +49,7 @@ extern "C" {
 #define CMGPU_NO_PINNED      0x2u  /* do not allocate the pinned host staging rings */
 #define CMGPU_FORCE_GENERIC  0x4u  /* always use the any-channel-count kernel (test hook) */
 #define CMGPU_PLANAR_F32     0x8u  /* also keep a ring of de-interleaved float planes (see CMGPU_PLANAR) */
+#define CMGPU_MIX_OUTPUT_METER_ONLY 0x10u /* downmix contexts (extension): meter the outputs only, not the inputs */
 
 /* cmgpu_process flags */
 #define CMGPU_TRANSFORM      0x1u  /* apply the gain tables (else pass PCM through untouched) */

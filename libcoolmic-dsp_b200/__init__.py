@@ -10,6 +10,6 @@ The directory name carries a hyphen (it mirrors the reference's name), so import
 """
 from .binding import (  # noqa: F401
     LIB_PATH, Engine, CmgpuError, MeterState, Result, lib, build_library,
-    PinnedArray, state_dict, Comm, Colors, RESULTS_DEVICE_DB, link_probe, FUSED, TRANSFORM, METER, SEPARATE_OUT, NO_PINNED, FORCE_GENERIC, PLANAR_F32, PLANAR,
+    PinnedArray, state_dict, Comm, Colors, RESULTS_DEVICE_DB, link_probe, FUSED, TRANSFORM, METER, SEPARATE_OUT, NO_PINNED, FORCE_GENERIC, PLANAR_F32, PLANAR, MIX_OUTPUT_METER_ONLY,
 )
 from . import sharding  # noqa: F401,E402

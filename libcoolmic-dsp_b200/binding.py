@@ -13,7 +13,7 @@ import os
 LIB_PATH = Path(os.environ.get("CMGPU_LIB", PKG / "lib" / "libcoolmic_b200.so"))
 MAX_CH = 16
 
-SEPARATE_OUT, NO_PINNED, FORCE_GENERIC, PLANAR_F32 = 0x1, 0x2, 0x4, 0x8
+SEPARATE_OUT, NO_PINNED, FORCE_GENERIC, PLANAR_F32, MIX_OUTPUT_METER_ONLY = 0x1, 0x2, 0x4, 0x8, 0x10
 TRANSFORM, METER, PLANAR = 0x1, 0x2, 0x4
 FUSED = TRANSFORM | METER
 

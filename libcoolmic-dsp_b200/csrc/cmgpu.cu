@@ -161,8 +161,10 @@ TickKernel tma_kernel(const cmgpu_ctx *c, int gm, bool meter)
     }
 }
 
+using SpanKernel = void (*)(const TickArgs, const uint32_t);
+
 template <int C>
-TickKernel span_kernel_c(int gm, bool meter, bool nc)
+SpanKernel span_kernel_c(int gm, bool meter, bool nc)
 {
     using namespace cmgpu;
     if (nc) {
@@ -178,7 +180,7 @@ TickKernel span_kernel_c(int gm, bool meter, bool nc)
     default:          return meter ? span_tick<C, GM_MASKED, true, false> : span_tick<C, GM_MASKED, false, false>;
     }
 }
-TickKernel span_kernel(const cmgpu_ctx *c, int gm, bool meter)
+SpanKernel span_kernel(const cmgpu_ctx *c, int gm, bool meter)
 {
     const bool nc = c->d_out != nullptr;
     switch (c->channels) {
@@ -281,18 +283,23 @@ cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter, cud
     // walks all ticks of the span and publishes its meter partials once (cmgpu_span.cuh)
     if (a.n_ticks > 1 && c->plan_g == 8 && c->channels <= 8 && !a.planar && a.n_ticks <= cmgpu::kSpanMaxTicks &&
         !c->env_span_by_tick && (c->env_span_by_stream || (uint64_t)a.n_streams * 8u * 2u >= (uint64_t)c->num_sms * 1024u)) {
-        TickKernel k = span_kernel(c, gm, meter);
+        SpanKernel k = span_kernel(c, gm, meter);
+        const uint32_t vmax = (uint32_t)((c->stride / 16 + 7) / 8);          // vectors of a stream-block per lane, <= 8
+        const size_t smem = (size_t)2 * vmax * 256 * 16;
         int &cap = c->span_grid_cap[gm][meter ? 1 : 0];
         if (!cap) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess)
+                return e;
             int n = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, 256, 0) != cudaSuccess || n < 1)
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, 256, smem) != cudaSuccess || n < 1)
                 n = 1;
             cap = n * c->num_sms;
         }
         uint64_t grid = ((uint64_t)a.n_streams + 31u) / 32u;
         if (grid > (uint64_t)cap)
             grid = (uint64_t)cap;
-        return launch_kernel(k, (unsigned)grid, 256, 0, st, pdl, a);
+        return launch_kernel(k, (unsigned)grid, 256, smem, st, pdl, a, vmax);
     }
     const uint64_t items = (uint64_t)a.n_streams * a.items_per_block * (a.n_ticks > 1 ? a.n_ticks : 1u);
     const uint64_t per_cta = c->plan_g > 0 ? 256u / (unsigned)c->plan_g : (c->plan_g < 0 ? 8u : 4u);
@@ -320,7 +327,11 @@ void make_plan(cmgpu_ctx *c)
         const unsigned lanes = 32 - 32 % m;
         const uint32_t nvec = (uint32_t)(c->stride / 16);
         const uint32_t quantum = lanes * 8u;                      // two batches of 4 per lane
-        const uint32_t target = 2048;
+        uint32_t target = 2048;
+        if (const char *e = getenv("CMGPU_ITEM_VECS"))            // tuning hook
+            target = (uint32_t)strtoul(e, nullptr, 10) ? (uint32_t)strtoul(e, nullptr, 10) : target;
+        if (target > 8192)                                        // the epilogue's sample index (vector * 8 + slot) fits 16 bits
+            target = 8192 - quantum;
         uint32_t items = (nvec + target - 1) / target;
         uint32_t per = (nvec + items - 1) / items;
         per = (per + quantum - 1) / quantum * quantum;
@@ -460,6 +471,27 @@ int rebuild_classes_locked(cmgpu_ctx *c)
 
 int flush_ticks_locked(cmgpu_ctx *c);
 
+// Dynamic work claims (TickArgs::work) for a launch of `n_items` warp-sized items on a grid of `grid`
+// CTAs out of `cap` resident ones. Every launch takes the next of kWorkCounters counters, so launches
+// that overlap never share one: with a grid of at least a quarter of the resident CTAs no more than five
+// launches fit on the GPU at once (a launch cannot finish before its predecessor has). Smaller
+// overlapping grids, spans, captured cycles (their ticks run side by side on forked streams and are
+// replayed with the same arguments) stay static.
+void assign_work(cmgpu_ctx *c, bool pdl, bool captured, cudaStream_t st, uint64_t n_items, uint64_t grid, uint64_t cap,
+                 unsigned int **work, uint32_t *base)
+{
+    *work = nullptr;
+    *base = 0;
+    if (captured || st != c->s_cmp || c->env_static || n_items >= 0xffffffffull)
+        return;
+    if (pdl && grid * 4u < cap)
+        return;
+    const unsigned k = c->work_next++ % cmgpu_ctx::kWorkCounters;
+    *work = c->d_work + k;
+    *base = c->work_base[k];
+    c->work_base[k] += (uint32_t)n_items;              // one claim per processed item (mod 2^32, like the counter)
+}
+
 #ifdef CMGPU_BOUNDS_CHECK
 int debug_set_bounds(cmgpu_ctx *c, cudaStream_t st)
 {
@@ -534,7 +566,9 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
         const unsigned per_cta = vec8 ? 8 : 4;
         uint64_t grid = (n_items + per_cta - 1) / per_cta;
         int occ = 0;
-        if ((vec8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cmgpu::mix8to2_tick, 256, 0)
+        const bool in_meter = !(c->flags & CMGPU_MIX_OUTPUT_METER_ONLY);
+        if ((vec8 ? (in_meter ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cmgpu::mix8to2_tick<true>, 256, 0)
+                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cmgpu::mix8to2_tick<false>, 256, 0))
                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cmgpu::mix_tick<false>, 128, 0)) != cudaSuccess ||
             occ < 1)
             occ = 1;
@@ -545,11 +579,15 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
         if (!captured && st == c->s_cmp)
             c->chain_open = true;
 #ifdef CMGPU_BOUNDS_CHECK
-        if (int brc = debug_set_bounds(c, st))
-            return brc;
+        if (!captured)
+            if (int brc = debug_set_bounds(c, st))
+                return brc;
 #endif
-        if (vec8)
-            CU(launch_kernel(cmgpu::mix8to2_tick, (unsigned)grid, 256, 0, st, mpdl, m));
+        assign_work(c, mpdl, captured, st, n_items, grid, (uint64_t)occ * c->num_sms, &m.work, &m.work_base);
+        if (vec8 && in_meter)
+            CU(launch_kernel(cmgpu::mix8to2_tick<true>, (unsigned)grid, 256, 0, st, mpdl, m));
+        else if (vec8)
+            CU(launch_kernel(cmgpu::mix8to2_tick<false>, (unsigned)grid, 256, 0, st, mpdl, m));
         else
             CU(launch_kernel(cmgpu::mix_tick<false>, (unsigned)grid, 128, 0, st, mpdl, m));
         c->launches++;
@@ -619,26 +657,20 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
             c->in_chain[i] = 1;
         c->chain_open = true;
     }
-    // Plain ticks of the warp-per-item kernels claim their work items dynamically (TickArgs::work). Every
-    // launch takes the next of kWorkCounters counters, so launches that overlap never share one: with a
-    // grid of at least a quarter of the resident CTAs no more than five launches fit on the GPU at once
-    // (a launch cannot finish before its predecessor has). Smaller grids, spans, captured cycles (their
-    // ticks run side by side on forked streams and are replayed with the same arguments) stay static.
+    // plain ticks of the warp-per-item kernels claim their work items dynamically (assign_work)
     a.work = nullptr;
     a.work_base = 0;
-    if (!captured && st == c->s_cmp && n_ticks <= 1 && c->plan_g == 32 && !c->tma && !c->env_static) {
+    if (n_ticks <= 1 && c->plan_g != 8 && !c->tma) {
         const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block;
+        const uint64_t per_cta = c->plan_g == 0 ? 4u : 8u;
         const uint64_t cap = (uint64_t)resident_ctas(c, gm, meter);
-        if (n_items >= 8u * cap / 4u || !pdl) {
-            const unsigned k = c->work_next++ % cmgpu_ctx::kWorkCounters;
-            a.work = c->d_work + k;
-            a.work_base = c->work_base[k];
-            c->work_base[k] += (uint32_t)n_items;          // one claim per processed item (mod 2^32, like the counter)
-        }
+        const uint64_t grid = std::min<uint64_t>((n_items + per_cta - 1) / per_cta, cap);
+        assign_work(c, pdl, captured, st, n_items, grid, cap, &a.work, &a.work_base);
     }
 #ifdef CMGPU_BOUNDS_CHECK
-    if (int brc = debug_set_bounds(c, st))
-        return brc;
+    if (!captured)                      // (a captured copy from host memory would be replayed from a dead stack frame)
+        if (int brc = debug_set_bounds(c, st))
+            return brc;
 #endif
     CU(launch_tick(c, a, gm, meter, st, pdl));
     c->launches++;
@@ -951,7 +983,9 @@ const char *cmgpu_kernel_name(const cmgpu_ctx_t *c)
     if (!c)
         return "";
     if (c->out_channels)
-        return (c->channels == 8 && c->out_channels == 2 && !(c->flags & CMGPU_FORCE_GENERIC)) ? "mix8to2_tick" : "mix_tick<generic>";
+        return (c->channels == 8 && c->out_channels == 2 && !(c->flags & CMGPU_FORCE_GENERIC))
+                   ? ((c->flags & CMGPU_MIX_OUTPUT_METER_ONLY) ? "mix8to2_tick<outputs metered>" : "mix8to2_tick")
+                   : "mix_tick<generic>";
     return c->kname;
 }
 unsigned cmgpu_meter_row_u64(const cmgpu_ctx_t *c) { return c ? c->row_u64 : 0; }
@@ -1495,6 +1529,10 @@ int cmgpu_process_cycle(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, u
     } else {
         if ((rc = flush_ticks_locked(c)))
             return rc;
+#ifdef CMGPU_BOUNDS_CHECK
+        if ((rc = debug_set_bounds(c, c->s_cmp)))
+            return rc;
+#endif
         CU(cudaGraphLaunch(c->graph, c->s_cmp));
         c->launches += c->graph_launches;
     }
@@ -1528,6 +1566,10 @@ int cmgpu_time_cycles(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, uns
         } else {
             if ((rc = flush_ticks_locked(c)))
                 return rc;
+#ifdef CMGPU_BOUNDS_CHECK
+            if ((rc = debug_set_bounds(c, c->s_cmp)))
+                return rc;
+#endif
             CU(cudaGraphLaunch(c->graph, c->s_cmp));
             c->launches += c->graph_launches;
         }

@@ -148,6 +148,21 @@ __device__ __forceinline__ void launch_begin() { asm volatile("griddepcontrol.la
 __device__ __forceinline__ void launch_end() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tick_end(const TickArgs &) { launch_end(); }
 
+// Work distribution of the warp-per-item loops (TickArgs::work): the item after `item` for this warp --
+// item + stride in the static order, or stride + (the number this warp claimed when it started on
+// `item`). `claimed` is valid in lane 0.
+__device__ __forceinline__ uint64_t next_item(uint64_t item, uint64_t stride, const unsigned int *work, uint32_t work_base,
+                                              uint32_t claimed)
+{
+    if (work != nullptr)
+        return stride + (uint32_t)(__shfl_sync(0xffffffffu, claimed, 0) - work_base);
+    return item + stride;
+}
+__device__ __forceinline__ uint32_t claim_item(unsigned int *work, uint32_t lane)
+{
+    return (work != nullptr && lane == 0) ? atomicAdd(work, 1u) : 0u;
+}
+
 // One sample through the gain recipe (see GainRow).
 struct Recipe {
     int mw;
@@ -740,7 +755,10 @@ __global__ void __launch_bounds__(256, 2) any_tick(const __grid_constant__ TickA
     const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block;
     const uint64_t stride = (uint64_t)gridDim.x * 8u;
 
-    for (uint64_t item = (uint64_t)blockIdx.x * 8u + (threadIdx.x >> 5); item < n_items; item += stride) {
+    uint32_t claimed = 0;
+    for (uint64_t item = (uint64_t)blockIdx.x * 8u + (threadIdx.x >> 5); item < n_items;
+         item = next_item(item, stride, a.work, a.work_base, claimed)) {
+        claimed = claim_item(a.work, lane);
         const uint32_t s = (uint32_t)(item / a.items_per_block);
         const uint32_t chunk = (uint32_t)(item - (uint64_t)s * a.items_per_block);
         const uint32_t nfr = a.frames ? min(__ldg(a.frames + s), a.block_frames) : a.block_frames;
@@ -999,7 +1017,10 @@ __global__ void __launch_bounds__(128) generic_tick(const __grid_constant__ Tick
     const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block;
     const uint64_t stride = (uint64_t)gridDim.x * warps_per_cta;
 
-    for (uint64_t item = (uint64_t)blockIdx.x * warps_per_cta + threadIdx.x / 32; item < n_items; item += stride) {
+    uint32_t claimed = 0;
+    for (uint64_t item = (uint64_t)blockIdx.x * warps_per_cta + threadIdx.x / 32; item < n_items;
+         item = next_item(item, stride, a.work, a.work_base, claimed)) {
+        claimed = claim_item(a.work, lane);
         const uint32_t si = (uint32_t)(item / a.items_per_block);
         const uint32_t chunk = (uint32_t)(item - (uint64_t)si * a.items_per_block);
         const uint32_t s = si;

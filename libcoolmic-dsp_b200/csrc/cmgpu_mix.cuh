@@ -88,7 +88,10 @@ __global__ void __launch_bounds__(128) mix_tick(const __grid_constant__ MixArgs 
     const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block;
     const uint64_t stride = (uint64_t)gridDim.x * 4u;
 
-    for (uint64_t item = (uint64_t)blockIdx.x * 4u + warp; item < n_items; item += stride) {
+    uint32_t claimed = 0;
+    for (uint64_t item = (uint64_t)blockIdx.x * 4u + (threadIdx.x >> 5); item < n_items;
+         item = next_item(item, stride, a.work, a.work_base, claimed)) {
+        claimed = claim_item(a.work, lane);
         const uint32_t s = (uint32_t)(item / a.items_per_block);
         const uint32_t chunk = (uint32_t)(item - (uint64_t)s * a.items_per_block);
         const uint32_t nfr = a.frames ? min(__ldg(a.frames + s), a.block_frames) : a.block_frames;
@@ -190,6 +193,9 @@ __device__ __forceinline__ int dp2a_hi_su(uint32_t a_s16x2, uint32_t b_u8x4, int
 // one 32-bit word per frame. The input side is metered by the 8-channel hot loop itself
 // (do_vector<8, identity>); the mix is 8 dp2a (signed 16-bit x unsigned 8-bit, weights split into
 // low and high bytes) + one 64-bit recombination per output instead of 8 half-rate IMAD.WIDE.
+// IN_METER false: the 8 input channels are not metered (cmgpu_mix_ctx_create flag CMGPU_MIX_OUTPUT_METER_ONLY):
+// half of the kernel's instructions, for callers that only want the levels of what they send on.
+template <bool IN_METER>
 __global__ void __launch_bounds__(256, 2) mix8to2_tick(const __grid_constant__ MixArgs a)
 {
     launch_begin();
@@ -209,7 +215,10 @@ __global__ void __launch_bounds__(256, 2) mix8to2_tick(const __grid_constant__ M
     ta.stride_bytes = a.stride_in;
     ta.row_u64 = 18;
 
-    for (uint64_t item = (uint64_t)blockIdx.x * 8u + (threadIdx.x >> 5); item < n_items; item += stride) {
+    uint32_t claimed = 0;
+    for (uint64_t item = (uint64_t)blockIdx.x * 8u + (threadIdx.x >> 5); item < n_items;
+         item = next_item(item, stride, a.work, a.work_base, claimed)) {
+        claimed = claim_item(a.work, lane);
         const uint32_t s = (uint32_t)(item / a.items_per_block);
         const uint32_t chunk = (uint32_t)(item - (uint64_t)s * a.items_per_block);
         const uint32_t nfr = a.frames ? min(__ldg(a.frames + s), a.block_frames) : a.block_frames;
@@ -238,7 +247,7 @@ __global__ void __launch_bounds__(256, 2) mix8to2_tick(const __grid_constant__ M
         it.src = a.in + (size_t)s * a.stride_in + (size_t)it.first * 16;
         it.tail_vec = it.tail_step = 0;
         it.tail_valid = 0;
-        it.count_frames = (chunk == 0 && lane == 0) ? nfr : 0;
+        it.count_frames = (IN_METER && chunk == 0 && lane == 0) ? nfr : 0;
         uint32_t *dst = reinterpret_cast<uint32_t *>(a.out + (size_t)s * a.stride_out) + it.first;
 
         Recipe none[8];
@@ -257,7 +266,8 @@ __global__ void __launch_bounds__(256, 2) mix8to2_tick(const __grid_constant__ M
 #define CMGPU_MIX_FRAME(vec_, iu)                                                             \
     {                                                                                       \
         const uint32_t radd = 0xffffu - (iu);                                               \
-        do_vector<8, GM_IDENTITY, true, false, false>(vec_, none, radd, kin, pin, 8);       \
+        if (IN_METER)                                                                       \
+            do_vector<8, GM_IDENTITY, true, false, false>(vec_, none, radd, kin, pin, 8);   \
         const uint32_t xw[4] = {(vec_).x, (vec_).y, (vec_).z, (vec_).w};                    \
         int r[2];                                                                           \
         _Pragma("unroll") for (int m = 0; m < 2; m++) {                                     \
@@ -306,7 +316,8 @@ __global__ void __launch_bounds__(256, 2) mix8to2_tick(const __grid_constant__ M
 #undef CMGPU_MIX_DO
 
         // input side: exactly the 8-channel epilogue (re-reads the sign from the input ring)
-        item_publish<8, 32>(ta, it, lane, 0xffffffffu, kin, pin);
+        if (IN_METER)
+            item_publish<8, 32>(ta, it, lane, 0xffffffffu, kin, pin);
         // output side: two channels, lane = frame
         const uint64_t pos_base = tick_pos_base(a.tick, a.tick_offset, a.pbits);
         __syncwarp();

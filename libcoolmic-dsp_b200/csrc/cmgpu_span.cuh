@@ -8,8 +8,8 @@
 //   * the meter partials (one merged peak key and one 64-bit power sum per channel of the lane) stay in
 //     registers across the ticks; ONE epilogue per stream and span publishes them -- the reference's
 //     meter window is many reads long anyway (vumeter.c:170-177 accumulates until result());
-//   * a lane's (at most 8) vectors of a tick sit in two half-buffers that are refilled with the NEXT
-//     tick's vectors as soon as they have been worked on, so every lane always has loads in flight.
+//   * a tick's vectors are staged through shared memory with cp.async, a whole tick ahead of the one
+//     being worked on (below), so every lane always has a full tick of loads in flight.
 // Per tick the arithmetic is fused_tick's (do_vector). Peak order: the in-loop key counts steps through
 // the whole span (tick * 8 + vector of the lane), the epilogue turns the winner into the 64-bit
 // position key of its tick, so "first occurrence" holds across ticks, launches and GPUs as before.
@@ -22,15 +22,30 @@ namespace cmgpu {
 
 constexpr uint32_t kSpanMaxTicks = 1024;      // (tick * 8 + step) * 8 + lane must fit 16 bits
 
+// Shared-memory staging of a tick's vectors (cp.async, 16 bytes per copy, L2 only): every lane copies
+// exactly the vectors it will work on into slots of its own, so no lane ever reads another's data and
+// the only synchronisation is the lane's own cp.async.wait_group. Two stages: while tick t is worked
+// on from stage t & 1, ALL of tick t + 1 is in flight into the other one. Measured on config 3
+// (profiles/r2_span_tick_cfg3_*): with the vectors held in two register half-buffers a lane had 1.6
+// vectors in flight on average and the launch ran at the rate Little's law gives for that (4.4 TB/s,
+// half the warp cycles on long_scoreboard); staged, a whole tick per lane is in flight all the time.
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gptr)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int C, int GM, bool METER, bool NC>
-__global__ void __launch_bounds__(256, Tune<C, 8>::kMinCtas) span_tick(const __grid_constant__ TickArgs a)
+__global__ void __launch_bounds__(256, Tune<C, 8>::kMinCtas) span_tick(const __grid_constant__ TickArgs a, const uint32_t vmax)
 {
     constexpr int G = 8;
     constexpr int P = Shape<C>::kPerLane;
-    constexpr int H = 4;                                  // vectors per half-buffer
     constexpr int S = (C <= 8) ? 8 / P : 1;               // frames per vector
     constexpr size_t kStep = (size_t)G * 16;
     static_assert(C <= 8, "16-channel frames span two lanes: they use the 32-lane kernels");
+    extern __shared__ uint4 span_stage[];                 // [2][vmax][256]: slot (stage, u) of thread tid
     launch_begin();
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gl = threadIdx.x & (G - 1);
@@ -38,6 +53,8 @@ __global__ void __launch_bounds__(256, Tune<C, 8>::kMinCtas) span_tick(const __g
     const uint32_t n_groups = gridDim.x * (256 / G);
     const ptrdiff_t out_delta = a.out - a.in;
     const uint32_t n_ticks = a.n_ticks ? a.n_ticks : 1u;
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(span_stage) + threadIdx.x * 16u;
+    const uint32_t stage_bytes = vmax * 256u * 16u;
 
     for (uint32_t s = blockIdx.x * (256 / G) + threadIdx.x / G; s < a.n_streams; s += n_groups) {
         Recipe rc[P];
@@ -66,58 +83,47 @@ __global__ void __launch_bounds__(256, Tune<C, 8>::kMinCtas) span_tick(const __g
         auto frames_of = [&](uint32_t t) -> uint32_t {
             return a.frames ? min(__ldg(a.frames + (size_t)t * a.frames_stride + s), a.block_frames) : a.block_frames;
         };
+        auto request = [&](const uint8_t *src_t, uint32_t n, uint32_t stage) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+#ifdef CMGPU_BOUNDS_CHECK
+                if ((uint32_t)u < n && !dbg_ok(src_t + (size_t)u * kStep))
+                    continue;
+#endif
+                if ((uint32_t)u < n)
+                    cp_async16(smem0 + stage * stage_bytes + (uint32_t)u * 4096u, src_t + (size_t)u * kStep);
+            }
+            cp_async_commit();                             // (an empty group when n == 0: the count stays uniform)
+        };
 
-        uint4 bufA[H], bufB[H];
         const uint8_t *src = a.in + (size_t)s * a.stride_bytes + (size_t)gl * 16;      // tick 0
         uint32_t nfr = frames_of(0);
         uint32_t nfr_next = n_ticks > 1 ? frames_of(1) : 0u;
         uint32_t n_i, tail_vec;
         int tail_valid;
         shape(nfr, n_i, tail_vec, tail_valid);
-#pragma unroll
-        for (int u = 0; u < H; u++) {
-            if ((uint32_t)u < n_i)
-                bufA[u] = ld_stream(src + (size_t)u * kStep, NC);
-            if ((uint32_t)(H + u) < n_i)
-                bufB[u] = ld_stream(src + (size_t)(H + u) * kStep, NC);
-        }
+        request(src, n_i, 0u);
         for (uint32_t t = 0; t < n_ticks; t++) {
             uint8_t *const dstp = const_cast<uint8_t *>(src) + out_delta;
             const uint32_t radd0 = 0xffffu - t * 8u;
-            // the next tick, so that each half-buffer can be refilled as soon as it is free
+            const uint32_t stage = t & 1u;
+            // all of the next tick goes out before this one is worked on
             const uint8_t *src_n = src + a.slot_bytes;
             uint32_t n_n = 0, tail_vec_n = 0;
             int tail_valid_n = 0;
-            const bool more = t + 1 < n_ticks;
-            if (more)
+            if (t + 1 < n_ticks)
                 shape(nfr_next, n_n, tail_vec_n, tail_valid_n);
+            request(src_n, n_n, stage ^ 1u);
+            cp_async_wait<1>();                            // this tick's copies have landed (the next tick's may be in flight)
+            const uint4 *mine = span_stage + (size_t)stage * vmax * 256u + threadIdx.x;
 #pragma unroll
-            for (int u = 0; u < H; u++) {
+            for (int u = 0; u < 8; u++) {
                 if ((uint32_t)u < n_i) {
-                    const uint4 o = do_vector<C, GM, METER, false, true, false, true>(bufA[u], rc, radd0 - (uint32_t)u, kmax, pacc, 8);
+                    const uint4 w = mine[(size_t)u * 256u];
+                    const uint4 o = do_vector<C, GM, METER, false, true, false, true>(w, rc, radd0 - (uint32_t)u, kmax, pacc, 8);
                     if (a.store)
                         st_stream(dstp + (size_t)u * kStep, o);
                 }
-            }
-            if (more) {
-#pragma unroll
-                for (int u = 0; u < H; u++)
-                    if ((uint32_t)u < n_n)
-                        bufA[u] = ld_stream(src_n + (size_t)u * kStep, NC);
-            }
-#pragma unroll
-            for (int u = 0; u < H; u++) {
-                if ((uint32_t)(H + u) < n_i) {
-                    const uint4 o = do_vector<C, GM, METER, false, true, false, true>(bufB[u], rc, radd0 - (uint32_t)(H + u), kmax, pacc, 8);
-                    if (a.store)
-                        st_stream(dstp + (size_t)(H + u) * kStep, o);
-                }
-            }
-            if (more) {
-#pragma unroll
-                for (int u = 0; u < H; u++)
-                    if ((uint32_t)(H + u) < n_n)
-                        bufB[u] = ld_stream(src_n + (size_t)(H + u) * kStep, NC);
             }
             if (tail_valid) {
                 // the one vector that straddles the end of the valid frames (ragged ticks only)
@@ -136,6 +142,7 @@ __global__ void __launch_bounds__(256, Tune<C, 8>::kMinCtas) span_tick(const __g
             tail_valid = tail_valid_n;
             nfr_next = t + 2 < n_ticks ? frames_of(t + 2) : 0u;
         }
+        cp_async_wait<0>();
         if (!METER)
             continue;
 

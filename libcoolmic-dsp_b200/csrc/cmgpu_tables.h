@@ -100,6 +100,8 @@ struct MixArgs {
     uint32_t stride_in, stride_out;
     uint32_t items_per_block, per_item;   // frames per item
     uint32_t cin, cout;
+    unsigned int *work;           // work-claim counter, see TickArgs::work
+    uint32_t work_base;
 };
 
 }  // namespace cmgpu

@@ -11,7 +11,7 @@ from oracle.pyoracle import Meter
 pytestmark = pytest.mark.gpu
 
 
-def run_mix(cm, port, cin, cout, n_streams, block_frames, seed, flags=0, ticks=1, kind="full"):
+def run_mix(cm, port, cin, cout, n_streams, block_frames, seed, flags=0, ticks=1, kind="full", in_meter=True):
     rng = np.random.default_rng(seed)
     with cm.Engine(cin, n_streams, block_frames, out_channels=cout, flags=flags) as eng:
         scales = rng.integers(1, 65536, size=n_streams)
@@ -45,8 +45,10 @@ def run_mix(cm, port, cin, cout, n_streams, block_frames, seed, flags=0, ticks=1
                 assert np.array_equal(got[s, : n * cout], want), f"tick {t} stream {s}"
         so = eng.snapshot()
         si = eng.input_snapshot()
+        if not in_meter:
+            assert all(int(si[s].frames) == 0 and not any(si[s].power) and not any(si[s].channel_peak) for s in range(n_streams))
         for s in range(n_streams):
-            for st, want, ch in ((so[s], m_out[s], cout), (si[s], m_in[s], cin)):
+            for st, want, ch in ((so[s], m_out[s], cout), (si[s], m_in[s], cin))[: 2 if in_meter else 1]:
                 assert int(st.frames) == int(want.frames)
                 assert int(st.global_peak) == int(want.global_peak)
                 for c in range(ch):
@@ -58,6 +60,13 @@ def run_mix(cm, port, cin, cout, n_streams, block_frames, seed, flags=0, ticks=1
 def test_downmix_8_to_2(cm, port):
     assert run_mix(cm, port, 8, 2, 37, 1000, seed=1) == "mix8to2_tick"
     assert run_mix(cm, port, 8, 2, 11, 5000, seed=2, ticks=3, kind="ties") == "mix8to2_tick"
+
+
+def test_downmix_8_to_2_outputs_metered_only(cm, port):
+    """CMGPU_MIX_OUTPUT_METER_ONLY: same PCM and output meters, the 8 input channels are not metered."""
+    assert run_mix(cm, port, 8, 2, 37, 1000, seed=3, flags=cm.MIX_OUTPUT_METER_ONLY, in_meter=False).startswith("mix8to2_tick")
+    assert run_mix(cm, port, 8, 2, 9, 7000, seed=4, ticks=2, kind="ties", flags=cm.MIX_OUTPUT_METER_ONLY,
+                   in_meter=False) == "mix8to2_tick<outputs metered>"
 
 
 def test_downmix_generic_kernel_agrees(cm, port):
