@@ -42,6 +42,9 @@
 #ifndef CMGPU_G8_CTAS_WIDE
 #define CMGPU_G8_CTAS_WIDE 2
 #endif
+#ifndef CMGPU_PLANAR_CTAS
+#define CMGPU_PLANAR_CTAS 2   // resident CTAs per SM of the kernels that also write float planes
+#endif
 
 namespace cmgpu {
 
@@ -308,10 +311,10 @@ __device__ __forceinline__ uint4 do_vector(uint4 w, const Recipe (&rc)[Shape<C>:
 // enc_vorbis.c:108-117 -- de-interleave and `sample / 32768.f` into one float plane per channel,
 // which is what vorbis_analysis_buffer() wants. The division by 2^15 is exact in binary32, so
 // multiplying by 2^-15 gives bit-identical floats. Only the PLANAR instantiations of the kernel call
-// it (a run-time flag in the plain kernels cost them 2 %); it stays out of line there.
+// it (a run-time flag in the plain kernels cost them 2 %).
 template <int C>
-__device__ __noinline__ void store_planar(float *planar, uint32_t plane_stride, uint32_t s, uint32_t v, uint4 o,
-                                          int nvalid)
+__device__ __forceinline__ void store_planar(float *planar, uint32_t plane_stride, uint32_t s, uint32_t v, uint4 o,
+                                             int nvalid)
 {
     constexpr int P = Shape<C>::kPerLane;
     const uint32_t w[4] = {o.x, o.y, o.z, o.w};
@@ -530,8 +533,10 @@ __device__ __forceinline__ void item_publish(const TickArgs &a, const Item &it, 
 // NC: the launch does not write its input ring (separate output ring), so the loads may take the
 // read-only path; in place they are plain loads. A compile-time choice: as a run-time flag it cost
 // the 8-channel kernel 5 %.
+// (the instantiations with the float-plane second output get 128 registers: at 80 they spilled 100-250
+//  bytes, and a kernel that writes three times what it reads is bound by its stores, not by occupancy)
 template <int C, int G, int GM, bool METER, bool PLANAR = false, bool NC = false>
-__global__ void __launch_bounds__(256, Tune<C, G>::kMinCtas) fused_tick(const __grid_constant__ TickArgs a)
+__global__ void __launch_bounds__(256, PLANAR ? CMGPU_PLANAR_CTAS : Tune<C, G>::kMinCtas) fused_tick(const __grid_constant__ TickArgs a)
 {
     constexpr int P = Shape<C>::kPerLane;
     constexpr int UNROLL = Tune<C, G>::kUnroll;
