@@ -702,7 +702,7 @@ def object_api_leg(cm, synth, device):
     fn.restype = C.c_int
     fn.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_void_p,
                    C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
-    streams, channels, block, n_ticks, slots, threads = 1024, 2, 12000, 40, 4, min(16, os.cpu_count() or 1)
+    streams, channels, block, n_ticks, slots, threads = 1024, 2, 12000, 40, 4, max(1, min(16, (os.cpu_count() or 2) // 2))
     period = synth.load_period(48000)
     pcm = np.ascontiguousarray(synth.synth_rows(period, 0, streams, channels, block * 4, 0, 7, 3, NOISE_EVERY, NOISE_PHASE))
     secs = C.c_double(0)

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <new>
 #include <algorithm>
@@ -327,7 +328,11 @@ void make_plan(cmgpu_ctx *c)
         const unsigned lanes = 32 - 32 % m;
         const uint32_t nvec = (uint32_t)(c->stride / 16);
         const uint32_t quantum = lanes * 8u;                      // two batches of 4 per lane
-        uint32_t target = 2048;
+        // Large items: this kernel has no cross-item prefetch (it spilled), so every item
+        // boundary exposes a load latency and a recipe gather. Measured on 6-channel streams
+        // (profiles/r2_*cfg6ch*): 2,048 vectors per item 0.81 of the copy rate, 4,096 0.85, 7,000 0.86;
+        // the epilogue's 16-bit sample index caps an item at 8,192 vectors.
+        uint32_t target = 7000;
         if (const char *e = getenv("CMGPU_ITEM_VECS"))            // tuning hook
             target = (uint32_t)strtoul(e, nullptr, 10) ? (uint32_t)strtoul(e, nullptr, 10) : target;
         if (target > 8192)                                        // the epilogue's sample index (vector * 8 + slot) fits 16 bits
@@ -1219,14 +1224,50 @@ int cmgpu_debug_violations(void)
 #endif
 }
 
+// Waiting for a stream or an event: poll for a short while before blocking. A blocking wait costs a
+// few microseconds of wake-up latency, which is most of what is left of a 20 ms-sized tick issued
+// alone (config 3: ~8 us on the device); work that is not about to finish falls through to the
+// blocking call after kSpinNs and costs nothing extra.
+namespace {
+constexpr long long kSpinNs = 60000;
+inline long long now_ns()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (long long)ts.tv_sec * 1000000000ll + ts.tv_nsec;
+}
+cudaError_t wait_stream(cudaStream_t st)
+{
+    const long long t0 = now_ns();
+    for (;;) {
+        const cudaError_t e = cudaStreamQuery(st);
+        if (e != cudaErrorNotReady)
+            return e;
+        if (now_ns() - t0 > kSpinNs)
+            return cudaStreamSynchronize(st);
+    }
+}
+cudaError_t wait_event(cudaEvent_t ev)
+{
+    const long long t0 = now_ns();
+    for (;;) {
+        const cudaError_t e = cudaEventQuery(ev);
+        if (e != cudaErrorNotReady)
+            return e;
+        if (now_ns() - t0 > kSpinNs)
+            return cudaEventSynchronize(ev);
+    }
+}
+}  // namespace
+
 int cmgpu_sync(cmgpu_ctx_t *c)
 {
     if (!c)
         return fail(CMGPU_ERR_FAULT, "NULL context");
     CU(cudaSetDevice(c->device));
-    CU(cudaStreamSynchronize(c->s_up));
-    CU(cudaStreamSynchronize(c->s_cmp));
-    CU(cudaStreamSynchronize(c->s_down));
+    CU(wait_stream(c->s_up));
+    CU(wait_stream(c->s_cmp));
+    CU(wait_stream(c->s_down));
 #ifdef CMGPU_BOUNDS_CHECK
     if (const int n = cmgpu_debug_violations())
         return fail(CMGPU_ERR_GENERIC, "bounds check: %d PCM vector accesses outside the context's rings", n);
@@ -1244,9 +1285,9 @@ int cmgpu_slot_wait(cmgpu_ctx_t *c, unsigned slot)
         if (int erc = ticks_done_event_locked(c, slot))
             return erc;
     }
-    CU(cudaEventSynchronize(c->ev_up[slot]));
-    CU(cudaEventSynchronize(c->ev_cmp[slot]));
-    CU(cudaEventSynchronize(c->ev_down[slot]));
+    CU(wait_event(c->ev_up[slot]));
+    CU(wait_event(c->ev_cmp[slot]));
+    CU(wait_event(c->ev_down[slot]));
     return CMGPU_OK;
 }
 

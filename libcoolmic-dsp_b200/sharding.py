@@ -1,10 +1,12 @@
-"""Stream sharding across GPUs and the one collective on the path: gathering per-stream meter rows.
+"""Stream sharding across GPUs: the partition rule, and the helpers of the CPU (gloo) test.
 
 Streams are independent, so rank r owns the contiguous range
-[r*N/R, (r+1)*N/R) and the data path needs no exchange. Once per reporting interval the raw
-meter rows ((2C+2) uint64 per stream, exact integers) travel to rank 0 with one
-torch.distributed gather (NCCL over NVLink on GPUs, gloo in the CPU tests); rank 0 decodes and
-finalises them with the C ABI (cmgpu_meter_decode / cmgpu_finalise). torch is plumbing only.
+[r*N/R, (r+1)*N/R) and the data path needs no exchange. The one collective -- per-stream meter
+results to rank 0 once per reporting interval -- is done by the C library itself over NCCL
+(cmgpu_comm_*, cmgpu_gather_results in csrc/cmgpu_comm.cu; binding.Comm). What is left here:
+`stream_range`, and `gather_rows` / `decode_rows`, which tests/test_sharding.py uses to push the same
+raw rows through a world-size-2 gloo gather on CPU and decode them with the C ABI
+(cmgpu_meter_decode / cmgpu_finalise) -- the host-side half of the N > 1 path, without GPUs.
 """
 from __future__ import annotations
 
