@@ -204,6 +204,20 @@ int main(int argc, char **argv)
         if (r && ms < best) best = ms;
     }
     report("cudaMemcpyAsync D2D", best);
+    {
+        // the same copy back to back for >= 2 s: what the part sustains once it runs into its power cap
+        // (the yardstick for bench.py's roofline.sustained)
+        const int reps = (int)(2200.0 / best) + 1;
+        cudaEventRecord(e0);
+        for (int r = 0; r < reps; r++)
+            cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        char name[64];
+        snprintf(name, sizeof(name), "cudaMemcpyAsync D2D, %d back to back (%.1f s)", reps, ms * 1e-3);
+        report(name, ms / reps);
+    }
     for (uint32_t per : {1024u, 2048u, 4096u}) {
         best = 1e9;
         for (int r = 0; r < 6; r++) {
