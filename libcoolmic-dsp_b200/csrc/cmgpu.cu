@@ -1123,6 +1123,7 @@ int cmgpu_slot_set_frames(cmgpu_ctx_t *c, unsigned slot, const uint32_t *frames)
 
 int cmgpu_submit(cmgpu_ctx_t *c, unsigned slot, const void *host)
 {
+    CMGPU_TRACE("cmgpu_submit");
     if (!slot_ok(c, slot))
         return fail(c ? CMGPU_ERR_INVAL : CMGPU_ERR_FAULT, "bad context or slot");
     std::lock_guard<std::mutex> lk(c->mu);
@@ -1145,6 +1146,7 @@ int cmgpu_submit(cmgpu_ctx_t *c, unsigned slot, const void *host)
 
 int cmgpu_process(cmgpu_ctx_t *c, unsigned slot, unsigned flags)
 {
+    CMGPU_TRACE("cmgpu_process");
     if (!slot_ok(c, slot))
         return fail(c ? CMGPU_ERR_INVAL : CMGPU_ERR_FAULT, "bad context or slot");
     std::lock_guard<std::mutex> lk(c->mu);
@@ -1164,6 +1166,7 @@ int cmgpu_process(cmgpu_ctx_t *c, unsigned slot, unsigned flags)
 
 int cmgpu_fetch(cmgpu_ctx_t *c, unsigned slot, void *host)
 {
+    CMGPU_TRACE("cmgpu_fetch");
     if (!slot_ok(c, slot))
         return fail(c ? CMGPU_ERR_INVAL : CMGPU_ERR_FAULT, "bad context or slot");
     std::lock_guard<std::mutex> lk(c->mu);
@@ -1262,6 +1265,7 @@ cudaError_t wait_event(cudaEvent_t ev)
 
 int cmgpu_sync(cmgpu_ctx_t *c)
 {
+    CMGPU_TRACE("cmgpu_sync");
     if (!c)
         return fail(CMGPU_ERR_FAULT, "NULL context");
     CU(cudaSetDevice(c->device));
@@ -1305,6 +1309,7 @@ int cmgpu_meter_decode(const uint64_t *rows, unsigned count, unsigned channels, 
 
 int cmgpu_meter_snapshot(cmgpu_ctx_t *c, unsigned first, unsigned count, cmgpu_meter_state_t *out, int reset)
 {
+    CMGPU_TRACE("cmgpu_meter_snapshot");
     if (!c || !out)
         return fail(CMGPU_ERR_FAULT, "NULL argument");
     if ((uint64_t)first + count > c->max_streams)
@@ -1547,6 +1552,7 @@ extern "C" {
 
 int cmgpu_process_cycle(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, unsigned flags)
 {
+    CMGPU_TRACE("cmgpu_process_cycle");
     if (!c)
         return fail(CMGPU_ERR_FAULT, "NULL context");
     if (!n_slots || (uint64_t)first_slot + n_slots > c->slots)

@@ -246,6 +246,7 @@ int cmgpu_comm_sum(cmgpu_comm_t *m, double *values, unsigned n) { return allredu
 int cmgpu_gather_results(cmgpu_ctx_t *c, cmgpu_comm_t *m, int root, uint32_t rate, int reset, cmgpu_result_t *results,
                          cmgpu_meter_state_t *states, int *rcs, unsigned *counts)
 {
+    CMGPU_TRACE("cmgpu_gather_results");
     if (!c || !m)
         return fail(CMGPU_ERR_FAULT, "NULL argument");
     if (root < 0 || root >= m->size)

@@ -9,6 +9,7 @@
 #include "../../include/cmgpu.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>       // header-only; the ranges cost nothing unless a tool (nsys, ncu --nvtx) is attached
 
 #include <cmath>
 #include <cstdarg>
@@ -33,6 +34,15 @@ void finalise_rows(const uint64_t *rows, size_t count, unsigned row_u64, unsigne
                    cmgpu_result_t *results, cmgpu_meter_state_t *states, int *rcs);
 
 }  // namespace cmgpu
+
+// NVTX range over an entry point of the C ABI (tracing).
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+#define CMGPU_TRACE(name) NvtxRange nvtx_range__(name)
 
 #define CU(call)                                                                                   \
     do {                                                                                           \

@@ -291,6 +291,7 @@ extern "C" {
 int cmgpu_meter_results(cmgpu_ctx_t *c, unsigned first, unsigned count, uint32_t rate, int reset, unsigned flags,
                         cmgpu_result_t *results, cmgpu_meter_state_t *states, int *rcs)
 {
+    CMGPU_TRACE("cmgpu_meter_results");
     if (!c)
         return fail(CMGPU_ERR_FAULT, "NULL context");
     if ((uint64_t)first + count > c->max_streams)
