@@ -249,6 +249,7 @@ _REAL_STDOUT = 1
 
 def main():
     global _REAL_STDOUT
+    t_start = time.perf_counter()
     # keep stdout clean for the JSON line: everything else written to fd 1 goes to stderr
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
@@ -589,6 +590,36 @@ def main():
             e2e["link"] = link
             e2e["link_ceiling_gbs"] = link["both_each_way_gbs_all_ranks"]
             e2e["frac_of_link"] = e2e["gbs_each_way_all_ranks"] / max(link["both_each_way_gbs_all_ranks"], 1e-9)
+        if not args.no_extras and not mix_out:
+            # Pass-through streams, the reference's default state (no master gain: transform.c:107-108
+            # leaves the buffer alone): uploaded from the pinned staging ring, metered, nothing downloaded.
+            pt_ticks = min(n_ticks, 8)
+            eng = cm.Engine(channels, streams_per_gpu, tick_frames, ring_slots=4, device=local)
+            for slot in range(4):
+                eng.host_slot(slot)[:] = pin_in.array[slot % n_ticks]
+            for _ in range(2):
+                for t in range(pt_ticks):
+                    eng.submit(t % 4); eng.process(t % 4); eng.fetch(t % 4)
+            eng.results(rate, out=results_out)
+            eng.sync()
+            up0, down0 = eng.transfer_bytes()
+            barrier()
+            t0 = time.perf_counter()
+            pt_steps = 3
+            for _ in range(pt_steps):
+                for t in range(pt_ticks):
+                    eng.submit(t % 4); eng.process(t % 4); eng.fetch(t % 4)
+                eng.results(rate, out=results_out)
+            eng.sync()
+            pt_wall = max_over_ranks(time.perf_counter() - t0)
+            up1, down1 = eng.transfer_bytes()
+            e2e["passthrough"] = {"value": streams_per_gpu * world * tick_frames * pt_ticks * channels * pt_steps / pt_wall / 1e6,
+                                  "unit": "Msamples/s", "h2d_bytes_per_step": (up1 - up0) // pt_steps,
+                                  "d2h_bytes_per_step": (down1 - down0) // pt_steps + meter_bytes,
+                                  "note": "every stream in the reference's default state (no gain set): uploaded from the "
+                                          "pinned staging ring, metered on the device, no PCM download -- the staging slot "
+                                          "already holds the result"}
+            eng.close()
         pin_in.free(); pin_out.free()
 
         if not args.no_extras and rank == 0 and not mix_out:
@@ -621,7 +652,7 @@ def main():
                 "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
                 "dtype": "int32 (S16 in/out, int64 power)", "data": "synthetic", "config": config,
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu,
+                "cpu_baseline": cpu, "bench_wall_s": time.perf_counter() - t_start,
                 "nccl": ({"version": int(cm.lib().cmgpu_comm_nccl_version()), "ranks": world,
                           "from": "libcoolmic_b200.so (cmgpu_comm_*), id exchanged through a file; no torch.distributed"}
                          if comm is not None else None)}

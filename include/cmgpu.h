@@ -158,6 +158,11 @@ int cmgpu_fetch(cmgpu_ctx_t *ctx, unsigned slot, void *host);
 void  *cmgpu_device_planar_slot(cmgpu_ctx_t *ctx, unsigned slot);
 size_t cmgpu_plane_stride(const cmgpu_ctx_t *ctx);           /* in floats */
 int    cmgpu_fetch_planar(cmgpu_ctx_t *ctx, unsigned slot, float *host);
+/* (A download is skipped when it could only copy the input onto itself: in-place context, `host` NULL
+ * after a submit with `host` NULL, and no tick has written the slot's PCM since -- pass-through
+ * streams, the reference's default state (transform.c:107-108), are metered without a byte coming
+ * back. cmgpu_transfer_bytes reports what submit / fetch have really copied.) */
+int cmgpu_transfer_bytes(const cmgpu_ctx_t *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 /* Wait for everything queued on the context. */
 int cmgpu_sync(cmgpu_ctx_t *ctx);
 /* Wait until the slot's last fetch (or tick, if none) has completed. */

@@ -102,6 +102,7 @@ SYMBOLS = {
     "cmgpu_device_planar_slot": (_P, [_P, C.c_uint]),
     "cmgpu_plane_stride": (C.c_size_t, [_P]),
     "cmgpu_fetch_planar": (C.c_int, [_P, C.c_uint, C.POINTER(C.c_float)]),
+    "cmgpu_transfer_bytes": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "cmgpu_sync": (C.c_int, [_P]),
     "cmgpu_slot_wait": (C.c_int, [_P, C.c_uint]),
     "cmgpu_meter_snapshot": (C.c_int, [_P, C.c_uint, C.c_uint, C.POINTER(MeterState), C.c_int]),
@@ -391,6 +392,12 @@ class Engine:
         _check(self.L.cmgpu_time_cycles(self.ctx, first_slot, n_slots, cycles, flags, C.byref(ms)),
                "cmgpu_time_cycles")
         return float(ms.value)
+
+    def transfer_bytes(self):
+        """(host -> device, device -> host) PCM bytes cmgpu_submit / cmgpu_fetch have copied so far."""
+        up, down = C.c_uint64(0), C.c_uint64(0)
+        _check(self.L.cmgpu_transfer_bytes(self.ctx, C.byref(up), C.byref(down)), "cmgpu_transfer_bytes")
+        return int(up.value), int(down.value)
 
     def launch_count(self) -> int:
         return int(self.L.cmgpu_launch_count(self.ctx))

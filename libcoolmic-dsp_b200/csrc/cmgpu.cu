@@ -638,6 +638,9 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
     a.store = store ? 1u : 0u;
     a.planar = planar ? c->d_planar + (size_t)slot * c->planar_slot_floats : nullptr;
     a.plane_stride = (uint32_t)c->plane_stride;
+    if (store && !separate)
+        for (unsigned i = slot; i < slot + n_ticks && i < c->slots; i++)
+            c->slot_dirty[i] = 1;                    // the device copy now differs from what was uploaded
     a.n_ticks = n_ticks;
     a.frames_stride = c->max_streams;
     a.slot_bytes = c->slot_bytes;
@@ -887,6 +890,8 @@ static cmgpu_ctx_t *ctx_create_impl(int device, unsigned channels, unsigned out_
     c->up_pending.assign(ring_slots, 0);
     c->down_pending.assign(ring_slots, 0);
     c->cmp_unrecorded.assign(ring_slots, 0);
+    c->from_staging.assign(ring_slots, 0);
+    c->slot_dirty.assign(ring_slots, 1);
     c->in_chain.assign(ring_slots, 0);
     for (unsigned i = 0; i < ring_slots; i++) {
         if ((e = cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming)) != cudaSuccess ||
@@ -983,6 +988,16 @@ unsigned cmgpu_block_frames(const cmgpu_ctx_t *c) { return c ? c->block_frames :
 size_t cmgpu_block_stride(const cmgpu_ctx_t *c) { return c ? c->stride : 0; }
 size_t cmgpu_slot_bytes(const cmgpu_ctx_t *c) { return c ? c->slot_bytes : 0; }
 uint64_t cmgpu_launch_count(const cmgpu_ctx_t *c) { return c ? c->launches : 0; }
+int cmgpu_transfer_bytes(const cmgpu_ctx_t *c, uint64_t *h2d, uint64_t *d2h)
+{
+    if (!c)
+        return fail(CMGPU_ERR_FAULT, "NULL context");
+    if (h2d)
+        *h2d = c->bytes_h2d;
+    if (d2h)
+        *d2h = c->bytes_d2h;
+    return CMGPU_OK;
+}
 const char *cmgpu_kernel_name(const cmgpu_ctx_t *c)
 {
     if (!c)
@@ -1141,6 +1156,9 @@ int cmgpu_submit(cmgpu_ctx_t *c, unsigned slot, const void *host)
                        c->s_up));
     CU(cudaEventRecord(c->ev_up[slot], c->s_up));
     c->up_pending[slot] = 1;
+    c->from_staging[slot] = c->h_ring && host == c->h_ring + (size_t)slot * c->slot_bytes;
+    c->slot_dirty[slot] = 0;
+    c->bytes_h2d += c->stride * c->active;
     return CMGPU_OK;
 }
 
@@ -1178,10 +1196,16 @@ int cmgpu_fetch(cmgpu_ctx_t *c, unsigned slot, void *host)
     if (!host)
         return fail(CMGPU_ERR_FAULT, "no host buffer and no pinned staging");
     CU(cudaSetDevice(c->device));
+    // nothing on the device differs from what the staging slot already holds (in place, no tick has
+    // written PCM since the upload from that very slot): the download would copy the input onto itself
+    if (!c->d_out && !c->out_channels && staging && host == staging + (size_t)slot * out_slot && c->from_staging[slot] &&
+        !c->slot_dirty[slot])
+        return CMGPU_OK;
     if (int erc = ticks_done_event_locked(c, slot))
         return erc;
     CU(cudaStreamWaitEvent(c->s_down, c->ev_cmp[slot], 0));
     CU(cudaStreamWaitEvent(c->s_down, c->ev_up[slot], 0));
+    c->bytes_d2h += out_stride * c->active;
     const uint8_t *src = (c->d_out ? c->d_out : c->d_in) + (size_t)slot * out_slot;
     CU(cudaMemcpyAsync(host, src, out_stride * c->active, cudaMemcpyDeviceToHost, c->s_down));
     CU(cudaEventRecord(c->ev_down[slot], c->s_down));
@@ -1582,6 +1606,8 @@ int cmgpu_process_cycle(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, u
 #endif
         CU(cudaGraphLaunch(c->graph, c->s_cmp));
         c->launches += c->graph_launches;
+        for (unsigned i = 0; i < n_slots; i++)
+            c->slot_dirty[first_slot + i] = 1;      // (a replayed graph does not say whether it stores: assume it does)
     }
     for (unsigned i = 0; i < n_slots; i++) {
         c->cmp_unrecorded[first_slot + i] = 1;
@@ -1619,6 +1645,8 @@ int cmgpu_time_cycles(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, uns
 #endif
             CU(cudaGraphLaunch(c->graph, c->s_cmp));
             c->launches += c->graph_launches;
+            for (unsigned i = 0; i < n_slots; i++)
+                c->slot_dirty[first_slot + i] = 1;
         }
     }
     CU(cudaEventRecord(c->ev_t1, c->s_cmp));

@@ -112,6 +112,12 @@ struct cmgpu_ctx {
     // recorded when an upload or download first asks for it. Back-to-back ticks on resident data are
     // then back-to-back kernel launches, which is what lets them overlap (launch_begin).
     std::vector<uint8_t> up_pending, down_pending, cmp_unrecorded;
+    // A slot whose device copy still equals what was uploaded from its pinned staging slot needs no
+    // download: from_staging[slot] = the last submit came from the staging slot; slot_dirty[slot] = some
+    // tick (or fill) has written the slot's PCM on the device since. Pass-through streams -- the
+    // reference's default state, transform.c:107-108 -- are metered without a byte coming back.
+    std::vector<uint8_t> from_staging, slot_dirty;
+    uint64_t bytes_h2d = 0, bytes_d2h = 0;         // PCM bytes copied by cmgpu_submit / cmgpu_fetch so far
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     std::mutex mu;
 

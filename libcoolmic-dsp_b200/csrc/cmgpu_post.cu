@@ -414,6 +414,7 @@ int cmgpu_tone_fill(cmgpu_ctx_t *c, unsigned slot, uint64_t first_frame, unsigne
                                                  first_frame, first_stream, stream_step, channel_step);
     CU(cudaGetLastError());
     c->cmp_unrecorded[slot] = 1;
+    c->slot_dirty[slot] = 1;
     return CMGPU_OK;
 }
 
@@ -439,6 +440,7 @@ int cmgpu_noise_fill(cmgpu_ctx_t *c, unsigned slot, uint64_t first_frame, unsign
                                                   first_stream, seed, every, phase);
     CU(cudaGetLastError());
     c->cmp_unrecorded[slot] = 1;
+    c->slot_dirty[slot] = 1;
     return CMGPU_OK;
 }
 

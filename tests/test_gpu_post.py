@@ -241,6 +241,45 @@ def test_tick_base_rebased_by_a_full_reset(cm, port):
             assert all(int(st[s].channel_peak[0]) == 1000 for s in range(n_streams))
 
 
+def test_passthrough_slots_are_not_downloaded(cm, port):
+    """The reference's default state is no gain at all (transform.c:107-108: the buffer is left alone).
+    Such a slot is metered on the device and nothing comes back: the staging slot it was uploaded from
+    already holds the result. As soon as a tick writes the slot's PCM the download happens again --
+    also when a LATER tick of the same upload is a pass-through."""
+    rng = np.random.default_rng(21)
+    channels, n_streams, block = 2, 300, 4800
+    with cm.Engine(channels, n_streams, block, ring_slots=2) as eng:
+        host = eng.host_slot(0)
+        host[:] = make_pcm(rng, "full", host.shape)
+        src = host.copy()
+        scale = np.zeros(n_streams, np.uint16)
+        gain = np.zeros((n_streams, channels), np.uint16)
+        fr = np.full(n_streams, block, np.uint32)
+        eng.submit(0); eng.process(0); eng.fetch(0); eng.sync()
+        up, down = eng.transfer_bytes()
+        assert up == n_streams * eng.stride and down == 0
+        assert np.array_equal(eng.host_slot(0), src)
+        want, meters = oracle_batch(port, src, fr, channels, scale, gain)
+        snap = eng.snapshot(reset=True)
+        assert all(int(snap[s].power[0]) == int(meters[s].power[0]) and int(snap[s].frames) == block for s in range(n_streams))
+        # one stream with a gain: the tick writes the slot, the download is back
+        assert eng.set_gain(5, 2, 1000, [500, 2000]) == 0
+        scale[5], gain[5] = 1000, [500, 2000]
+        eng.submit(0); eng.process(0)
+        # ... and a pass-through tick AFTER it (gain off again, no new upload) must not hide that
+        assert eng.set_gain(5, 0, 0, None) == 0
+        eng.process(0); eng.fetch(0); eng.sync()
+        up2, down2 = eng.transfer_bytes()
+        assert down2 == n_streams * eng.stride and up2 == 2 * up
+        want, _ = oracle_batch(port, src, fr, channels, scale, gain)
+        assert np.array_equal(eng.host_slot(0), want)
+        # a caller's own buffer is always filled
+        out = np.empty_like(src)
+        eng.host_slot(1)[:] = src
+        eng.submit(1); eng.process(1); eng.fetch(1, out); eng.sync()
+        assert np.array_equal(out, src) and eng.transfer_bytes()[1] == 2 * down2
+
+
 def _gather_ranks(tmp_path, nranks, total_streams, channels):
     path = tmp_path / "nccl.id"
     procs = []
