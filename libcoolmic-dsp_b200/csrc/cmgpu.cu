@@ -230,7 +230,8 @@ int resident_ctas(cmgpu_ctx *c, int gm, bool meter)
         return cap;
     int n = 0;
     cudaError_t e = c->plan_g > 0   ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pick_fast(c, gm, meter), 256, 0)
-                    : c->plan_g < 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, any_kernel(gm, meter, c->d_out != nullptr), 256, 0)
+                    : c->plan_g < 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, any_kernel(gm, meter, c->d_out != nullptr), 256,
+                                                                                    cmgpu::kAnySmemBytes)
                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, generic_kernel(gm, meter), 128, 0);
     if (e != cudaSuccess || n < 1)
         n = 1;
@@ -309,7 +310,8 @@ cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter, cud
     if (grid > cap)
         grid = cap;
     if (c->plan_g < 0)
-        return launch_kernel(any_kernel(gm, meter, c->d_out != nullptr), (unsigned)grid, 256, 0, st, pdl, a, (int)c->channels, c->plan_lanes);
+        return launch_kernel(any_kernel(gm, meter, c->d_out != nullptr), (unsigned)grid, 256, cmgpu::kAnySmemBytes, st, pdl, a,
+                             (int)c->channels, c->plan_lanes);
     if (c->plan_g == 0)
         return launch_kernel(generic_kernel(gm, meter), (unsigned)grid, 128, 0, st, pdl, a, (int)c->channels);
     return launch_kernel(pick_fast(c, gm, meter, a.planar != nullptr), (unsigned)grid, 256, 0, st, pdl, a);

@@ -113,6 +113,17 @@ __device__ __forceinline__ uint64_t shfl_xor64(unsigned mask, uint64_t v, int of
     return ((uint64_t)hi << 32) | lo;
 }
 
+// Asynchronous 16-byte copies from global to shared memory (L2 only), for the kernels that stage a
+// lane's vectors through slots of its own instead of registers (span_tick, any_tick).
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gptr)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+
 // Hides where a value came from, so that recomputing something from it is really recomputed
 // (and its first copy does not have to stay in registers across the hot loop).
 __device__ __forceinline__ uint64_t opaque(uint64_t v)
@@ -749,60 +760,98 @@ __device__ __noinline__ void store_planar_any(float *planar, uint32_t plane_stri
 // C, so each of the lane's 8 sample slots keeps ONE channel for the whole item -- the hot loop is
 // the 8-channel one (do_vector<8>: a recipe, a peak key and a power sum per slot), only the
 // recipes are gathered per lane and the epilogue folds slots into channels by a per-lane map.
+constexpr int kAnyDepth = 8;                               // vectors of a lane in flight
+constexpr int kAnySmemBytes = kAnyDepth * 256 * 16;        // [kAnyDepth][256] uint4: slot (i mod depth) of thread tid
+
+// Round 2: the lane's vectors are no longer held in two register batches but streamed through a ring of
+// kAnyDepth private shared-memory slots with cp.async -- 8 vectors per lane in flight whatever the
+// register budget, and the ring simply runs on into the NEXT item before the current item's epilogue,
+// which the register version could not afford (it spilled).
 template <int GM, bool METER, bool NC = false>
 __global__ void __launch_bounds__(256, 2) any_tick(const __grid_constant__ TickArgs a, const int C, const int L)
 {
+    extern __shared__ uint4 any_ring[];
     launch_begin();
-    constexpr int UNROLL = 4;
     const uint32_t lane = threadIdx.x & 31u;
     const bool active = (int)lane < L;
     const size_t kStep = (size_t)L * 16;
     const uint64_t n_items = (uint64_t)a.n_streams * a.items_per_block;
     const uint64_t stride = (uint64_t)gridDim.x * 8u;
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(any_ring) + threadIdx.x * 16u;
+    const ptrdiff_t out_delta = a.out - a.in;
 
-    uint32_t claimed = 0;
-    for (uint64_t item = (uint64_t)blockIdx.x * 8u + (threadIdx.x >> 5); item < n_items;
-         item = next_item(item, stride, a.work, a.work_base, claimed)) {
-        claimed = claim_item(a.work, lane);
+    struct AnyItem {
+        const uint8_t *src;       // the lane's first vector
+        size_t base;              // byte offset of the stream-block
+        uint32_t s, v0, v1, vfull, first, n_i, valid_bytes;
+    };
+    auto setup = [&](uint64_t item, AnyItem &it) -> bool {
+        it.src = a.in;
+        it.base = 0;
+        it.s = it.v0 = it.v1 = it.vfull = it.first = it.n_i = it.valid_bytes = 0;
+        if (item >= n_items)
+            return false;
         const uint32_t s = (uint32_t)(item / a.items_per_block);
         const uint32_t chunk = (uint32_t)(item - (uint64_t)s * a.items_per_block);
         const uint32_t nfr = a.frames ? min(__ldg(a.frames + s), a.block_frames) : a.block_frames;
-        const uint32_t valid_bytes = nfr * (uint32_t)(2 * C);
-        const uint32_t nvec = (valid_bytes + 15u) >> 4;
-        const uint32_t v0 = chunk * a.per_item;
-        const uint32_t v1 = min(v0 + a.per_item, nvec);
+        it.valid_bytes = nfr * (uint32_t)(2 * C);
+        const uint32_t nvec = (it.valid_bytes + 15u) >> 4;
+        it.s = s;
+        it.v0 = chunk * a.per_item;
+        it.v1 = min(it.v0 + a.per_item, nvec);
         if (METER && chunk == 0 && lane == 0 && nfr)
             atomicAdd(a.meters + (size_t)s * a.row_u64 + 2 * C, (unsigned long long)nfr);
-        if (v0 >= v1)
-            continue;
-
-        const size_t base = (size_t)s * a.stride_bytes;
-        const uint32_t first = v0 + lane;
-        const uint32_t vfull = min(v1, valid_bytes >> 4);
-        const uint32_t n_i = (active && first < vfull) ? (vfull - first + (uint32_t)L - 1u) / (uint32_t)L : 0u;
-        const uint8_t *src = a.in + base + (size_t)first * 16;
-        uint8_t *dst = a.out + base + (size_t)first * 16;
-
-        // the lane's slot -> channel map and recipes
-        int chan[8];
-        Recipe rc[8];
-        {
-            int ch = (int)(((uint64_t)first * 8u) % (uint32_t)C);
-            const GainRow *g = a.gains + s;
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                chan[k] = ch;
-                rc[k].mw = rc[k].addm = 0;
-                rc[k].mul = 1;
-                if (GM != GM_IDENTITY) {
-                    rc[k].mw = (int)__ldg(&g->mw[ch]);
-                    rc[k].mul = (int)__ldg(&g->mul[ch]);
-                    if (GM == GM_MASKED)
-                        rc[k].addm = (int)__ldg(&g->addm[ch]);
-                }
-                ch = ch + 1 == C ? 0 : ch + 1;
-            }
+        it.base = (size_t)s * a.stride_bytes;
+        it.first = it.v0 + lane;
+        it.vfull = min(it.v1, it.valid_bytes >> 4);
+        it.n_i = (active && it.v0 < it.v1 && it.first < it.vfull) ? (it.vfull - it.first + (uint32_t)L - 1u) / (uint32_t)L : 0u;
+        it.src = a.in + it.base + (size_t)it.first * 16;
+        return true;
+    };
+    // vector i of the item into ring slot i mod depth; always one commit, so that "all but the newest
+    // depth - 1 groups have landed" means "vector i is there" at step i
+    auto request = [&](const AnyItem &it, uint32_t i) {
+        if (i < it.n_i) {
+            const uint8_t *p = it.src + (size_t)i * kStep;
+#ifdef CMGPU_BOUNDS_CHECK
+            if (dbg_ok(p))
+#endif
+                cp_async16(smem0 + (i & (uint32_t)(kAnyDepth - 1)) * 4096u, p);
         }
+        cp_async_commit();
+    };
+    // the lane's slot -> channel map and recipes
+    auto gather = [&](const AnyItem &it, int (&chan)[8], Recipe (&rc)[8]) {
+        int ch = (int)(((uint64_t)it.first * 8u) % (uint32_t)C);
+        const GainRow *g = a.gains + it.s;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            chan[k] = ch;
+            rc[k].mw = rc[k].addm = 0;
+            rc[k].mul = 1;
+            if (GM != GM_IDENTITY) {
+                rc[k].mw = (int)__ldg(&g->mw[ch]);
+                rc[k].mul = (int)__ldg(&g->mul[ch]);
+                if (GM == GM_MASKED)
+                    rc[k].addm = (int)__ldg(&g->addm[ch]);
+            }
+            ch = ch + 1 == C ? 0 : ch + 1;
+        }
+    };
+
+    uint64_t item = (uint64_t)blockIdx.x * 8u + (threadIdx.x >> 5);
+    AnyItem cur;
+    int chan[8];
+    Recipe rc[8];
+    bool have = setup(item, cur);
+    if (have) {
+#pragma unroll
+        for (int i = 0; i < kAnyDepth; i++)
+            request(cur, (uint32_t)i);
+        gather(cur, chan, rc);
+    }
+    while (have) {
+        const uint32_t claimed = claim_item(a.work, lane);
         uint32_t kmax[8];
         uint64_t pacc[8];
 #pragma unroll
@@ -810,107 +859,95 @@ __global__ void __launch_bounds__(256, 2) any_tick(const __grid_constant__ TickA
             kmax[k] = 0;
             pacc[k] = 0;
         }
-
-        uint4 bufA[UNROLL], bufB[UNROLL];
-        const uint32_t nb = n_i / UNROLL;
-#define CMGPU_LOAD_BATCH(buf, b)                                                        \
-    _Pragma("unroll") for (int u = 0; u < UNROLL; u++)                                  \
-        buf[u] = ld_stream(src + (size_t)((b) * UNROLL + u) * kStep, NC);
-#define CMGPU_DO_BATCH(buf, b)                                                          \
-    _Pragma("unroll") for (int u = 0; u < UNROLL; u++) {                                \
-        const uint32_t iu = (b) * UNROLL + u;                                           \
-        const uint4 o = do_vector<8, GM, METER, false, true>(buf[u], rc, 0xffffu - iu, kmax, pacc, 8); \
-        if (a.store)                                                                    \
-            st_stream(dst + (size_t)iu * kStep, o);                                     \
-        if (a.planar)                                                                   \
-            store_planar_any(a.planar, a.plane_stride, s, C, first + iu * (uint32_t)L, o, 8); \
-    }
-        if (nb > 0) {
-            CMGPU_LOAD_BATCH(bufA, 0u)
-        }
-        for (uint32_t b = 0; b < nb; b += 2) {
-            if (b + 1 < nb) {
-                CMGPU_LOAD_BATCH(bufB, b + 1)
-            }
-            CMGPU_DO_BATCH(bufA, b)
-            if (b + 2 < nb) {
-                CMGPU_LOAD_BATCH(bufA, b + 2)
-            }
-            if (b + 1 < nb) {
-                CMGPU_DO_BATCH(bufB, b + 1)
-            }
-        }
-#undef CMGPU_LOAD_BATCH
-#undef CMGPU_DO_BATCH
-        for (uint32_t i = nb * UNROLL; i < n_i; i++) {
-            const uint4 w = ld_stream(src + (size_t)i * kStep, NC);
+        uint8_t *const dst = const_cast<uint8_t *>(cur.src) + out_delta;
+        for (uint32_t i = 0; i < cur.n_i; i++) {
+            cp_async_wait<kAnyDepth - 1>();
+            const uint4 w = any_ring[(size_t)(i & (uint32_t)(kAnyDepth - 1)) * 256u + threadIdx.x];
             const uint4 o = do_vector<8, GM, METER, false, true>(w, rc, 0xffffu - i, kmax, pacc, 8);
             if (a.store)
                 st_stream(dst + (size_t)i * kStep, o);
             if (a.planar)
-                store_planar_any(a.planar, a.plane_stride, s, C, first + i * (uint32_t)L, o, 8);
+                store_planar_any(a.planar, a.plane_stride, cur.s, C, cur.first + i * (uint32_t)L, o, 8);
+            request(cur, i + (uint32_t)kAnyDepth);
         }
-        if (active && vfull < v1 && (vfull << 4) < valid_bytes && ((vfull - v0) % (uint32_t)L) == lane) {
-            const uint32_t step = (vfull - v0) / (uint32_t)L;
-            const int nvalid = (int)((valid_bytes - (vfull << 4)) >> 1);
-            const uint4 w = ld_stream(a.in + base + (size_t)vfull * 16, NC);
+        if (active && cur.v0 < cur.v1 && cur.vfull < cur.v1 && (cur.vfull << 4) < cur.valid_bytes &&
+            ((cur.vfull - cur.v0) % (uint32_t)L) == lane) {
+            // the one vector that straddles the end of the valid frames
+            const uint32_t step = (cur.vfull - cur.v0) / (uint32_t)L;
+            const int nvalid = (int)((cur.valid_bytes - (cur.vfull << 4)) >> 1);
+            const uint4 w = ld_stream(a.in + cur.base + (size_t)cur.vfull * 16, NC);
             const uint4 o = do_vector<8, GM, METER, true, true>(w, rc, 0xffffu - step, kmax, pacc, nvalid);
             if (a.store)
-                st_stream(a.out + base + (size_t)vfull * 16, o);
+                st_stream(a.out + cur.base + (size_t)cur.vfull * 16, o);
             if (a.planar)
-                store_planar_any(a.planar, a.plane_stride, s, C, vfull, o, nvalid);
+                store_planar_any(a.planar, a.plane_stride, cur.s, C, cur.vfull, o, nvalid);
         }
-        if (!METER)
-            continue;
 
-        // ---- epilogue: fold the lane's slots by its channel map, combine lanes, publish ----
-        // Keys stay 32 bits wide until a channel's winner is known: magnitude << 16 | ~(index of the
-        // sample's vector among the item's vectors * 8 + slot) -- one SHFL + max per round, and ONE
-        // division by C (sample index -> frame) per channel instead of one per slot.
-        const uint64_t pos_base = tick_begin(a);
-        uint32_t key8[8];
+        // the next item: its first vectors go out before this item's epilogue
+        item = next_item(item, stride, a.work, a.work_base, claimed);
+        AnyItem nxt;
+        const bool have_n = setup(item, nxt);
+        if (have_n) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const uint32_t idx = ((0xffffu - (kmax[k] & 0xffffu)) * (uint32_t)L + lane) * 8u + (uint32_t)k;
-            key8[k] = (kmax[k] >> 16) ? ((kmax[k] & 0xffff0000u) | (0xffffu - idx)) : 0u;
+            for (int i = 0; i < kAnyDepth; i++)
+                request(nxt, (uint32_t)i);
         }
-        uint32_t key32 = 0;
-        uint64_t pw = 0;
-        for (int c = 0; c < C; c++) {
-            uint32_t kc = 0;
-            uint64_t pc = 0;
+
+        if (METER && cur.v0 < cur.v1) {
+            // ---- epilogue: fold the lane's slots by its channel map, combine lanes, publish ----
+            // Keys stay 32 bits wide until a channel's winner is known: magnitude << 16 | ~(index of the
+            // sample's vector among the item's vectors * 8 + slot) -- one SHFL + max per round, and ONE
+            // division by C (sample index -> frame) per channel instead of one per slot.
+            const uint64_t pos_base = tick_begin(a);
+            uint32_t key8[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                if (chan[k] == c) {
-                    kc = max(kc, key8[k]);
-                    pc += pacc[k];
+                const uint32_t idx = ((0xffffu - (kmax[k] & 0xffffu)) * (uint32_t)L + lane) * 8u + (uint32_t)k;
+                key8[k] = (kmax[k] >> 16) ? ((kmax[k] & 0xffff0000u) | (0xffffu - idx)) : 0u;
+            }
+            uint32_t key32 = 0;
+            uint64_t pw = 0;
+            for (int c = 0; c < C; c++) {
+                uint32_t kc = 0;
+                uint64_t pc = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (chan[k] == c) {
+                        kc = max(kc, key8[k]);
+                        pc += pacc[k];
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    kc = max(kc, __shfl_xor_sync(0xffffffffu, kc, off));
+                    pc += shfl_xor64(0xffffffffu, pc, off);
+                }
+                if ((int)lane == c) {
+                    key32 = kc;
+                    pw = pc;
                 }
             }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                kc = max(kc, __shfl_xor_sync(0xffffffffu, kc, off));
-                pc += shfl_xor64(0xffffffffu, pc, off);
-            }
-            if ((int)lane == c) {
-                key32 = kc;
-                pw = pc;
+            __syncwarp();
+            if ((int)lane < C) {
+                unsigned long long *row = a.meters + (size_t)cur.s * a.row_u64;
+                if (key32) {
+                    const uint32_t mag = key32 >> 16;
+                    const uint64_t sample = (uint64_t)cur.v0 * 8u + (0xffffu - (key32 & 0xffffu));
+                    const uint32_t frame = (uint32_t)(sample / (uint32_t)C);
+                    const volatile int16_t *y = reinterpret_cast<const volatile int16_t *>(a.out + cur.base);
+                    const int yv = y[(size_t)frame * C + lane];
+                    atomicMax(row + lane, (unsigned long long)(make_key(mag, pos_base + frame) | (yv < 0 ? 1ull : 0ull)));
+                }
+                if (pw)
+                    atomicAdd(row + C + lane, (unsigned long long)pw);
             }
         }
-        __syncwarp();
-        if ((int)lane < C) {
-            unsigned long long *row = a.meters + (size_t)s * a.row_u64;
-            if (key32) {
-                const uint32_t mag = key32 >> 16;
-                const uint64_t sample = (uint64_t)v0 * 8u + (0xffffu - (key32 & 0xffffu));
-                const uint32_t frame = (uint32_t)(sample / (uint32_t)C);
-                const volatile int16_t *y = reinterpret_cast<const volatile int16_t *>(a.out + base);
-                const int yv = y[(size_t)frame * C + lane];
-                atomicMax(row + lane, (unsigned long long)(make_key(mag, pos_base + frame) | (yv < 0 ? 1ull : 0ull)));
-            }
-            if (pw)
-                atomicAdd(row + C + lane, (unsigned long long)pw);
-        }
+        if (have_n)
+            gather(nxt, chan, rc);
+        cur = nxt;
+        have = have_n;
     }
+    cp_async_wait<0>();
     tick_end(a);
 }
 

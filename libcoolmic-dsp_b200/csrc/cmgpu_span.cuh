@@ -29,14 +29,6 @@ constexpr uint32_t kSpanMaxTicks = 1024;      // (tick * 8 + step) * 8 + lane mu
 // (profiles/r2_span_tick_cfg3_*): with the vectors held in two register half-buffers a lane had 1.6
 // vectors in flight on average and the launch ran at the rate Little's law gives for that (4.4 TB/s,
 // half the warp cycles on long_scoreboard); staged, a whole tick per lane is in flight all the time.
-__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gptr)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 template <int C, int GM, bool METER, bool NC>
 __global__ void __launch_bounds__(256, Tune<C, 8>::kMinCtas) span_tick(const __grid_constant__ TickArgs a, const uint32_t vmax)
 {
