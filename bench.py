@@ -414,19 +414,14 @@ def main():
     # small-buffer regime: one tick alone, device time and launch-to-complete
     if wl["graph"]:
         dev_us = min(eng.time_process(1, 0, 1, flags=pflags) for _ in range(20)) * 1e3
-        walls = []
-        for _ in range(50):
-            eng.sync()
-            t0 = time.perf_counter()
-            eng.process(0, pflags)
-            eng.sync()
-            walls.append((time.perf_counter() - t0) * 1e6)
+        med_us, min_us = eng.time_single_tick(0, pflags, reps=200)
         tick_ms = 1e3 * frames / rate
-        config["single_tick"] = {"device_us": dev_us, "launch_to_complete_us": float(np.median(walls)),
-                                 "launch_to_complete_us_min": float(np.min(walls)),
+        config["single_tick"] = {"device_us": dev_us, "launch_to_complete_us": med_us, "launch_to_complete_us_min": min_us,
                                  "cadence": f"real time needs one tick per {tick_ms:g} ms = {1e3 / tick_ms:g} ticks/s; the span "
                                             f"figure sustains {1e3 * ticks / ms_step:.0f} ticks/s",
-                                 "note": "one tick of the same shape issued alone, outside the timed steps"}
+                                 "note": "one tick of the same shape issued alone, outside the timed steps: device = between CUDA "
+                                         "events; launch-to-complete = cmgpu_process + cmgpu_sync timed in C "
+                                         "(cmgpu_time_single_tick, median / minimum of 200)"}
     kernel = eng.kernel_name()
     peak, peak_src = measured_peak()
     launches_per_step = max(1, launches // max(args.steps, 1))
@@ -733,7 +728,7 @@ def object_api_leg(cm, synth, device):
     fn.restype = C.c_int
     fn.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_void_p,
                    C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
-    streams, channels, block, n_ticks, slots, threads = 1024, 2, 12000, 40, 4, max(1, min(16, (os.cpu_count() or 2) // 2))
+    streams, channels, block, n_ticks, slots, threads = 1024, 2, 12000, 40, 4, max(1, min(16, os.cpu_count() or 1))
     period = synth.load_period(48000)
     pcm = np.ascontiguousarray(synth.synth_rows(period, 0, streams, channels, block * 4, 0, 7, 3, NOISE_EVERY, NOISE_PHASE))
     secs = C.c_double(0)

@@ -295,6 +295,11 @@ int cmgpu_time_process(cmgpu_ctx_t *ctx, unsigned first_slot, unsigned n_slots, 
 /* The same for `cycles` replays of the cached CUDA graph of n_slots ticks (cmgpu_process_cycle). */
 int cmgpu_time_cycles(cmgpu_ctx_t *ctx, unsigned first_slot, unsigned n_slots, unsigned cycles,
                       unsigned flags, float *ms);
+/* The latency of ONE tick issued alone, as a C caller sees it: `reps` times cmgpu_process + cmgpu_sync on
+ * an idle context, wall clock from the call to the return of the wait (median and minimum, in
+ * microseconds) -- the honest figure for 20 ms-sized blocks, where one tick is what arrives at a time. */
+int cmgpu_time_single_tick(cmgpu_ctx_t *ctx, unsigned slot, unsigned flags, unsigned reps, float *median_us,
+                           float *min_us);
 /* What the host link of `device` gives for page-locked buffers of `bytes` bytes, `reps` times each:
  * upload alone, download alone, and both at once (GB/s per direction). The end-to-end path moves
  * every sample across the link twice, so `both` is its ceiling; with several ranks calling this at the

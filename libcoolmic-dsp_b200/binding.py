@@ -120,6 +120,7 @@ SYMBOLS = {
     "cmgpu_host_out_slot": (_P, [_P, C.c_uint]),
     "cmgpu_time_process": (C.c_int, [_P, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_float)]),
     "cmgpu_time_cycles": (C.c_int, [_P, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_float)]),
+    "cmgpu_time_single_tick": (C.c_int, [_P, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "cmgpu_link_probe": (C.c_int, [C.c_int, C.c_size_t, C.c_uint, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                    C.POINTER(C.c_float)]),
     "cmgpu_debug_violations": (C.c_int, []),
@@ -398,6 +399,12 @@ class Engine:
         up, down = C.c_uint64(0), C.c_uint64(0)
         _check(self.L.cmgpu_transfer_bytes(self.ctx, C.byref(up), C.byref(down)), "cmgpu_transfer_bytes")
         return int(up.value), int(down.value)
+
+    def time_single_tick(self, slot: int = 0, flags: int = FUSED, reps: int = 200):
+        """(median, minimum) microseconds of cmgpu_process + cmgpu_sync on an idle context, timed in C."""
+        med, mn = C.c_float(0), C.c_float(0)
+        _check(self.L.cmgpu_time_single_tick(self.ctx, slot, flags, reps, C.byref(med), C.byref(mn)), "cmgpu_time_single_tick")
+        return float(med.value), float(mn.value)
 
     def launch_count(self) -> int:
         return int(self.L.cmgpu_launch_count(self.ctx))

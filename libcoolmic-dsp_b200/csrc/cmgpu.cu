@@ -1657,6 +1657,28 @@ int cmgpu_time_cycles(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, uns
     return CMGPU_OK;
 }
 
+int cmgpu_time_single_tick(cmgpu_ctx_t *c, unsigned slot, unsigned flags, unsigned reps, float *median_us, float *min_us)
+{
+    if (!c || !median_us || !min_us)
+        return fail(CMGPU_ERR_FAULT, "NULL argument");
+    if (!slot_ok(c, slot) || !reps)
+        return fail(CMGPU_ERR_INVAL, "bad slot or reps");
+    std::vector<float> us(reps);
+    for (unsigned r = 0; r < reps; r++) {
+        int rc = cmgpu_sync(c);
+        if (rc)
+            return rc;
+        const long long t0 = now_ns();
+        if ((rc = cmgpu_process(c, slot, flags)) || (rc = cmgpu_sync(c)))
+            return rc;
+        us[r] = (float)(now_ns() - t0) * 1e-3f;
+    }
+    std::sort(us.begin(), us.end());
+    *median_us = us[reps / 2];
+    *min_us = us[0];
+    return CMGPU_OK;
+}
+
 int cmgpu_recipe_eval(uint16_t gain, uint16_t scale, int16_t x)
 {
     if (!scale)

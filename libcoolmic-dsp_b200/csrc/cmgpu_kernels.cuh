@@ -859,16 +859,45 @@ __global__ void __launch_bounds__(256, 2) any_tick(const __grid_constant__ TickA
             kmax[k] = 0;
             pacc[k] = 0;
         }
-        uint8_t *const dst = const_cast<uint8_t *>(cur.src) + out_delta;
-        for (uint32_t i = 0; i < cur.n_i; i++) {
-            cp_async_wait<kAnyDepth - 1>();
-            const uint4 w = any_ring[(size_t)(i & (uint32_t)(kAnyDepth - 1)) * 256u + threadIdx.x];
+        // The ring is walked in rounds of kAnyDepth vectors, fully unrolled: slot offsets are constants and
+        // the two addresses run along as pointers (the first version of this loop, one vector per
+        // iteration with computed slots, spent 30 instructions per vector on its own bookkeeping and was
+        // issue-bound at the old kernel's speed).
+        const uint8_t *ld_p = cur.src + (size_t)kAnyDepth * kStep;      // the next vector to request
+        uint8_t *st_p = const_cast<uint8_t *>(cur.src) + out_delta;
+        const uint4 *const mine = any_ring + threadIdx.x;
+        uint32_t i = 0;
+        const uint32_t n_round = cur.n_i & ~(uint32_t)(kAnyDepth - 1);
+        for (; i < n_round; i += kAnyDepth) {
+#pragma unroll
+            for (int u = 0; u < kAnyDepth; u++) {
+                cp_async_wait<kAnyDepth - 1>();
+                const uint4 w = mine[u * 256];
+                const uint4 o = do_vector<8, GM, METER, false, true>(w, rc, 0xffffu - i - (uint32_t)u, kmax, pacc, 8);
+                if (a.store)
+                    st_stream(st_p, o);
+                if (a.planar)
+                    store_planar_any(a.planar, a.plane_stride, cur.s, C, cur.first + (i + (uint32_t)u) * (uint32_t)L, o, 8);
+                if (i + (uint32_t)(kAnyDepth + u) < cur.n_i) {
+#ifdef CMGPU_BOUNDS_CHECK
+                    if (dbg_ok(ld_p))
+#endif
+                        cp_async16(smem0 + (uint32_t)u * 4096u, ld_p);
+                }
+                cp_async_commit();
+                ld_p += kStep;
+                st_p += kStep;
+            }
+        }
+        for (; i < cur.n_i; i++) {          // what is left of the lane's vectors (< kAnyDepth): nothing more to request
+            cp_async_wait<0>();
+            const uint4 w = mine[(i & (uint32_t)(kAnyDepth - 1)) * 256u];
             const uint4 o = do_vector<8, GM, METER, false, true>(w, rc, 0xffffu - i, kmax, pacc, 8);
             if (a.store)
-                st_stream(dst + (size_t)i * kStep, o);
+                st_stream(st_p, o);
             if (a.planar)
                 store_planar_any(a.planar, a.plane_stride, cur.s, C, cur.first + i * (uint32_t)L, o, 8);
-            request(cur, i + (uint32_t)kAnyDepth);
+            st_p += kStep;
         }
         if (active && cur.v0 < cur.v1 && cur.vfull < cur.v1 && (cur.vfull << 4) < cur.valid_bytes &&
             ((cur.vfull - cur.v0) % (uint32_t)L) == lane) {

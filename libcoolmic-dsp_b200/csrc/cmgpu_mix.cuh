@@ -195,8 +195,10 @@ __device__ __forceinline__ int dp2a_hi_su(uint32_t a_s16x2, uint32_t b_u8x4, int
 // low and high bytes) + one 64-bit recombination per output instead of 8 half-rate IMAD.WIDE.
 // IN_METER false: the 8 input channels are not metered (cmgpu_mix_ctx_create flag CMGPU_MIX_OUTPUT_METER_ONLY):
 // half of the kernel's instructions, for callers that only want the levels of what they send on.
+// (without the input meter the kernel fits 80 registers: three resident CTAs instead of two hide the load
+//  latency that ncu showed as 46 % long_scoreboard stalls at two CTAs)
 template <bool IN_METER>
-__global__ void __launch_bounds__(256, 2) mix8to2_tick(const __grid_constant__ MixArgs a)
+__global__ void __launch_bounds__(256, IN_METER ? 2 : 3) mix8to2_tick(const __grid_constant__ MixArgs a)
 {
     launch_begin();
     constexpr int UNROLL = 4;
