@@ -408,6 +408,7 @@ def main():
     ms_step = ms_total / args.steps
     value = samples_per_step_rank * world / (ms_step * 1e-3) / 1e6
 
+    kernel = eng.kernel_name()
     # meter sanity on what was just measured: K identical ticks -> K * frames frames per stream
     snap = eng.snapshot(0, min(4, streams_per_gpu))
     assert int(snap[0].frames) == (args.steps * ticks * frames if pflags & cm.METER else 0), "meter did not see every timed tick"
@@ -422,7 +423,6 @@ def main():
                                  "note": "one tick of the same shape issued alone, outside the timed steps: device = between CUDA "
                                          "events; launch-to-complete = cmgpu_process + cmgpu_sync timed in C "
                                          "(cmgpu_time_single_tick, median / minimum of 200)"}
-    kernel = eng.kernel_name()
     peak, peak_src = measured_peak()
     launches_per_step = max(1, launches // max(args.steps, 1))
     alg_bytes = bytes_per_sample * samples_per_step_rank / launches_per_step        # per kernel launch

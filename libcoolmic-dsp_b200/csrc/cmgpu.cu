@@ -301,8 +301,10 @@ cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter, cud
         uint64_t grid = ((uint64_t)a.n_streams + 31u) / 32u;
         if (grid > (uint64_t)cap)
             grid = (uint64_t)cap;
+        snprintf(c->kname_last, sizeof(c->kname_last), "span_tick<C=%u> (%u ticks per launch)", c->channels, a.n_ticks);
         return launch_kernel(k, (unsigned)grid, 256, smem, st, pdl, a, vmax);
     }
+    c->kname_last[0] = 0;
     const uint64_t items = (uint64_t)a.n_streams * a.items_per_block * (a.n_ticks > 1 ? a.n_ticks : 1u);
     const uint64_t per_cta = c->plan_g > 0 ? 256u / (unsigned)c->plan_g : (c->plan_g < 0 ? 8u : 4u);
     uint64_t grid = (items + per_cta - 1) / per_cta;
@@ -330,10 +332,9 @@ void make_plan(cmgpu_ctx *c)
         const unsigned lanes = 32 - 32 % m;
         const uint32_t nvec = (uint32_t)(c->stride / 16);
         const uint32_t quantum = lanes * 8u;                      // two batches of 4 per lane
-        // Large items: this kernel has no cross-item prefetch (it spilled), so every item
-        // boundary exposes a load latency and a recipe gather. Measured on 6-channel streams
-        // (profiles/r2_*cfg6ch*): 2,048 vectors per item 0.81 of the copy rate, 4,096 0.85, 7,000 0.86;
-        // the epilogue's 16-bit sample index caps an item at 8,192 vectors.
+        // Large items: every item boundary costs an epilogue and a recipe gather. Measured on 6-channel
+        // streams with the cp.async ring (profiles/r2_*cfg6ch*): 2,048 vectors per item 0.89 of
+        // the copy rate, 4,096 0.94, 7,000 0.985; the epilogue's 16-bit sample index caps an item at 8,192.
         uint32_t target = 7000;
         if (const char *e = getenv("CMGPU_ITEM_VECS"))            // tuning hook
             target = (uint32_t)strtoul(e, nullptr, 10) ? (uint32_t)strtoul(e, nullptr, 10) : target;
@@ -1008,7 +1009,7 @@ const char *cmgpu_kernel_name(const cmgpu_ctx_t *c)
         return (c->channels == 8 && c->out_channels == 2 && !(c->flags & CMGPU_FORCE_GENERIC))
                    ? ((c->flags & CMGPU_MIX_OUTPUT_METER_ONLY) ? "mix8to2_tick<outputs metered>" : "mix8to2_tick")
                    : "mix_tick<generic>";
-    return c->kname;
+    return c->kname_last[0] ? c->kname_last : c->kname;       // (the span kernel is chosen per launch, not per context)
 }
 unsigned cmgpu_meter_row_u64(const cmgpu_ctx_t *c) { return c ? c->row_u64 : 0; }
 void *cmgpu_device_meters(cmgpu_ctx_t *c) { return c ? c->d_meters : nullptr; }

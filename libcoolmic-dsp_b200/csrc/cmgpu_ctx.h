@@ -155,6 +155,7 @@ struct cmgpu_ctx {
     int grid_cap[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // resident CTAs per (gain mode, meter) kernel
     int span_grid_cap[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // ... of the stream-major span kernel
     char kname[64] = "";
+    char kname_last[64] = "";     // set when the last launch used a kernel other than the context's plan (span_tick)
 };
 
 
