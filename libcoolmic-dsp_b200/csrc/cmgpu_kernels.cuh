@@ -321,7 +321,8 @@ __device__ __forceinline__ uint4 do_vector(uint4 w, const Recipe (&rc)[Shape<C>:
 // Optional second output: the encoder-side sample-format stage of
 // enc_vorbis.c:108-117 -- de-interleave and `sample / 32768.f` into one float plane per channel,
 // which is what vorbis_analysis_buffer() wants. The division by 2^15 is exact in binary32, so
-// multiplying by 2^-15 gives bit-identical floats. Only the PLANAR instantiations of the kernel call
+// multiplying by 2^-15 gives bit-identical floats (checked against the reference's own enc_vorbis.c
+// object code: tests/golden/planar.json, oracle/ref_enc_harness.c). Only the PLANAR instantiations of the kernel call
 // it (a run-time flag in the plain kernels cost them 2 %).
 template <int C>
 __device__ __forceinline__ void store_planar(float *planar, uint32_t plane_stride, uint32_t s, uint32_t v, uint4 o,

@@ -339,6 +339,16 @@ void oracle_batch(int16_t *pcm, size_t n_streams, size_t stride_samples, const u
     }
 }
 
+/* enc_vorbis.c:108-117: de-interleave, one division by 32768.f per sample (binary32) */
+void oracle_planar(const int16_t *in, size_t frames, unsigned channels, float *planes, size_t plane_stride)
+{
+    size_t f;
+    unsigned c;
+    for (f = 0; f < frames; f++)
+        for (c = 0; c < channels; c++)
+            planes[(size_t)c * plane_stride + f] = in[f * channels + c] / 32768.f;
+}
+
 /* EXTENSION CHECKER: see coolmic_oracle.h. No reference lines to cite for the mix itself. */
 void oracle_mix_process(const int16_t *in, size_t frames, unsigned cin, unsigned cout, uint16_t scale,
                         const uint16_t *w, int16_t *out, oracle_meter_t *min, oracle_meter_t *mout)

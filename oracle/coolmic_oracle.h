@@ -121,6 +121,12 @@ void oracle_batch(int16_t *pcm, size_t n_streams, size_t stride_samples, const u
 void oracle_mix_process(const int16_t *in, size_t frames, unsigned cin, unsigned cout, uint16_t scale,
                         const uint16_t *w, int16_t *out, oracle_meter_t *min, oracle_meter_t *mout);
 
+/* enc_vorbis.c:108-117 (__vorbis_read_data): the encoder-side sample-format stage -- interleaved S16 ->
+ * one float plane per channel, planes[c][f] = in[f * channels + c] / 32768.f (plane_stride floats apart).
+ * Pinned against the reference's own enc_vorbis.c object code (oracle/_ref/libcoolmic_refenc.so,
+ * tests/golden/planar.json). */
+void oracle_planar(const int16_t *in, size_t frames, unsigned channels, float *planes, size_t plane_stride);
+
 /* Multi-threaded form of oracle_batch for bench.py's cpu_baseline ("port"); returns seconds. */
 double oracle_batch_threads(int16_t *pcm, size_t n_streams, size_t stride_samples, const uint32_t *frames,
                             unsigned channels, const uint16_t *scale, const uint16_t *gain,

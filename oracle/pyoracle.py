@@ -10,6 +10,9 @@ ctypes bindings for the two CPU checkers built by oracle/Makefile:
   src/transform.c and src/vumeter.c were (oracle/Makefile). Same ``RefLib`` interface; every
   transform / vumeter read in it runs on the GPU through the product library. It is the thing
   being tested, not a checker. GPU tests only.
+* ``refenc`` -- oracle/_ref/libcoolmic_refenc.so: the reference's own src/enc_vorbis.c (unmodified)
+  behind oracle/ref_enc_harness.c and a header-only libvorbis stand-in: its S16 -> planar float
+  stage (enc_vorbis.c:76-122) as the oracle of the product's float planes. ``None`` when absent.
 * ``port`` -- oracle/_build/libcoolmic_port.so: our plain-C restatement (coolmic_oracle.c).
 
 May be imported only from tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs.
@@ -26,6 +29,7 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 REF_SO = HERE / "_ref" / "libcoolmic_ref.so"
 DROPIN_SO = HERE / "_ref" / "libcoolmic_dropin.so"
+REFENC_SO = HERE / "_ref" / "libcoolmic_refenc.so"
 PORT_SO = HERE / "_build" / "libcoolmic_port.so"
 MAX_CH = 16
 
@@ -293,6 +297,16 @@ class PortLib(_Lib):
                                     C.byref(meter_out) if meter_out is not None else None)
         return out
 
+    def planar(self, pcm, channels: int) -> np.ndarray:
+        """enc_vorbis.c:108-117: interleaved int16 -> float32 [channels][frames] = sample / 32768.f."""
+        src = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1)
+        frames = src.size // channels
+        out = np.zeros((channels, max(frames, 1)), dtype=np.float32)
+        self.lib.oracle_planar.restype = None
+        self.lib.oracle_planar.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t]
+        self.lib.oracle_planar(src.ctypes.data, frames, channels, out.ctypes.data, out.shape[1])
+        return out[:, :frames]
+
     def finalise(self, meter: Meter, rate: int, channels: int) -> dict:
         res = Result()
         rc = self.lib.oracle_meter_finalise(C.byref(meter), rate, channels, C.byref(res))
@@ -357,3 +371,41 @@ def ref():
         if REF_SO.exists():
             _ref = RefLib()
     return _ref
+
+
+class RefEncLib:
+    """The reference's own enc_vorbis.c sample-format stage (interleaved S16 -> planar float / 32768.f)."""
+
+    kind = "reference enc_vorbis.c"
+
+    def __init__(self, path: Path = REFENC_SO):
+        self.lib = C.CDLL(str(path))
+        self.lib.refenc_vorbis_planes.restype = C.c_long
+        self.lib.refenc_vorbis_planes.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_size_t]
+
+    def planes(self, pcm, channels: int) -> np.ndarray:
+        """int16 [frames * channels] interleaved -> float32 [channels][frames], as enc_vorbis.c writes them."""
+        src = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1)
+        frames = src.size // channels
+        out = np.full((channels, max(frames, 1)), np.nan, dtype=np.float32)
+        n = self.lib.refenc_vorbis_planes(src.ctypes.data, src.size * 2, channels, out.ctypes.data, out.shape[1])
+        if n != frames:
+            raise RuntimeError(f"refenc_vorbis_planes: {n} frames, expected {frames}")
+        return out[:, :frames]
+
+
+_refenc = None
+
+
+def refenc():
+    """RefEncLib or None (no prebuilt library and no /root/reference to build it from)."""
+    global _refenc
+    if _refenc is None:
+        if not REFENC_SO.exists():
+            try:
+                build()
+            except Exception:
+                pass
+        if REFENC_SO.exists():
+            _refenc = RefEncLib()
+    return _refenc

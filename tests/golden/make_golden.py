@@ -135,6 +135,23 @@ def main():
             "out_bytes": [int(b) for b in out], "results": [hexify(r) for r in results],
         })
     (OUT / "fuzz_pipeline.json").write_text(json.dumps(fuzz) + "\n")
+
+    # The encoder-side sample-format stage: the reference's own src/enc_vorbis.c,
+    # compiled unmodified against the libvorbis stand-in (oracle/Makefile target refenc), fed interleaved
+    # S16 and asked for its float planes. Bit patterns, so that comparisons are exact.
+    planar_file = OUT / "planar.json"
+    enc = po.refenc()
+    if enc is not None:
+        rng = np.random.default_rng(20260109)
+        planar = []
+        edge = np.array([-32768, -32767, -1, 0, 1, 2, 3, 255, 256, 12345, -12345, 32766, 32767, 21845, -21845, 16384], np.int16)
+        for ch, frames in [(1, 16), (2, 8), (1, 700), (2, 513), (3, 77), (4, 333), (6, 500), (8, 257), (16, 100), (5, 1)]:
+            pcm = rng.integers(-32768, 32768, size=ch * frames).astype(np.int16)
+            pcm[: min(edge.size, pcm.size)] = edge[: min(edge.size, pcm.size)]
+            planes = enc.planes(pcm, ch)
+            planar.append({"channels": ch, "frames": frames, "pcm": [int(v) for v in pcm],
+                           "planes_u32": [[int(v) for v in planes[c].view(np.uint32)] for c in range(ch)]})
+        planar_file.write_text(json.dumps(planar) + "\n")
     print("wrote", [p.name for p in sorted(OUT.glob("*.json"))])
 
 

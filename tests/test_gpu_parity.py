@@ -598,10 +598,13 @@ def test_stream_major_span(cm, port, monkeypatch, channels, block, ragged, ring,
 @pytest.mark.parametrize("channels,block", [(1, 320), (2, 1000), (2, 4799), (4, 333), (8, 257), (16, 100), (6, 500), (3, 77)])
 def test_planar_float_second_output(cm, port, channels, block):
     """the encoder-side sample-format stage (enc_vorbis.c:108-117: de-interleave,
-    sample / 32768.f) as an optional second output of the fused pass. Dividing an int16 by 2^15 is
-    exact in binary32, so the planes must equal numpy's float32 division bit for bit. The reference
-    file needs libvorbis and cannot be built here: this row is checked against that one-line
-    restatement only."""
+    sample / 32768.f) as an optional second output of the fused pass. The checker is the oracle
+    port's oracle_planar, which is pinned bit for bit to what the reference's OWN enc_vorbis.c writes
+    (compiled unmodified against a libvorbis stand-in, oracle/Makefile target refenc;
+    tests/golden/planar.json, tests/test_oracle.py) -- and, where that object code is present, it is
+    asked directly as well."""
+    from oracle import pyoracle
+    enc = pyoracle.refenc()
     rng = np.random.default_rng(channels + block)
     n_streams = 21
     with cm.Engine(channels, n_streams, block, flags=cm.PLANAR_F32) as eng:
@@ -623,14 +626,37 @@ def test_planar_float_second_output(cm, port, channels, block):
         check_meters(cm, port, eng, meters, n_streams, channels)
         for s in range(n_streams):
             n = int(frames[s])
-            y = want[s, : n * channels].reshape(n, channels)
-            ref = (y.astype(np.float32) / np.float32(32768.0)).T            # [channel][frame]
+            ref = port.planar(want[s, : n * channels], channels)                # [channel][frame]
             got = planes[s, :, :n]
             assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), ref.view(np.uint32)), f"stream {s}"
+            if enc is not None and n:
+                assert np.array_equal(got.view(np.uint32), enc.planes(want[s, : n * channels], channels).view(np.uint32)), f"stream {s}"
     with cm.Engine(2, 2, 16) as eng:                                       # no plane ring: the flag is refused
         eng.submit(0)
         with pytest.raises(cm.CmgpuError):
             eng.process(0, cm.FUSED | cm.PLANAR)
+
+
+PLANAR_GOLD = json.loads((GOLD / "planar.json").read_text()) if (GOLD / "planar.json").exists() else []
+
+
+@pytest.mark.parametrize("case", PLANAR_GOLD, ids=lambda k: f"{k['channels']}ch_{k['frames']}f")
+def test_planar_golden_from_reference_enc_vorbis(cm, case):
+    """The float planes the reference's own enc_vorbis.c wrote for these inputs (tests/golden/planar.json),
+    reproduced by the device's second output with the gain off (the encoder sees the transform's output;
+    with no gain that is the input)."""
+    channels, frames = case["channels"], case["frames"]
+    pcm = np.array(case["pcm"], dtype=np.int16)
+    with cm.Engine(channels, 3, frames, flags=cm.PLANAR_F32) as eng:
+        host = eng.host_slot(0)
+        host[:] = 0
+        host[1, : frames * channels] = pcm
+        eng.submit(0)
+        eng.process(0, cm.FUSED | cm.PLANAR)
+        planes = eng.fetch_planar(0)
+        eng.sync()
+        want = np.array(case["planes_u32"], dtype=np.uint32)
+        assert np.array_equal(planes[1, :, :frames].view(np.uint32), want)
 
 
 def test_opus_sized_blocks(cm, port):

@@ -180,3 +180,33 @@ def test_gain_adapt_matches_reference_cases(port):
     assert port.gain_adapt(2, 0, 10, [1, 2], state=(5, [9, 9]))[:2] == (0, 0)
     assert port.gain_adapt(2, 2, 0, [1, 2], state=(5, [9, 9]))[:2] == (0, 0)
     assert port.gain_adapt(2, 2, 9, None, state=(5, [9, 9]))[:2] == (0, 0)
+
+
+# ---- the encoder-side sample-format stage (enc_vorbis.c:108-117) ---------------------
+PLANAR = json.loads((GOLD / "planar.json").read_text()) if (GOLD / "planar.json").exists() else []
+
+
+@pytest.mark.parametrize("case", PLANAR, ids=lambda k: f"{k['channels']}ch_{k['frames']}f")
+def test_planar_port_matches_reference_enc_vorbis_fixture(port, case):
+    """oracle_planar (the port of enc_vorbis.c:108-117) against planes the reference's OWN enc_vorbis.c wrote
+    (tests/golden/planar.json, generated by make_golden.py through oracle/_ref/libcoolmic_refenc.so)."""
+    pcm = np.array(case["pcm"], dtype=np.int16)
+    got = port.planar(pcm, case["channels"])
+    want = np.array(case["planes_u32"], dtype=np.uint32)
+    assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want)
+
+
+def test_planar_port_matches_reference_enc_vorbis_live(port):
+    """... and against that object code run here on fresh inputs, every channel count, odd lengths."""
+    from oracle import pyoracle
+    enc = pyoracle.refenc()
+    if enc is None:
+        pytest.skip("oracle/_ref/libcoolmic_refenc.so is not available here")
+    rng = np.random.default_rng(99)
+    for ch in range(1, 17):
+        frames = int(rng.integers(1, 3000))
+        pcm = rng.integers(-32768, 32768, size=ch * frames).astype(np.int16)
+        assert np.array_equal(port.planar(pcm, ch).view(np.uint32), enc.planes(pcm, ch).view(np.uint32)), ch
+    # all 65,536 sample values
+    allx = np.arange(-32768, 32768, dtype=np.int16)
+    assert np.array_equal(port.planar(allx, 1).view(np.uint32), enc.planes(allx, 1).view(np.uint32))
