@@ -34,5 +34,5 @@ cap cfg4b mix8to2 mix8to2_cfg4b
 cap cfg4c mix8to2 mix8to2_cfg4c
 cap cfg3 span_tick span_tick_cfg3
 cap cfg2p fused_tick fused_tick_cfg2p
-cp profiles/traffic.json $O/traffic.json
+cp $O/traffic.json $O/traffic_from_this_run.json 2>/dev/null
 ls -la $O; du -sh $O

@@ -48,9 +48,10 @@ def main():
             if k in vals:
                 lines.append(f"{k:75s} {vals[k][0]:>16s} {vals[k][1]}")
         try:
-            rd = float(vals["dram__bytes_read.sum"][0]); wr = float(vals["dram__bytes_write.sum"][0])
-            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[vals["dram__bytes_read.sum"][1]]
-            traffic = (rd + wr) * scale
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            rd = float(vals["dram__bytes_read.sum"][0]) * scale[vals["dram__bytes_read.sum"][1]]
+            wr = float(vals["dram__bytes_write.sum"][0]) * scale[vals["dram__bytes_write.sum"][1]]
+            traffic = rd + wr
             lines.append(f"{'dram bytes read+write per launch':75s} {traffic:16.0f} byte")
         except Exception:
             pass
