@@ -283,7 +283,7 @@ cudaError_t launch_tick(cmgpu_ctx *c, const TickArgs &a, int gm, bool meter, cud
     }
     // Small-buffer spans with enough streams to fill the machine with 8-lane groups: one group per STREAM
     // walks all ticks of the span and publishes its meter partials once (cmgpu_span.cuh)
-    if (a.n_ticks > 1 && c->plan_g == 8 && c->channels <= 8 && !a.planar && a.n_ticks <= cmgpu::kSpanMaxTicks &&
+    if ((a.n_ticks > 1 || c->env_span_single) && c->plan_g == 8 && c->channels <= 8 && !a.planar && a.n_ticks <= cmgpu::kSpanMaxTicks &&
         !c->env_span_by_tick && (c->env_span_by_stream || (uint64_t)a.n_streams * 8u * 2u >= (uint64_t)c->num_sms * 1024u)) {
         SpanKernel k = span_kernel(c, gm, meter);
         const uint32_t vmax = (uint32_t)((c->stride / 16 + 7) / 8);          // vectors of a stream-block per lane, <= 8
@@ -796,7 +796,8 @@ static cmgpu_ctx_t *ctx_create_impl(int device, unsigned channels, unsigned out_
     c->env_no_span = getenv("CMGPU_NO_SPAN") != nullptr;
     c->env_static = getenv("CMGPU_STATIC_ITEMS") != nullptr;
     c->env_span_by_tick = getenv("CMGPU_SPAN_BY_TICK") != nullptr;    // A/B hook: spans as (tick, stream) work items
-    c->env_span_by_stream = getenv("CMGPU_SPAN_BY_STREAM") != nullptr;    // test hook: stream-major spans for any stream count
+    c->env_span_by_stream = getenv("CMGPU_SPAN_BY_STREAM") != nullptr;
+    c->env_span_single = getenv("CMGPU_SPAN_SINGLE") != nullptr;        // A/B hook: single ticks through the span kernel too    // test hook: stream-major spans for any stream count
     c->channels = channels;
     c->max_streams = c->active = max_streams;
     c->slots = ring_slots;

@@ -62,7 +62,7 @@ struct cmgpu_ctx {
     uint64_t launches = 0;
     int num_sms = 0;
     // environment hooks, read ONCE at cmgpu_ctx_create (never on the launch path)
-    bool env_no_pdl = false, env_no_span = false, env_static = false, env_span_by_tick = false, env_span_by_stream = false;
+    bool env_no_pdl = false, env_no_span = false, env_static = false, env_span_by_tick = false, env_span_by_stream = false, env_span_single = false;
     // work-claim counters (TickArgs::work): launch number n uses counter n % kWorkCounters; each only grows,
     // work_base[] is its value when the next launch that uses it starts (host arithmetic, no resets)
     static constexpr unsigned kWorkCounters = 8;
