@@ -274,10 +274,12 @@ int cmgpu_gather_results(cmgpu_ctx_t *c, cmgpu_comm_t *m, int root, uint32_t rat
     CU(cudaGetLastError());
     if (m->rank == root) {
         NC(ncclGroupStart());
-        for (int r = 0; r < m->size; r++)
+        ncclResult_t gr = ncclSuccess;
+        for (int r = 0; r < m->size && gr == ncclSuccess; r++)
             if (r != root)
-                NC(ncclRecv(m->d_counts + r, 1, ncclUint32, r, m->nccl, st));
-        NC(ncclGroupEnd());
+                gr = ncclRecv(m->d_counts + r, 1, ncclUint32, r, m->nccl, st);
+        NC(ncclGroupEnd());                             // (closed before any error return: no group is left open)
+        NC(gr);
         CU(cudaMemcpyAsync(m->h_counts, m->d_counts, sizeof(unsigned) * (size_t)m->size, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     } else {
@@ -308,13 +310,15 @@ int cmgpu_gather_results(cmgpu_ctx_t *c, cmgpu_comm_t *m, int root, uint32_t rat
         }
         size_t off = 0;
         NC(ncclGroupStart());
-        for (int r = 0; r < m->size; r++) {
+        ncclResult_t gr = ncclSuccess;
+        for (int r = 0; r < m->size && gr == ncclSuccess; r++) {
             const size_t n = (size_t)m->h_counts[r] * row;
             if (r != root && n)
-                NC(ncclRecv(m->d_gather + off, n, ncclUint64, r, m->nccl, st));
+                gr = ncclRecv(m->d_gather + off, n, ncclUint64, r, m->nccl, st);
             off += n;
         }
         NC(ncclGroupEnd());
+        NC(gr);
         off = 0;
         for (int r = 0; r < root; r++)
             off += (size_t)m->h_counts[r] * row;

@@ -397,9 +397,9 @@ void *shim_batch_cursor_new(coolmic_b200_batch_t *b, unsigned stream)
     if (!c)
         return NULL;
     c->stream = stream;
-    c->epoch = b->epoch;                               /* a new reader starts at the next tick's output */
     c->offset = 0;
     pthread_mutex_lock(&b->cursor_mu);
+    c->epoch = b->epoch;                               /* a new reader starts at the next tick's output */
     c->next = b->cursors;
     b->cursors = c;
     pthread_mutex_unlock(&b->cursor_mu);

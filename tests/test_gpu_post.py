@@ -280,6 +280,83 @@ def test_passthrough_slots_are_not_downloaded(cm, port):
         assert np.array_equal(out, src) and eng.transfer_bytes()[1] == 2 * down2
 
 
+def test_claimed_work_items_under_overlapping_launches(cm, port):
+    """Dynamic work claims (TickArgs::work): counters that only grow, one of eight per launch, the base
+    handed over by the host. 160 ticks in random slot order with a separate output ring (so the chain of
+    overlapping launches never closes) while the number of active streams -- and with it the grid, and
+    whether a launch claims dynamically or stays static -- keeps changing. Every stream's meter must
+    equal the oracle's over exactly the ticks it took part in."""
+    rng = np.random.default_rng(77)
+    channels, n_streams, block, ring = 2, 2400, 3000, 6
+    with cm.Engine(channels, n_streams, block, ring_slots=ring, flags=cm.SEPARATE_OUT) as eng:
+        scale, gain = make_gains(rng, n_streams, channels)
+        eng.set_gain_table(scale, gain)
+        data = make_pcm(rng, "ties", (ring, n_streams, block * channels))
+        for slot in range(ring):
+            eng.host_slot(slot)[:, : block * channels] = data[slot]
+            eng.submit(slot)
+        eng.sync()
+        order = []
+        for i in range(160):
+            active = int(rng.choice([7, 60, 300, 1200, n_streams]))
+            slot = int(rng.integers(0, ring))
+            eng.set_active(active)
+            eng.process(slot)
+            order.append((slot, active))
+        eng.set_active(n_streams)
+        snap = eng.snapshot()
+        # oracle: ticks in issue order (first-occurrence peaks depend on it)
+        meters = None
+        for slot, active in order:
+            fr = np.zeros(n_streams, np.uint32)
+            fr[:active] = block
+            work = data[slot].copy()
+            meters, _ = port.batch(work, fr, channels, scale, gain, meters=meters, threads=8)
+        for s in range(n_streams):
+            assert int(snap[s].frames) == int(meters[s].frames), f"stream {s}"
+            for c in range(channels):
+                assert int(snap[s].power[c]) == int(meters[s].power[c]), f"stream {s} ch {c}"
+                assert int(snap[s].channel_peak[c]) == int(meters[s].channel_peak[c]), f"stream {s} ch {c}"
+            assert int(snap[s].global_peak) == int(meters[s].global_peak)
+
+
+def test_adopting_a_communicator_made_elsewhere(cm, port):
+    """cmgpu_comm_adopt: an ncclComm_t the application already has (made here with libnccl directly) is
+    used for the gather and NOT destroyed by cmgpu_comm_destroy."""
+    nccl = C.CDLL("libnccl.so.2")
+    uid = (C.c_ubyte * 128)()
+    assert nccl.ncclGetUniqueId(uid) == 0
+
+    class Uid(C.Structure):
+        _fields_ = [("b", C.c_ubyte * 128)]
+
+    comm = C.c_void_p()
+    nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, Uid, C.c_int]
+    u = Uid()
+    C.memmove(u.b, uid, 128)
+    with cm.Engine(2, 50, 480) as eng:                   # (creates the CUDA context on device 0 first)
+        assert nccl.ncclCommInitRank(C.byref(comm), 1, u, 0) == 0
+        lib = cm.lib()
+        mine = lib.cmgpu_comm_adopt(comm, 0)
+        assert mine and lib.cmgpu_comm_size(mine) == 1 and lib.cmgpu_comm_rank(mine) == 0
+        rng = np.random.default_rng(3)
+        meters = _run_ticks(cm, port, eng, rng, 50, 2, 480, n_ticks=2)
+        res = (cm.Result * 50)()
+        rcs = (C.c_int * 50)()
+        counts = (C.c_uint * 1)()
+        assert lib.cmgpu_gather_results(eng.ctx, mine, 0, 48000, 1, res, None, rcs, counts) == 0
+        assert counts[0] == 50 and all(rc == 0 for rc in rcs)
+        for s in range(50):
+            assert same_result(res[s].as_dict(), port.finalise(meters[s], 48000, 2))
+        lib.cmgpu_comm_destroy(mine)
+        # still usable: the adopted communicator was not destroyed
+        n = C.c_int(0)
+        nccl.ncclCommCount.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        assert nccl.ncclCommCount(comm, C.byref(n)) == 0 and n.value == 1
+        nccl.ncclCommDestroy.argtypes = [C.c_void_p]
+        assert nccl.ncclCommDestroy(comm) == 0
+
+
 def _gather_ranks(tmp_path, nranks, total_streams, channels):
     path = tmp_path / "nccl.id"
     procs = []
