@@ -725,7 +725,7 @@ int tick_waits_locked(cmgpu_ctx *c, unsigned slot)
 
 extern "C" {
 
-const char *cmgpu_version(void) { return "coolmic-b200 0.1 (sm_100a)"; }
+const char *cmgpu_version(void) { return "coolmic-b200 0.2 (sm_100a)"; }
 
 const char *cmgpu_last_error(void) { return cmgpu::g_err; }
 
