@@ -73,6 +73,15 @@ WORKLOADS = {
                   e2e_frames=9600, e2e_ticks=10, mix_out=2, bytes_per_sample=2.5, sstep=7, cstep=5, out_meter_only=True,
                   desc="EXTENSION, PARITY UNPINNED: cfg4b with only the 2 OUTPUT channels metered "
                        "(CMGPU_MIX_OUTPUT_METER_ONLY), not the 8 inputs"),
+    "cfg1ch": dict(channels=1, streams=8192, rate=48000, frames=96000, ticks=1, ring=1, graph=False,
+                   e2e_frames=4800, e2e_ticks=10, sstep=7, cstep=0,
+                   desc="DIAGNOSTIC: 8,192 x 48 kHz mono streams x 2 s per GPU"),
+    "cfg4ch": dict(channels=4, streams=4096, rate=48000, frames=96000, ticks=1, ring=1, graph=False,
+                   e2e_frames=4800, e2e_ticks=10, sstep=7, cstep=3,
+                   desc="DIAGNOSTIC: 4,096 x 48 kHz 4-channel streams x 2 s per GPU"),
+    "cfg16ch": dict(channels=16, streams=2048, rate=48000, frames=96000, ticks=1, ring=1, graph=False,
+                    e2e_frames=2400, e2e_ticks=10, sstep=7, cstep=3,
+                    desc="DIAGNOSTIC: 2,048 x 48 kHz 16-channel streams x 2 s per GPU (the maximum, transform.h:35)"),
     "cfg2p": dict(channels=2, streams=1024, rate=48000, frames=240000, ticks=1, ring=1, graph=False, planar=True,
                   bytes_per_sample=8.0, e2e_frames=12000, e2e_ticks=20, sstep=7, cstep=3,
                   desc="DIAGNOSTIC (SURVEY 8f N2): cfg2 x 5 s with the float-plane second output (S16 -> planar float "
