@@ -82,6 +82,10 @@ WORKLOADS = {
     "cfg16ch": dict(channels=16, streams=2048, rate=48000, frames=96000, ticks=1, ring=1, graph=False,
                     e2e_frames=2400, e2e_ticks=10, sstep=7, cstep=3,
                     desc="DIAGNOSTIC: 2,048 x 48 kHz 16-channel streams x 2 s per GPU (the maximum, transform.h:35)"),
+    "cfg5pt": dict(channels=2, streams=65536, rate=48000, frames=48000, ticks=1, ring=1, graph=False, passthrough=True,
+                   bytes_per_sample=2.0, e2e_frames=4800, e2e_ticks=10, strong=True, sstep=7, cstep=3,
+                   desc="DIAGNOSTIC: cfg5 with every stream in the reference's default state (no master gain, "
+                        "transform.c:107-108): in place, metered only, nothing written -- 2 B read per sample"),
     "cfg2p": dict(channels=2, streams=1024, rate=48000, frames=240000, ticks=1, ring=1, graph=False, planar=True,
                   bytes_per_sample=8.0, e2e_frames=12000, e2e_ticks=20, sstep=7, cstep=3,
                   desc="DIAGNOSTIC (SURVEY 8f N2): cfg2 x 5 s with the float-plane second output (S16 -> planar float "
@@ -364,7 +368,11 @@ def main():
     planar = bool(wl.get("planar"))
     bytes_per_sample = wl.get("bytes_per_sample", 4.0)
 
+    passthrough = bool(wl.get("passthrough"))
+
     def configure(e):
+        if passthrough:
+            return                      # no gain set: transform.c:107-108
         if mix_out:
             mscale, mw = mix_table(first_stream, streams_per_gpu, channels, mix_out)
             for i in range(streams_per_gpu):
@@ -373,7 +381,7 @@ def main():
             e.set_gain_table(scale, gain)
 
     eng = cm.Engine(channels, streams_per_gpu, frames, ring_slots=ring, device=local,
-                    flags=cm.NO_PINNED | (0 if mix_out else cm.SEPARATE_OUT) | (cm.PLANAR_F32 if planar else 0) | mix_flags,
+                    flags=cm.NO_PINNED | (0 if (mix_out or passthrough) else cm.SEPARATE_OUT) | (cm.PLANAR_F32 if planar else 0) | mix_flags,
                     out_channels=mix_out)
     configure(eng)
     eng.tone_table(period)
@@ -467,7 +475,7 @@ def main():
                                  "frac": sus / peak, "clocks": clk_sus}
     eng.close()
 
-    if not args.no_extras and not wl["graph"] and args.mode == "fused" and not mix_out and not planar:
+    if not args.no_extras and not wl["graph"] and args.mode == "fused" and not mix_out and not planar and not passthrough:
         # (b) the in-place figure: ONE slot transformed in place (what the reference does, transform.c:120),
         #     where the overlap rule forbids consecutive launches to overlap: each tick is a full dependency
         e2 = cm.Engine(channels, streams_per_gpu, frames, ring_slots=1, device=local, flags=cm.NO_PINNED)

@@ -458,11 +458,12 @@ __device__ __forceinline__ void item_publish(const TickArgs &a, const Item &it, 
     static_assert(MERGE || C >= 8, "narrow frames keep one running key per channel (do_vector<MERGE>)");
     constexpr int P = Shape<C>::kPerLane;
     constexpr int S = (C <= 8) ? 8 / P : 1;      // slots of one channel in a vector (= frames per vector)
-    // Where the tick number is read is measured, not guessed (A/B on B200): warps that walk long
-    // items want it requested first, so that its latency hides behind the shuffle rounds instead of
-    // adding to the re-read's (cfg5: 3 %); the 8-lane groups of the small-buffer regime, where the
-    // epilogue is a third of all instructions, are 6 % faster reading it only in the publishing lanes.
-    constexpr bool kEarlyTick = G > 8;
+    // The tick number is requested first, so that its latency hides behind the shuffle rounds instead of
+    // adding to the re-read's (cfg5: 3 %). The 8-lane groups used to read it late, in the publishing
+    // lanes only (6 % faster when they walked config 3's spans); spans with many streams now run in
+    // span_tick, and what is left for them -- single ticks, where the dependent latency chain of the
+    // epilogue is the kernel's tail -- wants the early read as well.
+    constexpr bool kEarlyTick = true;
     uint64_t pos_base = 0;
     if (kEarlyTick)
         pos_base = tick_pos_base(a.tick, a.tick_offset + it.tk, a.pbits);
