@@ -143,32 +143,37 @@ int cmgpu_submit(cmgpu_ctx_t *ctx, unsigned slot, const void *host);
 int cmgpu_process(cmgpu_ctx_t *ctx, unsigned slot, unsigned flags);
 /* Small-buffer regime: `n_slots` consecutive ticks (slots first_slot ..) issued as ONE launch that
  * walks all of them (the ring is one allocation), so that per-tick launch latency does not
- * dominate 20 ms blocks; contexts whose kernels cannot do that (channel counts that do not tile 16
+ * dominate 20 ms blocks -- with enough streams to fill the GPU, one 8-lane group per STREAM that keeps
+ * its meter partials in registers across the ticks and publishes them once; contexts whose kernels
+ * cannot do that (channel counts that do not tile 16
  * bytes, downmix, float planes, frame counts set for only some of the slots) get ONE cached CUDA
  * graph of per-tick launches instead, rebuilt when gains, frames or the active stream count
  * change. Either way the ticks count as slots first_slot, first_slot + 1, ... in time order.
  * Ordered after the slots' last submits. Asynchronous. */
 int cmgpu_process_cycle(cmgpu_ctx_t *ctx, unsigned first_slot, unsigned n_slots, unsigned flags);
 /* Device -> host copy of the slot's (transformed) PCM on the download stream, ordered after
- * the slot's last tick. `host` NULL = the pinned staging slot. Asynchronous if page-locked. */
+ * the slot's last tick. `host` NULL = the pinned staging slot. Asynchronous if page-locked.
+ * The download is skipped when it could only copy the input onto itself: in-place context, `host`
+ * NULL after a submit with `host` NULL, and no tick has written the slot's PCM since -- pass-through
+ * streams, the reference's default state (transform.c:107-108), are metered without a byte coming
+ * back. cmgpu_transfer_bytes reports what submit / fetch have really copied. */
 int cmgpu_fetch(cmgpu_ctx_t *ctx, unsigned slot, void *host);
+int cmgpu_transfer_bytes(const cmgpu_ctx_t *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 /* Float planes of a slot (CMGPU_PLANAR): [stream][channel][cmgpu_plane_stride()] float, valid for
  * the stream's frames of the tick. Device pointer, and a download like cmgpu_fetch (`host` must be
  * given: max_streams * channels * plane_stride floats). */
 void  *cmgpu_device_planar_slot(cmgpu_ctx_t *ctx, unsigned slot);
 size_t cmgpu_plane_stride(const cmgpu_ctx_t *ctx);           /* in floats */
 int    cmgpu_fetch_planar(cmgpu_ctx_t *ctx, unsigned slot, float *host);
-/* (A download is skipped when it could only copy the input onto itself: in-place context, `host` NULL
- * after a submit with `host` NULL, and no tick has written the slot's PCM since -- pass-through
- * streams, the reference's default state (transform.c:107-108), are metered without a byte coming
- * back. cmgpu_transfer_bytes reports what submit / fetch have really copied.) */
-int cmgpu_transfer_bytes(const cmgpu_ctx_t *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 /* Wait for everything queued on the context. */
 int cmgpu_sync(cmgpu_ctx_t *ctx);
 /* Wait until the slot's last fetch (or tick, if none) has completed. */
 int cmgpu_slot_wait(cmgpu_ctx_t *ctx, unsigned slot);
 
-/* ---- meters (replaces coolmic_vumeter_read/result/reset, vumeter.c:93-99,138-218) ------ */
+/* ---- meters (replaces coolmic_vumeter_read/result/reset, vumeter.c:93-99,138-218) ------
+ * "First occurrence" of a peak is kept across ticks by a position key that holds 46 - ceil(log2
+ * block_frames) bits of tick number: one meter window (reset to result) may span that many ticks --
+ * 2^33 at 4,800-frame ticks. A reset / result of ALL streams starts the count again. */
 /* Integer state of streams [first, first+count), waiting for queued ticks first. With
  * `reset` the device state is cleared in the same stream-ordered step. */
 int cmgpu_meter_snapshot(cmgpu_ctx_t *ctx, unsigned first, unsigned count,
