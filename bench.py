@@ -733,7 +733,7 @@ def spot_check(cm, synth, wl, period, streams_per_gpu, world, channels, tick_fra
             f"doubles on all, as gathered by cmgpu_gather_results)")
 
 
-def object_api_leg(cm, synth, device):
+def object_api_leg(cm, synth, device, threads=None, slots=4, block=12000, n_ticks=40):
     """The path a libcoolmic-dsp maintainer would call (src/simple.c:212-229,445-505 with
     coolmic_b200_batch_tick in place of the per-stream pull loop): 1,024 member transforms fed by memory
     iohandles, fused meters, every transform's output read back through its iohandle -- the reference-
@@ -745,7 +745,8 @@ def object_api_leg(cm, synth, device):
     fn.restype = C.c_int
     fn.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_void_p,
                    C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
-    streams, channels, block, n_ticks, slots, threads = 1024, 2, 12000, 40, 4, max(1, min(16, os.cpu_count() or 1))
+    streams, channels = 1024, 2
+    threads = threads or max(1, min(16, os.cpu_count() or 1))
     period = synth.load_period(48000)
     pcm = np.ascontiguousarray(synth.synth_rows(period, 0, streams, channels, block * 4, 0, 7, 3, NOISE_EVERY, NOISE_PHASE))
     secs = C.c_double(0)
@@ -758,11 +759,34 @@ def object_api_leg(cm, synth, device):
             return {"error": f"coolmic_b200_bench_objects: {rc}"}
         best = secs.value if best is None else min(best, secs.value)
     samples = streams * channels * block * n_ticks
-    return {"through": "coolmic_b200_batch_tick + coolmic_iohandle_read on 1,024 member transforms (memory iohandles in, "
-                       "per-transform handles out), fused vumeters, coolmic_vumeter_result per stream at the end",
-            "value": samples / best / 1e6, "unit": "Msamples/s", "ms_per_step": best * 1e3,
-            "shape": f"{streams} x stereo x {block} frames x {n_ticks} ticks, {slots}-slot ring, {threads} host threads",
-            "frames_metered_checksum": int(check.value)}
+    out = {"through": "coolmic_b200_batch_tick + coolmic_iohandle_read on 1,024 member transforms (memory iohandles in, "
+                      "per-transform handles out), fused vumeters, coolmic_vumeter_result per stream at the end",
+           "value": samples / best / 1e6, "unit": "Msamples/s", "ms_per_step": best * 1e3,
+           "shape": f"{streams} x stereo x {block} frames x {n_ticks} ticks, {slots}-slot ring, {threads} host threads",
+           "frames_metered_checksum": int(check.value)}
+    alone = host_loop_alone(threads, slots, streams, block, n_ticks)
+    if alone:
+        out["host_loop_alone"] = alone
+    return out
+
+
+def host_loop_alone(threads, slots, streams, block, n_ticks):
+    """The ceiling of the object-API leg on this host: the same driver and the same object code linked against
+    an engine whose calls return at once (tools/hostprobe), i.e. only the two host copies per sample the
+    iohandle contract costs (source -> pinned slot, pinned slot -> consumer). Diagnostic, no GPU involved."""
+    exe = os.path.join(ROOT, "tools", "hostprobe", "hostloop")
+    try:
+        if not os.path.exists(exe):
+            subprocess.run(["make", "-C", os.path.dirname(exe), "hostloop"], capture_output=True, timeout=120)
+        r = subprocess.run([exe, str(threads), str(slots), str(streams), str(block), str(n_ticks)], capture_output=True,
+                           text=True, timeout=120)
+        f = r.stdout.split()
+        secs = float(f[f.index("seconds") + 1])
+        return {"value": streams * 2 * block * n_ticks / secs / 1e6, "unit": "Msamples/s", "ms_per_step": secs * 1e3,
+                "note": "the object-API driver on an engine that returns at once: the host copies alone (no DMA competing "
+                        "for host memory); no GPU run through the objects can be faster on this host"}
+    except Exception:
+        return None
 
 
 if __name__ == "__main__":

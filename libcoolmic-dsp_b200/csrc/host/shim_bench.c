@@ -10,11 +10,50 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#define SHIM_BENCH_STREAMING 1
+#endif
 
 typedef struct cyc_src {
     const unsigned char *data;
     size_t len, pos;
+    int streaming;
 } cyc_src_t;
+
+/* What a capture device does when it fills the buffer it was handed: the destination is a pinned ring
+ * slot that the CPU never reads again (the copy engine does), so the bulk goes out with non-temporal
+ * stores -- no read-for-ownership of the destination lines, no cache pollution. COOLMIC_B200_BENCH_PLAIN_COPY=1
+ * falls back to memcpy (A/B). */
+static void capture_copy(void *dst, const void *src, size_t n, int streaming)
+{
+#ifdef SHIM_BENCH_STREAMING
+    unsigned char *d = dst;
+    const unsigned char *s = src;
+    if (streaming && n >= 256) {
+        const size_t head = (size_t)(-(uintptr_t)d & 15u);
+        size_t i;
+        memcpy(d, s, head);
+        d += head; s += head; n -= head;
+        for (i = 0; i + 64 <= n; i += 64) {
+            const __m128i a = _mm_loadu_si128((const __m128i *)(s + i));
+            const __m128i b = _mm_loadu_si128((const __m128i *)(s + i + 16));
+            const __m128i c = _mm_loadu_si128((const __m128i *)(s + i + 32));
+            const __m128i e = _mm_loadu_si128((const __m128i *)(s + i + 48));
+            _mm_stream_si128((__m128i *)(d + i), a);
+            _mm_stream_si128((__m128i *)(d + i + 16), b);
+            _mm_stream_si128((__m128i *)(d + i + 32), c);
+            _mm_stream_si128((__m128i *)(d + i + 48), e);
+        }
+        _mm_sfence();
+        memcpy(d + i, s + i, n - i);
+        return;
+    }
+#else
+    (void)streaming;
+#endif
+    memcpy(dst, src, n);
+}
 
 static ssize_t cyc_read(void *userdata, void *buffer, size_t len)
 {
@@ -22,7 +61,7 @@ static ssize_t cyc_read(void *userdata, void *buffer, size_t len)
     size_t n = m->len - m->pos;
     if (n > len)
         n = len;
-    memcpy(buffer, m->data + m->pos, n);
+    capture_copy(buffer, m->data + m->pos, n, m->streaming);
     m->pos += n;
     if (m->pos == m->len)
         m->pos = 0;                     /* endless, like a capture device */
@@ -138,6 +177,8 @@ int coolmic_b200_bench_objects(int device, unsigned int channels, unsigned int s
     struct timespec t0, t1;
     unsigned s, t, i, lag;
     int rc = COOLMIC_ERROR_NONE;
+    const char *env;
+    const int streaming = !((env = getenv("COOLMIC_B200_BENCH_PLAIN_COPY")) && *env == '1');
 
     if (!pcm || !seconds || !frames_metered || !streams || !threads || !ring_slots || !n_ticks ||
         bytes_per_stream % (2u * channels))
@@ -174,6 +215,7 @@ int coolmic_b200_bench_objects(int device, unsigned int channels, unsigned int s
             gain[i] = (uint16_t)((uint32_t)scale * 3u / 4u + 37u * ((s + i) % 64u));
         src[s].data = (const unsigned char *)pcm + (size_t)s * bytes_per_stream;
         src[s].len = bytes_per_stream;
+        src[s].streaming = streaming;
         tr[s] = coolmic_b200_batch_transform_new(batch, "tr", SHIM_RO_NULL, 48000);
         in = coolmic_iohandle_new("mem", SHIM_RO_NULL, &src[s], NULL, cyc_read, NULL);
         if (!tr[s] || !in) {
