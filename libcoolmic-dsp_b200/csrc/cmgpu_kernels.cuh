@@ -39,6 +39,9 @@
 #ifndef CMGPU_G8_CTAS
 #define CMGPU_G8_CTAS 4
 #endif
+#ifndef CMGPU_G8_CTAS_STEREO
+#define CMGPU_G8_CTAS_STEREO 3   // 80 registers: at 4 (64 registers) the stereo 8-lane kernels spilled 52-96 bytes
+#endif
 #ifndef CMGPU_G8_CTAS_WIDE
 #define CMGPU_G8_CTAS_WIDE 2
 #endif
@@ -243,7 +246,7 @@ struct Shape {
 template <int C, int G>
 struct Tune {
     static constexpr int kUnroll = (G == 8) ? 4 : (C >= 4 ? CMGPU_UNROLL_WIDE : CMGPU_UNROLL);
-    static constexpr int kMinCtas = (G == 8) ? (C >= 4 ? CMGPU_G8_CTAS_WIDE : CMGPU_G8_CTAS) : (C >= 4 ? CMGPU_MIN_CTAS_WIDE : CMGPU_MIN_CTAS);
+    static constexpr int kMinCtas = (G == 8) ? (C >= 4 ? CMGPU_G8_CTAS_WIDE : (C == 2 ? CMGPU_G8_CTAS_STEREO : CMGPU_G8_CTAS)) : (C >= 4 ? CMGPU_MIN_CTAS_WIDE : CMGPU_MIN_CTAS);
     static constexpr bool kSatPack = CMGPU_SATPACK_ALL ? true : ((G == 8) || (C >= 4));
 };
 
