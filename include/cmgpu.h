@@ -318,6 +318,9 @@ int cmgpu_link_probe(int device, size_t bytes, unsigned reps, int write_combined
 int cmgpu_debug_violations(void);
 /* Number of kernel launches this context has issued so far. */
 uint64_t cmgpu_launch_count(const cmgpu_ctx_t *ctx);
+/* How many cmgpu_sync calls saw the compute stream's end through the completion word of its last tick
+ * launch (a word of mapped host memory the launch's last CTA writes) instead of asking the driver. */
+uint64_t cmgpu_word_waits(const cmgpu_ctx_t *ctx);
 /* Name of the kernel variant cmgpu_process would pick for the current shape (for logs). */
 const char *cmgpu_kernel_name(const cmgpu_ctx_t *ctx);
 

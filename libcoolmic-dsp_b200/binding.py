@@ -125,6 +125,7 @@ SYMBOLS = {
                                    C.POINTER(C.c_float)]),
     "cmgpu_debug_violations": (C.c_int, []),
     "cmgpu_launch_count": (C.c_uint64, [_P]),
+    "cmgpu_word_waits": (C.c_uint64, [_P]),
     "cmgpu_kernel_name": (C.c_char_p, [_P]),
     "cmgpu_meter_results": (C.c_int, [_P, C.c_uint, C.c_uint, C.c_uint32, C.c_int, C.c_uint, C.POINTER(Result),
                                       C.POINTER(MeterState), C.POINTER(C.c_int)]),
@@ -408,6 +409,9 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self.L.cmgpu_launch_count(self.ctx))
+
+    def word_waits(self) -> int:
+        return int(self.L.cmgpu_word_waits(self.ctx))
 
     def kernel_name(self) -> str:
         return self.L.cmgpu_kernel_name(self.ctx).decode()

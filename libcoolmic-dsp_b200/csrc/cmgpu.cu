@@ -413,7 +413,7 @@ int upload_gains_locked(cmgpu_ctx *c)
         return CMGPU_OK;
     // pageable source: the runtime stages it before returning, later edits cannot race
     CU(cudaMemcpyAsync(c->d_gains + c->dirty_lo, c->h_gains.data() + c->dirty_lo,
-                       sizeof(GainRow) * (c->dirty_hi - c->dirty_lo), cudaMemcpyHostToDevice, c->s_cmp));
+                       sizeof(GainRow) * (c->dirty_hi - c->dirty_lo), cudaMemcpyHostToDevice, c->cmp()));
     c->dirty_lo = c->max_streams;
     c->dirty_hi = 0;
     return CMGPU_OK;
@@ -526,7 +526,7 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
                   bool captured = false, unsigned n_ticks = 1)
 {
     if (!st)
-        st = c->s_cmp;
+        st = c->cmp();
     int rc = upload_gains_locked(c);
     if (rc)
         return rc;
@@ -683,12 +683,28 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
         if (int brc = debug_set_bounds(c, st))
             return brc;
 #endif
+    // completion word: the tail of the compute stream is now this launch (cmgpu_sync polls the word)
+    // Only a launch queued on a compute stream somebody has just waited for gets one: the word costs the
+    // launch an atomic per CTA and a write across the host link at its very end (3 us on a 10 us tick,
+    // serialised from launch to launch in a back-to-back burst: 8.2 -> 11.1 us per config-3 tick), and it
+    // only pays where the host waits tick by tick (17.5 -> 14.4 us launch-to-complete there).
+    const bool flagged = !captured && st == c->s_cmp && c->h_done != nullptr && c->idle_hint.exchange(false, std::memory_order_acq_rel);
+    if (flagged) {
+        a.done_count = c->d_done_count;
+        a.done_flag = c->d_done_flag;
+        a.done_gen = c->done_gen_next;
+    }
     CU(launch_tick(c, a, gm, meter, st, pdl));
     c->launches++;
     if (!captured) {
         c->pending_ticks += n_ticks;
         if (st == c->s_cmp)
             c->last_first = slot;
+    }
+    if (flagged) {
+        c->tail_gen.store(a.done_gen, std::memory_order_release);
+        if (++c->done_gen_next == 0)
+            c->done_gen_next = 1;
     }
     return CMGPU_OK;
 }
@@ -700,7 +716,7 @@ bool slot_ok(const cmgpu_ctx *c, unsigned slot) { return c && slot < c->slots; }
 int ticks_done_event_locked(cmgpu_ctx *c, unsigned slot)
 {
     if (c->cmp_unrecorded[slot]) {
-        CU(cudaEventRecord(c->ev_cmp[slot], c->s_cmp));
+        CU(cudaEventRecord(c->ev_cmp[slot], c->cmp()));
         c->cmp_unrecorded[slot] = 0;
         c->last_first = ~0u;
         c->chain_open = false;
@@ -711,11 +727,11 @@ int ticks_done_event_locked(cmgpu_ctx *c, unsigned slot)
 int tick_waits_locked(cmgpu_ctx *c, unsigned slot)
 {
     if (c->up_pending[slot]) {
-        CU(cudaStreamWaitEvent(c->s_cmp, c->ev_up[slot], 0));
+        CU(cudaStreamWaitEvent(c->cmp(), c->ev_up[slot], 0));
         c->up_pending[slot] = 0;
     }
     if (c->down_pending[slot]) {
-        CU(cudaStreamWaitEvent(c->s_cmp, c->ev_down[slot], 0));
+        CU(cudaStreamWaitEvent(c->cmp(), c->ev_down[slot], 0));
         c->down_pending[slot] = 0;
     }
     return CMGPU_OK;
@@ -884,6 +900,23 @@ static cmgpu_ctx_t *ctx_create_impl(int device, unsigned channels, unsigned out_
     if ((e = cudaMalloc(&c->d_work, sizeof(unsigned int) * cmgpu_ctx::kWorkCounters)) != cudaSuccess ||
         (e = cudaMemset(c->d_work, 0, sizeof(unsigned int) * cmgpu_ctx::kWorkCounters)) != cudaSuccess)
         return bail("cudaMalloc(work counters)", e);
+    if ((e = cudaMalloc(&c->d_done_count, sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMemset(c->d_done_count, 0, sizeof(unsigned int))) != cudaSuccess)
+        return bail("cudaMalloc(completion count)", e);
+    {
+        // the completion word is an optimisation: without mapped host memory the waits ask the driver
+        void *h = nullptr, *d = nullptr;
+        if (!getenv("CMGPU_NO_DONE_WORD") && cudaHostAlloc(&h, sizeof(unsigned int), cudaHostAllocMapped) == cudaSuccess) {
+            if (cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+                c->h_done = static_cast<volatile unsigned int *>(h);
+                *c->h_done = 0;
+                c->d_done_flag = static_cast<unsigned int *>(d);
+            } else {
+                cudaFreeHost(h);
+            }
+        }
+        cudaGetLastError();
+    }
     if ((e = cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->s_cmp, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking)) != cudaSuccess)
@@ -955,6 +988,8 @@ void cmgpu_ctx_destroy(cmgpu_ctx_t *c)
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    cudaFree(c->d_done_count);
+    if (c->h_done) cudaFreeHost(const_cast<unsigned int *>(c->h_done));
     if (c->s_up) cudaStreamDestroy(c->s_up);
     if (c->s_cmp) cudaStreamDestroy(c->s_cmp);
     if (c->s_down) cudaStreamDestroy(c->s_down);
@@ -992,6 +1027,7 @@ unsigned cmgpu_block_frames(const cmgpu_ctx_t *c) { return c ? c->block_frames :
 size_t cmgpu_block_stride(const cmgpu_ctx_t *c) { return c ? c->stride : 0; }
 size_t cmgpu_slot_bytes(const cmgpu_ctx_t *c) { return c ? c->slot_bytes : 0; }
 uint64_t cmgpu_launch_count(const cmgpu_ctx_t *c) { return c ? c->launches : 0; }
+uint64_t cmgpu_word_waits(const cmgpu_ctx_t *c) { return c ? c->word_waits.load(std::memory_order_relaxed) : 0; }
 int cmgpu_transfer_bytes(const cmgpu_ctx_t *c, uint64_t *h2d, uint64_t *d2h)
 {
     if (!c)
@@ -1134,8 +1170,8 @@ int cmgpu_slot_set_frames(cmgpu_ctx_t *c, unsigned slot, const uint32_t *frames)
     uint32_t *stage = c->h_frames + (size_t)slot * c->max_streams;
     memcpy(stage, frames, sizeof(uint32_t) * c->active);
     CU(cudaMemcpyAsync(c->d_frames + (size_t)slot * c->max_streams, stage, sizeof(uint32_t) * c->active,
-                       cudaMemcpyHostToDevice, c->s_cmp));
-    CU(cudaEventRecord(c->ev_frames[slot], c->s_cmp));
+                       cudaMemcpyHostToDevice, c->cmp()));
+    CU(cudaEventRecord(c->ev_frames[slot], c->cmp()));
     c->has_frames[slot] = 1;
     return CMGPU_OK;
 }
@@ -1154,6 +1190,7 @@ int cmgpu_submit(cmgpu_ctx_t *c, unsigned slot, const void *host)
     // the slot must not be overwritten while its previous tick or download is in flight
     if (int erc = ticks_done_event_locked(c, slot))
         return erc;
+    c->up_seq.fetch_add(1, std::memory_order_release);
     CU(cudaStreamWaitEvent(c->s_up, c->ev_cmp[slot], 0));
     CU(cudaStreamWaitEvent(c->s_up, c->ev_down[slot], 0));
     CU(cudaMemcpyAsync(c->d_in + (size_t)slot * c->slot_bytes, host, c->stride * c->active, cudaMemcpyHostToDevice,
@@ -1207,6 +1244,7 @@ int cmgpu_fetch(cmgpu_ctx_t *c, unsigned slot, void *host)
         return CMGPU_OK;
     if (int erc = ticks_done_event_locked(c, slot))
         return erc;
+    c->down_seq.fetch_add(1, std::memory_order_release);
     CU(cudaStreamWaitEvent(c->s_down, c->ev_cmp[slot], 0));
     CU(cudaStreamWaitEvent(c->s_down, c->ev_up[slot], 0));
     c->bytes_d2h += out_stride * c->active;
@@ -1235,6 +1273,7 @@ int cmgpu_fetch_planar(cmgpu_ctx_t *c, unsigned slot, float *host)
     CU(cudaSetDevice(c->device));
     if (int erc = ticks_done_event_locked(c, slot))      // a tick on resident data has not recorded it yet
         return erc;
+    c->down_seq.fetch_add(1, std::memory_order_release);
     CU(cudaStreamWaitEvent(c->s_down, c->ev_cmp[slot], 0));
     CU(cudaMemcpyAsync(host, c->d_planar + (size_t)slot * c->planar_slot_floats,
                        c->plane_stride * c->channels * c->active * sizeof(float), cudaMemcpyDeviceToHost, c->s_down));
@@ -1297,9 +1336,33 @@ int cmgpu_sync(cmgpu_ctx_t *c)
     if (!c)
         return fail(CMGPU_ERR_FAULT, "NULL context");
     CU(cudaSetDevice(c->device));
-    CU(wait_stream(c->s_up));
-    CU(wait_stream(c->s_cmp));
-    CU(wait_stream(c->s_down));
+    // side streams: only if something was queued on them since the last wait (a query of an idle stream
+    // still costs 1.4 us)
+    const uint64_t up = c->up_seq.load(std::memory_order_acquire), down = c->down_seq.load(std::memory_order_acquire);
+    if (up != c->up_synced.load(std::memory_order_relaxed)) {
+        CU(wait_stream(c->s_up));
+        c->up_synced.store(up, std::memory_order_relaxed);
+    }
+    // compute stream: when its tail is a tick launch, that launch's completion word says when it is done
+    // (and, launches completing in stream order, everything before it); a launch that never finishes --
+    // a fault -- never writes the word, and the blocking wait below reports the error
+    bool cmp_done = false;
+    if (const uint32_t gen = c->tail_gen.load(std::memory_order_acquire)) {
+        const long long t0 = now_ns();
+        unsigned spins = 0;
+        while (!(cmp_done = *c->h_done == gen))
+            if ((++spins & 63u) == 0 && now_ns() - t0 > kSpinNs)
+                break;
+    }
+    if (cmp_done)
+        c->word_waits.fetch_add(1, std::memory_order_relaxed);
+    else
+        CU(wait_stream(c->s_cmp));
+    if (down != c->down_synced.load(std::memory_order_relaxed)) {
+        CU(wait_stream(c->s_down));
+        c->down_synced.store(down, std::memory_order_relaxed);
+    }
+    c->idle_hint.store(true, std::memory_order_release);       // the next tick launch is waited for tick by tick, it seems
 #ifdef CMGPU_BOUNDS_CHECK
     if (const int n = cmgpu_debug_violations())
         return fail(CMGPU_ERR_GENERIC, "bounds check: %d PCM vector accesses outside the context's rings", n);
@@ -1349,17 +1412,17 @@ int cmgpu_meter_snapshot(cmgpu_ctx_t *c, unsigned first, unsigned count, cmgpu_m
     const size_t n = (size_t)count * c->row_u64;
     c->scratch.resize(n);
     unsigned long long *src = c->d_meters + (size_t)first * c->row_u64;
-    CU(cudaMemcpyAsync(c->scratch.data(), src, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->s_cmp));
+    CU(cudaMemcpyAsync(c->scratch.data(), src, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->cmp()));
     if (reset) {
-        CU(cudaMemsetAsync(src, 0, n * sizeof(uint64_t), c->s_cmp));
+        CU(cudaMemsetAsync(src, 0, n * sizeof(uint64_t), c->cmp()));
         if (first == 0 && count == c->max_streams && !c->out_channels) {      // as in cmgpu_meter_reset
-            CU(cudaMemsetAsync(c->d_tick, 0, sizeof(unsigned long long), c->s_cmp));
+            CU(cudaMemsetAsync(c->d_tick, 0, sizeof(unsigned long long), c->cmp()));
             c->pending_ticks = 0;
         }
     }
     c->last_first = ~0u;
     c->chain_open = false;
-    CU(cudaStreamSynchronize(c->s_cmp));
+    CU(cudaStreamSynchronize(c->cmp()));
     for (unsigned i = 0; i < count; i++)
         cmgpu::decode_row(c->scratch.data() + (size_t)i * c->row_u64, c->out_channels ? c->out_channels : c->channels, out + i);
     return CMGPU_OK;
@@ -1380,10 +1443,10 @@ int cmgpu_mix_input_snapshot(cmgpu_ctx_t *c, unsigned first, unsigned count, cmg
     const size_t n = (size_t)count * c->row_in_u64;
     c->scratch.resize(n);
     unsigned long long *src = c->d_meters_in + (size_t)first * c->row_in_u64;
-    CU(cudaMemcpyAsync(c->scratch.data(), src, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->s_cmp));
+    CU(cudaMemcpyAsync(c->scratch.data(), src, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->cmp()));
     if (reset)
-        CU(cudaMemsetAsync(src, 0, n * sizeof(uint64_t), c->s_cmp));
-    CU(cudaStreamSynchronize(c->s_cmp));
+        CU(cudaMemsetAsync(src, 0, n * sizeof(uint64_t), c->cmp()));
+    CU(cudaStreamSynchronize(c->cmp()));
     for (unsigned i = 0; i < count; i++)
         cmgpu::decode_row(c->scratch.data() + (size_t)i * c->row_in_u64, c->channels, out + i);
     return CMGPU_OK;
@@ -1428,14 +1491,14 @@ int cmgpu_meter_reset(cmgpu_ctx_t *c, unsigned first, unsigned count)
         return CMGPU_OK;
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
-    CU(cudaMemsetAsync(c->d_meters + (size_t)first * c->row_u64, 0, sizeof(uint64_t) * c->row_u64 * count, c->s_cmp));
+    CU(cudaMemsetAsync(c->d_meters + (size_t)first * c->row_u64, 0, sizeof(uint64_t) * c->row_u64 * count, c->cmp()));
     if (c->d_meters_in)
         CU(cudaMemsetAsync(c->d_meters_in + (size_t)first * c->row_in_u64, 0, sizeof(uint64_t) * c->row_in_u64 * count,
-                           c->s_cmp));
+                           c->cmp()));
     if (first == 0 && count == c->max_streams) {
         // every meter window starts afresh: rebase the position keys' tick number to zero, so that the
         // 46 - pbits bits a key keeps of it can only wrap INSIDE one window of that many ticks
-        CU(cudaMemsetAsync(c->d_tick, 0, sizeof(unsigned long long), c->s_cmp));
+        CU(cudaMemsetAsync(c->d_tick, 0, sizeof(unsigned long long), c->cmp()));
         c->pending_ticks = 0;
     }
     c->last_first = ~0u;
@@ -1465,13 +1528,13 @@ int cmgpu_time_process(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, un
     int rc = upload_gains_locked(c);
     if (rc)
         return rc;
-    CU(cudaEventRecord(c->ev_t0, c->s_cmp));
+    CU(cudaEventRecord(c->ev_t0, c->cmp()));
     for (unsigned r = 0; r < reps; r++) {
         rc = launch_locked(c, first_slot + r % n_slots, flags);
         if (rc)
             return rc;
     }
-    CU(cudaEventRecord(c->ev_t1, c->s_cmp));
+    CU(cudaEventRecord(c->ev_t1, c->cmp()));
     CU(cudaEventSynchronize(c->ev_t1));
     CU(cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
     return CMGPU_OK;
@@ -1493,7 +1556,7 @@ int flush_ticks_locked(cmgpu_ctx *c)
     c->chain_open = false;
     if (!c->pending_ticks)
         return CMGPU_OK;
-    cmgpu::bump_tick<<<1, 32, 0, c->s_cmp>>>(c->d_tick, c->pending_ticks);
+    cmgpu::bump_tick<<<1, 32, 0, c->cmp()>>>(c->d_tick, c->pending_ticks);
     CU(cudaGetLastError());
     c->pending_ticks = 0;
     return CMGPU_OK;
@@ -1524,7 +1587,7 @@ static int build_cycle_locked(cmgpu_ctx *c, unsigned first_slot, unsigned n_slot
     int rc = upload_gains_locked(c);
     if (rc)
         return rc;
-    CU(cudaStreamSynchronize(c->s_cmp));
+    CU(cudaStreamSynchronize(c->cmp()));
     const unsigned kFork = 8;
     if (c->s_fork.empty()) {
         c->s_fork.assign(kFork, nullptr);
@@ -1536,9 +1599,9 @@ static int build_cycle_locked(cmgpu_ctx *c, unsigned first_slot, unsigned n_slot
         CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     }
     const uint64_t before = c->launches;
-    CU(cudaStreamBeginCapture(c->s_cmp, cudaStreamCaptureModeThreadLocal));
+    CU(cudaStreamBeginCapture(c->cmp(), cudaStreamCaptureModeThreadLocal));
     const unsigned lanes = n_slots < kFork ? n_slots : kFork;
-    cudaError_t ce = cudaEventRecord(c->ev_fork, c->s_cmp);
+    cudaError_t ce = cudaEventRecord(c->ev_fork, c->cmp());
     for (unsigned i = 0; i < lanes && ce == cudaSuccess; i++)
         ce = cudaStreamWaitEvent(c->s_fork[i], c->ev_fork, 0);
     for (unsigned i = 0; i < n_slots && rc == CMGPU_OK && ce == cudaSuccess; i++)
@@ -1546,14 +1609,14 @@ static int build_cycle_locked(cmgpu_ctx *c, unsigned first_slot, unsigned n_slot
     for (unsigned i = 0; i < lanes && ce == cudaSuccess; i++) {
         ce = cudaEventRecord(c->ev_join[i], c->s_fork[i]);
         if (ce == cudaSuccess)
-            ce = cudaStreamWaitEvent(c->s_cmp, c->ev_join[i], 0);
+            ce = cudaStreamWaitEvent(c->cmp(), c->ev_join[i], 0);
     }
     if (ce == cudaSuccess) {
-        cmgpu::bump_tick<<<1, 32, 0, c->s_cmp>>>(c->d_tick, n_slots);
+        cmgpu::bump_tick<<<1, 32, 0, c->cmp()>>>(c->d_tick, n_slots);
         ce = cudaGetLastError();             // (the one-thread bump is not counted as a tick launch)
     }
     cudaGraph_t g = nullptr;
-    cudaError_t e = cudaStreamEndCapture(c->s_cmp, &g);
+    cudaError_t e = cudaStreamEndCapture(c->cmp(), &g);
     c->graph_launches = c->launches - before;
     c->launches = before;                           // capturing is not launching
     if (rc != CMGPU_OK || e != cudaSuccess || ce != cudaSuccess) {
@@ -1599,16 +1662,16 @@ int cmgpu_process_cycle(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, u
             return rc;
     }
     if (span) {
-        if ((rc = launch_locked(c, first_slot, flags, c->s_cmp, 0, false, n_slots)))
+        if ((rc = launch_locked(c, first_slot, flags, c->cmp(), 0, false, n_slots)))
             return rc;
     } else {
         if ((rc = flush_ticks_locked(c)))
             return rc;
 #ifdef CMGPU_BOUNDS_CHECK
-        if ((rc = debug_set_bounds(c, c->s_cmp)))
+        if ((rc = debug_set_bounds(c, c->cmp())))
             return rc;
 #endif
-        CU(cudaGraphLaunch(c->graph, c->s_cmp));
+        CU(cudaGraphLaunch(c->graph, c->cmp()));
         c->launches += c->graph_launches;
         for (unsigned i = 0; i < n_slots; i++)
             c->slot_dirty[first_slot + i] = 1;      // (a replayed graph does not say whether it stores: assume it does)
@@ -1635,25 +1698,25 @@ int cmgpu_time_cycles(cmgpu_ctx_t *c, unsigned first_slot, unsigned n_slots, uns
     int rc = span ? upload_gains_locked(c) : build_cycle_locked(c, first_slot, n_slots, flags);
     if (rc)
         return rc;
-    CU(cudaEventRecord(c->ev_t0, c->s_cmp));
+    CU(cudaEventRecord(c->ev_t0, c->cmp()));
     for (unsigned r = 0; r < cycles; r++) {
         if (span) {
-            if ((rc = launch_locked(c, first_slot, flags, c->s_cmp, 0, false, n_slots)))
+            if ((rc = launch_locked(c, first_slot, flags, c->cmp(), 0, false, n_slots)))
                 return rc;
         } else {
             if ((rc = flush_ticks_locked(c)))
                 return rc;
 #ifdef CMGPU_BOUNDS_CHECK
-            if ((rc = debug_set_bounds(c, c->s_cmp)))
+            if ((rc = debug_set_bounds(c, c->cmp())))
                 return rc;
 #endif
-            CU(cudaGraphLaunch(c->graph, c->s_cmp));
+            CU(cudaGraphLaunch(c->graph, c->cmp()));
             c->launches += c->graph_launches;
             for (unsigned i = 0; i < n_slots; i++)
                 c->slot_dirty[first_slot + i] = 1;
         }
     }
-    CU(cudaEventRecord(c->ev_t1, c->s_cmp));
+    CU(cudaEventRecord(c->ev_t1, c->cmp()));
     CU(cudaEventSynchronize(c->ev_t1));
     CU(cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
     return CMGPU_OK;

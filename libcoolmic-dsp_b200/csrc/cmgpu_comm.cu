@@ -258,7 +258,7 @@ int cmgpu_gather_results(cmgpu_ctx_t *c, cmgpu_comm_t *m, int root, uint32_t rat
     std::lock_guard<std::mutex> lkc(c->mu);
     std::lock_guard<std::mutex> lkm(m->mu);
     CU(cudaSetDevice(c->device));
-    cudaStream_t st = c->s_cmp;
+    cudaStream_t st = c->cmp();
     CU(cudaEventRecord(m->ev0, st));
 
     // 1. my rows -> device staging (+ reset), ordered after every tick queued so far

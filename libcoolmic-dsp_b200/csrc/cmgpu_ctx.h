@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -106,6 +107,26 @@ struct cmgpu_ctx {
     std::vector<cudaEvent_t> ev_frames;
 
     cudaStream_t s_up = nullptr, s_cmp = nullptr, s_down = nullptr;
+    // Whoever queues anything on the compute stream takes it through cmp(): that forgets the completion
+    // word of the last tick launch (tail_gen), because the stream's tail is then something else.
+    cudaStream_t cmp()
+    {
+        tail_gen.store(0, std::memory_order_relaxed);
+        return s_cmp;
+    }
+    // Completion word of tick launches (TickArgs::done_flag): one word of mapped host memory the last CTA
+    // of a launch writes its generation to. tail_gen = generation of the launch that is the LAST thing
+    // queued on s_cmp (0: the tail is something else, or nothing was launched): cmgpu_sync then polls the
+    // word instead of the driver. up_seq / down_seq count what was queued on the side streams, *_synced
+    // what cmgpu_sync has already waited for: idle streams are not asked at all.
+    unsigned int *d_done_count = nullptr;
+    volatile unsigned int *h_done = nullptr;
+    unsigned int *d_done_flag = nullptr;              // device alias of h_done
+    uint32_t done_gen_next = 1;
+    std::atomic<uint32_t> tail_gen{0};
+    std::atomic<uint64_t> word_waits{0};
+    std::atomic<bool> idle_hint{true};                // a cmgpu_sync has returned since the last tick launch
+    std::atomic<uint64_t> up_seq{0}, down_seq{0}, up_synced{0}, down_synced{0};
     std::vector<cudaEvent_t> ev_up, ev_cmp, ev_down;
     // Cross-stream ordering is queued only where it orders something: a tick waits for a slot's upload /
     // download only if one was issued since the slot's last tick, and a slot's "ticks done" event is

@@ -163,7 +163,24 @@ __device__ __forceinline__ uint64_t tick_begin(const TickArgs &a) { return tick_
 // launch does not finish before the one before it.
 __device__ __forceinline__ void launch_begin() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void launch_end() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void tick_end(const TickArgs &) { launch_end(); }
+// The end of a tick launch: completion in stream order, then the completion word (TickArgs::done_flag).
+// The count is touched only after griddepcontrol.wait, i.e. after the previous launch has finished
+// entirely, so consecutive launches -- overlapping or not -- can share one counter; every CTA's writes
+// are fenced before it counts itself, so whoever sees the word sees the launch's results.
+__device__ __forceinline__ void tick_end(const TickArgs &a)
+{
+    launch_end();
+    if (a.done_flag != nullptr) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(a.done_count, 1u) == gridDim.x - 1u) {
+                *a.done_count = 0;
+                *reinterpret_cast<volatile unsigned int *>(a.done_flag) = a.done_gen;
+            }
+        }
+    }
+}
 
 // Work distribution of the warp-per-item loops (TickArgs::work): the item after `item` for this warp --
 // item + stride in the static order, or stride + (the number this warp claimed when it started on

@@ -234,7 +234,7 @@ int take_rows_locked(cmgpu_ctx *c, unsigned first, unsigned count, int reset, bo
     if (device_db && !c->d_results)
         CU(cudaMalloc(&c->d_results, sizeof(cmgpu_result_t) * c->max_streams));
     const unsigned C = c->out_channels ? c->out_channels : c->channels;
-    meter_take<<<(count + 127) / 128, 128, 0, c->s_cmp>>>(c->d_meters + (size_t)first * c->row_u64, c->row_u64, C, count,
+    meter_take<<<(count + 127) / 128, 128, 0, c->cmp()>>>(c->d_meters + (size_t)first * c->row_u64, c->row_u64, C, count,
                                                           c->d_take, reset, device_db ? c->d_results : nullptr, rate);
     CU(cudaGetLastError());
     c->last_first = ~0u;            // something other than a tick is now last on the compute stream
@@ -242,7 +242,7 @@ int take_rows_locked(cmgpu_ctx *c, unsigned first, unsigned count, int reset, bo
     if (reset && first == 0 && count == c->max_streams && !c->out_channels) {
         // every window starts afresh: bring the position base back to zero (the keys keep 46 - pbits
         // bits of tick number; a window must not span more ticks than that)
-        CU(cudaMemsetAsync(c->d_tick, 0, sizeof(unsigned long long), c->s_cmp));
+        CU(cudaMemsetAsync(c->d_tick, 0, sizeof(unsigned long long), c->cmp()));
         c->pending_ticks = 0;
     }
     return CMGPU_OK;
@@ -305,10 +305,10 @@ int cmgpu_meter_results(cmgpu_ctx_t *c, unsigned first, unsigned count, uint32_t
     int rc = cmgpu::take_rows_locked(c, first, count, reset, device_db, rate);
     if (rc)
         return rc;
-    CU(cudaMemcpyAsync(c->h_take, c->d_take, sizeof(uint64_t) * c->row_u64 * count, cudaMemcpyDeviceToHost, c->s_cmp));
+    CU(cudaMemcpyAsync(c->h_take, c->d_take, sizeof(uint64_t) * c->row_u64 * count, cudaMemcpyDeviceToHost, c->cmp()));
     if (device_db)
-        CU(cudaMemcpyAsync(results, c->d_results, sizeof(cmgpu_result_t) * count, cudaMemcpyDeviceToHost, c->s_cmp));
-    CU(cudaStreamSynchronize(c->s_cmp));
+        CU(cudaMemcpyAsync(results, c->d_results, sizeof(cmgpu_result_t) * count, cudaMemcpyDeviceToHost, c->cmp()));
+    CU(cudaStreamSynchronize(c->cmp()));
     if (device_db) {
         // the dB values came from the device; only the integer state and the return codes are derived here
         cmgpu::finalise_rows(c->h_take, count, c->row_u64, C, rate, nullptr, states, rcs);
@@ -348,14 +348,14 @@ int cmgpu_meter_colors(cmgpu_ctx_t *c, unsigned first, unsigned count, double al
     CU(cudaSetDevice(c->device));
     if (!c->d_colors)
         CU(cudaMalloc(&c->d_colors, sizeof(cmgpu_colors_t) * c->max_streams));
-    cmgpu::meter_colors<<<(count + 127) / 128, 128, 0, c->s_cmp>>>(c->d_meters + (size_t)first * c->row_u64, c->row_u64, C,
+    cmgpu::meter_colors<<<(count + 127) / 128, 128, 0, c->cmp()>>>(c->d_meters + (size_t)first * c->row_u64, c->row_u64, C,
                                                                    count, alpha, saturation, value,
                                                                    static_cast<cmgpu_colors_t *>(c->d_colors));
     CU(cudaGetLastError());
     c->last_first = ~0u;
     c->chain_open = false;
-    CU(cudaMemcpyAsync(out, c->d_colors, sizeof(cmgpu_colors_t) * count, cudaMemcpyDeviceToHost, c->s_cmp));
-    CU(cudaStreamSynchronize(c->s_cmp));
+    CU(cudaMemcpyAsync(out, c->d_colors, sizeof(cmgpu_colors_t) * count, cudaMemcpyDeviceToHost, c->cmp()));
+    CU(cudaStreamSynchronize(c->cmp()));
     return CMGPU_OK;
 }
 
@@ -370,7 +370,7 @@ int cmgpu_tone_set_table(cmgpu_ctx_t *c, const int16_t *period, unsigned n)
     if (!c->d_tone)
         CU(cudaMalloc(&c->d_tone, sizeof(int16_t) * 4096));
     // pageable source: staged by the runtime before the call returns
-    CU(cudaMemcpyAsync(c->d_tone, period, sizeof(int16_t) * n, cudaMemcpyHostToDevice, c->s_cmp));
+    CU(cudaMemcpyAsync(c->d_tone, period, sizeof(int16_t) * n, cudaMemcpyHostToDevice, c->cmp()));
     c->tone_len = n;
     return CMGPU_OK;
 }
@@ -380,11 +380,11 @@ static int fill_prologue_locked(cmgpu_ctx *c, unsigned slot)
     // like an upload: the slot must not be overwritten while a download of it is in flight, and the
     // fill runs on the compute stream, so ticks before and after it are ordered by the stream itself
     if (c->down_pending[slot]) {
-        CU(cudaStreamWaitEvent(c->s_cmp, c->ev_down[slot], 0));
+        CU(cudaStreamWaitEvent(c->cmp(), c->ev_down[slot], 0));
         c->down_pending[slot] = 0;
     }
     if (c->up_pending[slot]) {
-        CU(cudaStreamWaitEvent(c->s_cmp, c->ev_up[slot], 0));
+        CU(cudaStreamWaitEvent(c->cmp(), c->ev_up[slot], 0));
         c->up_pending[slot] = 0;
     }
     c->last_first = ~0u;
@@ -408,7 +408,7 @@ int cmgpu_tone_fill(cmgpu_ctx_t *c, unsigned slot, uint64_t first_frame, unsigne
         return rc;
     const uint64_t vecs = (uint64_t)c->active * (c->stride / 16);
     const unsigned grid = (unsigned)std::min<uint64_t>((vecs + 255) / 256, (uint64_t)c->num_sms * 16);
-    cmgpu::tone_fill<<<grid, 256, 0, c->s_cmp>>>(c->d_in + (size_t)slot * c->slot_bytes,
+    cmgpu::tone_fill<<<grid, 256, 0, c->cmp()>>>(c->d_in + (size_t)slot * c->slot_bytes,
                                                  c->has_frames[slot] ? c->d_frames + (size_t)slot * c->max_streams : nullptr,
                                                  c->active, c->block_frames, c->channels, c->stride, c->d_tone, c->tone_len,
                                                  first_frame, first_stream, stream_step, channel_step);
@@ -434,7 +434,7 @@ int cmgpu_noise_fill(cmgpu_ctx_t *c, unsigned slot, uint64_t first_frame, unsign
         return rc;
     const uint64_t vecs = (uint64_t)c->active * (c->stride / 16);
     const unsigned grid = (unsigned)std::min<uint64_t>((vecs + 255) / 256, (uint64_t)c->num_sms * 16);
-    cmgpu::noise_fill<<<grid, 256, 0, c->s_cmp>>>(c->d_in + (size_t)slot * c->slot_bytes,
+    cmgpu::noise_fill<<<grid, 256, 0, c->cmp()>>>(c->d_in + (size_t)slot * c->slot_bytes,
                                                   c->has_frames[slot] ? c->d_frames + (size_t)slot * c->max_streams : nullptr,
                                                   c->active, c->block_frames, c->channels, c->stride, first_frame,
                                                   first_stream, seed, every, phase);

@@ -380,3 +380,72 @@ def test_nccl_gather_in_c(cm, tmp_path, channels):
     out = _gather_ranks(tmp_path, n, 1000 + 3 * n + 1, channels)
     assert out["ok"], out
     assert out["ranks"] == n and out["streams_checked"] == out["total_streams"]
+
+
+# ---- the completion word of a tick launch (TickArgs::done_flag) -------------------------------------
+
+def _cudart():
+    for name in ("libcudart.so.12", "libcudart.so"):
+        try:
+            return C.CDLL(name)
+        except OSError:
+            continue
+    pytest.skip("no libcudart to read device memory behind the library's back")
+
+
+@pytest.mark.parametrize("channels,n_streams,block,separate", [(1, 512, 320, False), (2, 64, 4800, True), (6, 8, 1000, False),
+                                                               (8, 300, 64, False)])
+def test_sync_by_completion_word_sees_the_finished_tick(cm, port, channels, n_streams, block, separate):
+    """cmgpu_sync straight after cmgpu_process returns when the launch's last CTA has written the completion
+    word to host memory -- no driver call. Everything the tick wrote must be visible by then: the output
+    ring is read with a plain cudaMemcpy on another stream (nothing orders it after the tick except that
+    the host saw the word), tick after tick with a different gain each time."""
+    rt = _cudart()
+    rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    rng = np.random.default_rng(channels * 1000 + block)
+    flags = cm.SEPARATE_OUT if separate else 0
+    with cm.Engine(channels, n_streams, block, ring_slots=1, flags=flags) as eng:
+        host = eng.host_slot(0)
+        got = np.empty_like(host)
+        meters = None
+        for it in range(40):
+            pcm = make_pcm(rng, "full", host.shape)
+            scale, gain = make_gains(rng, n_streams, channels, "plain")
+            scale[scale == 0] = 7
+            eng.set_gain_table(scale, gain)
+            host[:] = pcm
+            eng.submit(0)
+            eng.process(0)                      # consumes the upload: a streaming tick (it records its event)
+            eng.sync()                          # (a launch gets a completion word only on a stream that was just waited for)
+            fr = np.full(n_streams, block, np.uint32)
+            want = pcm.copy()
+            meters, _ = port.batch(want, fr, channels, scale, gain, meters=meters)
+            again = pcm.copy() if separate else want        # in place the second tick works on the first one's output
+            meters, _ = port.batch(again, fr, channels, scale, gain, meters=meters)
+            want = again
+            eng.process(0)                      # on resident data: a bare launch, the tail of the compute stream
+            eng.sync()                          # <- by completion word
+            assert rt.cudaMemcpy(got.ctypes.data, eng.device_out_slot(0), got.nbytes, 2) == 0
+            n = block * channels
+            assert np.array_equal(got[:, :n], want[:, :n]), f"tick {it}: output not complete when cmgpu_sync returned"
+        assert eng.word_waits() >= 40, "cmgpu_sync never took the completion-word path"
+        snap = eng.snapshot(0, n_streams)
+        for s in range(n_streams):
+            assert int(snap[s].frames) == int(meters[s].frames)
+            for c in range(channels):
+                assert int(snap[s].power[c]) == int(meters[s].power[c])
+                assert int(snap[s].channel_peak[c]) == int(meters[s].channel_peak[c])
+
+
+def test_completion_word_can_be_switched_off(cm, port, monkeypatch):
+    """CMGPU_NO_DONE_WORD=1 (read at cmgpu_ctx_create): every wait asks the driver, results are the same."""
+    monkeypatch.setenv("CMGPU_NO_DONE_WORD", "1")
+    rng = np.random.default_rng(5)
+    with cm.Engine(2, 33, 777) as eng:
+        meters = _run_ticks(cm, port, eng, rng, 33, 2, 777, n_ticks=3)
+        eng.process(0, cm.TRANSFORM)            # a bare launch on resident data, nothing metered
+        eng.sync()
+        assert eng.word_waits() == 0
+        snap = eng.snapshot(0, 33)
+        assert all(int(snap[s].frames) == int(meters[s].frames) for s in range(33))
+        assert all(int(snap[s].power[0]) == int(meters[s].power[0]) for s in range(33))
