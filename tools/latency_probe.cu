@@ -26,6 +26,12 @@ static long long now_ns()
 }
 
 __global__ void empty_kernel() {}
+struct BigArgs { unsigned long long w[30]; };      // 240 bytes, the size of the tick kernels' argument block
+__global__ void big_arg_kernel(const __grid_constant__ BigArgs a, unsigned *sink)
+{
+    if (a.w[29] == 0x1234567ull)
+        *sink = 1;
+}
 
 __global__ void flag_kernel(unsigned *count, volatile unsigned *host_flag, unsigned gen)
 {
@@ -100,6 +106,34 @@ int main()
             us[r] = (now_ns() - t0) * 1e-3f;
         }
         report("empty kernel: the launch call alone (host)", us);
+    }
+    {
+        BigArgs big = {};
+        for (unsigned r = 0; r < reps; r++) {
+            cudaStreamSynchronize(st);
+            const long long t0 = now_ns();
+            big_arg_kernel<<<1, 32, 0, st>>>(big, d_count);
+            us[r] = (now_ns() - t0) * 1e-3f;
+        }
+        report("240-byte argument block, <<<>>>: the launch call alone (host)", us);
+        for (int pdl = 0; pdl < 2; pdl++) {
+            for (unsigned r = 0; r < reps; r++) {
+                cudaStreamSynchronize(st);
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(512);
+                cfg.blockDim = dim3(256);
+                cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = pdl;
+                const long long t0 = now_ns();
+                cudaLaunchKernelEx(&cfg, big_arg_kernel, big, d_count);
+                us[r] = (now_ns() - t0) * 1e-3f;
+            }
+            report(pdl ? "240-byte block, cudaLaunchKernelEx + PDL attribute, grid 512: call" : "240-byte block, cudaLaunchKernelEx, grid 512: call alone", us);
+        }
     }
     {
         // completion through a stream memory operation: the front end writes the flag when the stream gets there
