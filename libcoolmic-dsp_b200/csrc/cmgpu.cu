@@ -1350,7 +1350,8 @@ int cmgpu_sync(cmgpu_ctx_t *c)
     if (const uint32_t gen = c->tail_gen.load(std::memory_order_acquire)) {
         const long long t0 = now_ns();
         unsigned spins = 0;
-        while (!(cmp_done = *c->h_done == gen))
+        // (>= in generation order: another thread's later launch may have finished as well by now)
+        while (!(cmp_done = (int32_t)(*c->h_done - gen) >= 0))
             if ((++spins & 63u) == 0 && now_ns() - t0 > kSpinNs)
                 break;
     }
