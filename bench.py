@@ -272,6 +272,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-equal-shards", action="store_true",
+                    help="end-to-end leg on N > 1 GPUs: equal stream counts per rank instead of counts in proportion to each rank's host-link rate")
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="fused", choices=["fused", "transform", "meter", "copy"],
                     help="diagnostic: which parts of the tick run in the device-timed loop (default: fused = the product)")
@@ -370,15 +372,19 @@ def main():
 
     passthrough = bool(wl.get("passthrough"))
 
-    def configure(e):
+    def configure(e, first=None, n=None):
         if passthrough:
             return                      # no gain set: transform.c:107-108
+        first = first_stream if first is None else first
+        n = streams_per_gpu if n is None else n
         if mix_out:
-            mscale, mw = mix_table(first_stream, streams_per_gpu, channels, mix_out)
-            for i in range(streams_per_gpu):
+            mscale, mw = mix_table(first, n, channels, mix_out)
+            for i in range(n):
                 assert e.set_mix(i, int(mscale[i]), mw[i]) == 0
-        else:
+        elif first == first_stream and n == streams_per_gpu:
             e.set_gain_table(scale, gain)
+        else:
+            e.set_gain_table(*gain_table(first, n, channels))
 
     eng = cm.Engine(channels, streams_per_gpu, frames, ring_slots=ring, device=local,
                     flags=cm.NO_PINNED | (0 if (mix_out or passthrough) else cm.SEPARATE_OUT) | (cm.PLANAR_F32 if planar else 0) | mix_flags,
@@ -496,15 +502,31 @@ def main():
         tick_frames = wl["e2e_frames"]
         n_ticks = wl["e2e_ticks"]
         e2e_steps = args.e2e_steps or min(args.steps, 5)
+        # Shards of the end-to-end leg. Every sample crosses the host link twice, and the GPUs of a box do not
+        # get equal shares of it (links behind a common bridge halve each other: 9.6 to over 20 GB/s per rank on
+        # an 8-GPU box): with equal stream counts the step ends when the rank on the slowest link does and the
+        # others idle. So the stream counts follow what cmgpu_link_probe gives each rank while all ranks drive
+        # their links at once -- still contiguous ranges, still no data-path exchange.
+        total_streams = streams_per_gpu * world
+        shard_counts = [streams_per_gpu] * world
+        shard_gbs = None
+        if comm is not None and world > 1 and not args.e2e_equal_shards:
+            probe_bytes = min(256 << 20, max(16 << 20, streams_per_gpu * tick_frames * channels * 2))
+            barrier()
+            mine = cm.link_probe(local, probe_bytes, reps=max(4, (1 << 30) // probe_bytes), both_only=True)["both_each_way_gbs"]
+            shard_gbs = [float(x) for x in comm.sum(*[mine if r == rank else 0.0 for r in range(world)])]
+            shard_counts = proportional_shards(shard_gbs, total_streams)
+        e2e_n = shard_counts[rank]
+        e2e_first = sum(shard_counts[:rank])
         # host inputs: written by the same device generator into a scratch (identity, in-place) context
         # and brought down once -- setup, not measured
-        gen = cm.Engine(channels, streams_per_gpu, tick_frames, ring_slots=2, device=local, flags=cm.NO_PINNED)
+        gen = cm.Engine(channels, e2e_n, tick_frames, ring_slots=2, device=local, flags=cm.NO_PINNED)
         gen.tone_table(period)
-        shape = (n_ticks, streams_per_gpu, gen.stride // 2)
+        shape = (n_ticks, e2e_n, gen.stride // 2)
         pin_in = cm.PinnedArray(shape, wc=args.e2e_wc)
         stage = cm.PinnedArray(shape[1:]) if args.e2e_wc else None
         for t in range(n_ticks):
-            synth.device_fill(gen, t % 2, None, first_stream, t * tick_frames, **fill)
+            synth.device_fill(gen, t % 2, None, e2e_first, t * tick_frames, **fill)
             if stage is None:
                 gen.fetch(t % 2, pin_in.array[t])
             else:
@@ -516,16 +538,15 @@ def main():
         if stage is not None:
             stage.free()
 
-        eng = cm.Engine(channels, streams_per_gpu, tick_frames, ring_slots=4, device=local, flags=cm.NO_PINNED | mix_flags,
+        eng = cm.Engine(channels, e2e_n, tick_frames, ring_slots=4, device=local, flags=cm.NO_PINNED | mix_flags,
                         out_channels=mix_out)
-        configure(eng)
-        pin_out = cm.PinnedArray((n_ticks, streams_per_gpu, eng.out_stride // 2))
-        total_streams = streams_per_gpu * world
+        configure(eng, e2e_first, e2e_n)
+        pin_out = cm.PinnedArray((n_ticks, e2e_n, eng.out_stride // 2))
         gathered = [None]
         gather = not args.e2e_no_gather
         # result arrays allocated once (65,536 x 192 B of ctypes structures take milliseconds to create)
         gather_out = cm.Comm.alloc_results(total_streams, world) if (comm is not None and rank == 0) else None
-        results_out = cm.Engine.alloc_results(streams_per_gpu)
+        results_out = cm.Engine.alloc_results(e2e_n)
 
         presubmitted = [0]
         ahead = min(3, n_ticks)
@@ -551,7 +572,7 @@ def main():
                 out = comm.gather_results(eng, rate, total_streams, out=gather_out)
             else:
                 res, st, rcs = eng.results(rate, out=results_out)
-                out = (res, st, rcs, [streams_per_gpu])
+                out = (res, st, rcs, [e2e_n])
             if out is not None:
                 gathered[0] = out
 
@@ -572,16 +593,17 @@ def main():
         spot = "skipped (--no-verify)"
         if rank == 0:
             res, st, rcs, counts = gathered[0]
-            assert int(st[0].frames) == tick_frames * n_ticks and sum(counts) == (total_streams if comm is not None and gather else streams_per_gpu)
+            gathered_all = comm is not None and gather
+            assert int(st[0].frames) == tick_frames * n_ticks and list(counts) == (shard_counts if gathered_all else [e2e_n])
             if not args.no_verify:
-                spot = spot_check(cm, synth, wl, period, streams_per_gpu, world if (comm is not None and gather) else 1,
+                spot = spot_check(cm, synth, wl, period, shard_counts if gathered_all else [e2e_n],
                                   channels, tick_frames, n_ticks, rate, pin_out.array, res, st)
-        slot_bytes = streams_per_gpu * eng.stride
-        out_slot_bytes = streams_per_gpu * eng.out_stride
-        meter_bytes = streams_per_gpu * eng.meter_row_u64() * 8
-        samples_e2e_rank = streams_per_gpu * tick_frames * n_ticks * channels
+        slot_bytes = e2e_n * eng.stride
+        out_slot_bytes = e2e_n * eng.out_stride
+        meter_bytes = e2e_n * eng.meter_row_u64() * 8
+        samples_e2e_all = total_streams * tick_frames * n_ticks * channels
         e2e = {"parity_spot_check": spot, "through": "cmgpu_submit / cmgpu_process / cmgpu_fetch / cmgpu_gather_results (C ABI)",
-               "value": samples_e2e_rank * world * e2e_steps / wall / 1e6, "unit": "Msamples/s",
+               "value": samples_e2e_all * e2e_steps / wall / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": n_ticks * slot_bytes, "d2h_bytes_per_step": n_ticks * out_slot_bytes + meter_bytes,
                "steps": e2e_steps, "ms_per_step": 1e3 * wall / e2e_steps,
                "gbs_each_way_all_ranks": sum_over_ranks(n_ticks * slot_bytes * e2e_steps / wall_mine / 1e9),
@@ -591,6 +613,13 @@ def main():
                       "host waits for this step's results); per step the meter results of all ranks are gathered to "
                       "rank 0 by cmgpu_gather_results (NCCL send/recv of the raw rows on the compute stream, decode + dB "
                       "finalise on rank 0); steps are queued back to back and drained before the clock stops"}
+        if world > 1:
+            e2e["shards"] = {"streams_per_rank": shard_counts, "link_gbs_per_rank": shard_gbs,
+                             "rule": "equal" if shard_gbs is None else "in proportion to each rank's share of the host links "
+                                     "(cmgpu_link_probe, all ranks at once, both directions), contiguous stream ranges",
+                             "note": "h2d / d2h bytes per step are rank 0's"}
+            e2e["h2d_bytes_per_step_all_ranks"] = int(sum_over_ranks(float(n_ticks * slot_bytes)))
+            e2e["d2h_bytes_per_step_all_ranks"] = int(sum_over_ranks(float(n_ticks * out_slot_bytes + meter_bytes)))
         eng.close()
         if not args.no_extras:
             # what the host link gives when every rank drives it at once, both directions (the e2e ceiling)
@@ -606,7 +635,7 @@ def main():
             # Pass-through streams, the reference's default state (no master gain: transform.c:107-108
             # leaves the buffer alone): uploaded from the pinned staging ring, metered, nothing downloaded.
             pt_ticks = min(n_ticks, 8)
-            eng = cm.Engine(channels, streams_per_gpu, tick_frames, ring_slots=4, device=local)
+            eng = cm.Engine(channels, e2e_n, tick_frames, ring_slots=4, device=local)
             for slot in range(4):
                 eng.host_slot(slot)[:] = pin_in.array[slot % n_ticks]
             for _ in range(2):
@@ -625,7 +654,7 @@ def main():
             eng.sync()
             pt_wall = max_over_ranks(time.perf_counter() - t0)
             up1, down1 = eng.transfer_bytes()
-            e2e["passthrough"] = {"value": streams_per_gpu * world * tick_frames * pt_ticks * channels * pt_steps / pt_wall / 1e6,
+            e2e["passthrough"] = {"value": total_streams * tick_frames * pt_ticks * channels * pt_steps / pt_wall / 1e6,
                                   "unit": "Msamples/s", "h2d_bytes_per_step": (up1 - up0) // pt_steps,
                                   "d2h_bytes_per_step": (down1 - down0) // pt_steps + meter_bytes,
                                   "note": "every stream in the reference's default state (no gain set): uploaded from the "
@@ -675,7 +704,31 @@ def main():
     return 0
 
 
-def spot_check(cm, synth, wl, period, streams_per_gpu, world, channels, tick_frames, n_ticks, rate, out0, results, states):
+def proportional_shards(weights, total, quantum=64):
+    """Stream counts per rank in proportion to `weights`, multiples of `quantum` (the last rank takes the
+    remainder), at least one quantum each; contiguous ranges follow from the running sum."""
+    world = len(weights)
+    w = [max(float(x), 1e-6) for x in weights]
+    units = total // quantum
+    if units < world:
+        return [total // world + (1 if r < total % world else 0) for r in range(world)]
+    raw = [x / sum(w) * units for x in w]
+    counts = [max(1, int(x)) for x in raw]
+    # hand the units rounding left over to the ranks with the largest remainders (or take them back)
+    order = sorted(range(world), key=lambda r: raw[r] - int(raw[r]), reverse=True)
+    i = 0
+    while sum(counts) < units:
+        counts[order[i % world]] += 1
+        i += 1
+    while sum(counts) > units:
+        r = max(range(world), key=lambda k: counts[k])
+        counts[r] -= 1
+    counts = [c * quantum for c in counts]
+    counts[-1] += total - sum(counts)
+    return counts
+
+
+def spot_check(cm, synth, wl, period, counts, channels, tick_frames, n_ticks, rate, out0, results, states):
     """Rank 0 re-derives, with the oracle port, what a few streams of EVERY rank must have produced
     in the last end-to-end step: transformed PCM (rank 0's own streams), the integer meter state and the
     finalised dB values (all ranks, from the rows that came over NCCL). The oracle is the checker here,
@@ -684,7 +737,8 @@ def spot_check(cm, synth, wl, period, streams_per_gpu, world, channels, tick_fra
     port = pyoracle.port()
     frames = tick_frames * n_ticks
     checked = 0
-    picks = sorted({0, 5, streams_per_gpu // 2, streams_per_gpu - 1})
+    world = len(counts)
+    firsts = [sum(counts[:r]) for r in range(world)]
 
     def rows(g):
         return np.ascontiguousarray(synth.synth_rows(period, g, 1, channels, frames, 0, wl["sstep"], wl["cstep"],
@@ -693,7 +747,7 @@ def spot_check(cm, synth, wl, period, streams_per_gpu, world, channels, tick_fra
     if wl.get("mix_out"):
         # extension: our own restatement is the only checker there is (parity unpinned)
         cout = wl["mix_out"]
-        for s in picks:
+        for s in sorted({0, 5, counts[0] // 2, counts[0] - 1}):
             pcm = rows(s)
             mscale, mw = mix_table(s, 1, channels, cout)
             m_out = pyoracle.Meter()
@@ -708,8 +762,8 @@ def spot_check(cm, synth, wl, period, streams_per_gpu, world, channels, tick_fra
             checked += 1
         return f"ok: {checked} streams bit-exact vs our own CPU restatement (extension, parity unpinned)"
     for r in range(world):
-        for s in picks:
-            g = r * streams_per_gpu + s
+        for s in sorted({0, min(5, counts[r] - 1), counts[r] // 2, counts[r] - 1}):
+            g = firsts[r] + s
             pcm = rows(g)
             scale, gain = gain_table(g, 1, channels)
             meters, _ = port.batch(pcm, np.array([frames], np.uint32), channels, scale, gain)

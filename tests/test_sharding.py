@@ -27,6 +27,27 @@ def test_stream_range_partitions_exactly():
         cm.sharding.stream_range(8, 2, 2)
 
 
+def test_link_proportional_shards_of_the_end_to_end_leg():
+    """bench.py's end-to-end leg on N > 1 GPUs gives each rank a contiguous stream range whose size follows
+    the rank's share of the host links: the counts must partition the total, stay multiples of the quantum
+    (the last rank takes the remainder), never be empty, and follow the weights."""
+    import bench
+    rng = np.random.default_rng(11)
+    for total in (65536, 4096, 1000, 64, 7):
+        for world in (1, 2, 4, 8):
+            for _ in range(20):
+                w = rng.uniform(5.0, 50.0, size=world).tolist()
+                counts = bench.proportional_shards(w, total)
+                assert len(counts) == world and sum(counts) == total and min(counts) >= (1 if total >= world else 0)
+                if total // 64 >= world:
+                    assert all(c % 64 == 0 for c in counts[:-1]) and min(counts) >= 64
+                    ideal = [x / sum(w) * total for x in w]
+                    assert all(abs(c - i) <= 128 + total % 64 for c, i in zip(counts, ideal)), (w, counts)
+    assert bench.proportional_shards([34.0, 44.2], 65536) == [28480, 37056]
+    assert bench.proportional_shards([1.0] * 8, 65536) == [8192] * 8
+    assert bench.proportional_shards([0.0, 10.0], 1024) == [64, 960]      # a dead link still gets a quantum, not a division by zero
+
+
 def encode_row(meter, positions, channels):
     """What fused_tick leaves in a meter row: key = mag<<47 | ~pos<<1 | neg, then power, frames."""
     row = np.zeros(2 * channels + 2, dtype=np.uint64)
