@@ -75,7 +75,18 @@ def make_world(total, channels, frames, seed=3):
     return pcm, scale, gain
 
 
-def worker(rank, world, port_no, total, channels, frames, result_q):
+def shard_ranges(cm, total, world, weights):
+    """Equal contiguous ranges (sharding.stream_range), or the link-proportional ones of bench.py's
+    end-to-end leg for per-rank `weights`."""
+    if weights is None:
+        return [cm.sharding.stream_range(total, world, r) for r in range(world)]
+    import bench
+    counts = bench.proportional_shards(weights, total, quantum=1)
+    firsts = [sum(counts[:r]) for r in range(world)]
+    return [(f, f + n) for f, n in zip(firsts, counts)]
+
+
+def worker(rank, world, port_no, total, channels, frames, result_q, weights=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port_no)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -84,13 +95,13 @@ def worker(rank, world, port_no, total, channels, frames, result_q):
         cm = load_package()
         port = pyoracle.port()
         pcm, scale, gain = make_world(total, channels, frames)
-        lo, hi = cm.sharding.stream_range(total, world, rank)
+        ranges = shard_ranges(cm, total, world, weights)
+        lo, hi = ranges[rank]
         mine = pcm[lo:hi].copy()
         meters, _ = port.batch(mine, np.full(hi - lo, frames, np.uint32), channels, scale[lo:hi], gain[lo:hi])
         rows = np.concatenate([encode_row(meters[i], first_peak_frames(mine[i], channels), channels)
                                for i in range(hi - lo)]) if hi > lo else np.zeros(0, np.uint64)
-        counts = [(cm.sharding.stream_range(total, world, r)[1] - cm.sharding.stream_range(total, world, r)[0])
-                  * (2 * channels + 2) for r in range(world)]
+        counts = [(b - a) * (2 * channels + 2) for a, b in ranges]
         got = cm.sharding.gather_rows(torch.from_numpy(rows.view(np.int64)), dist, rank, world, counts)
         if rank == 0:
             allrows = np.concatenate([t.numpy() for t in got])
@@ -112,13 +123,15 @@ def free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("total,channels", [(9, 2), (16, 1), (5, 8)])
-def test_two_rank_gather_equals_single_process(total, channels, port):
+@pytest.mark.parametrize("total,channels,weights", [(9, 2, None), (16, 1, None), (5, 8, None), (23, 2, [34.0, 9.5])])
+def test_two_rank_gather_equals_single_process(total, channels, weights, port):
+    """weights: the ranks' stream ranges follow their (here: made-up) host-link shares, as in bench.py's
+    end-to-end leg -- what arrives at rank 0 must not depend on how the streams were cut."""
     frames = 257
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port_no = free_port()
-    procs = [ctx.Process(target=worker, args=(r, 2, port_no, total, channels, frames, q)) for r in range(2)]
+    procs = [ctx.Process(target=worker, args=(r, 2, port_no, total, channels, frames, q, weights)) for r in range(2)]
     for p in procs:
         p.start()
     out = q.get(timeout=120)
