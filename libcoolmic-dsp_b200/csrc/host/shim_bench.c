@@ -55,6 +55,32 @@ static void capture_copy(void *dst, const void *src, size_t n, int streaming)
     memcpy(dst, src, n);
 }
 
+#ifdef SHIM_BENCH_SELFTEST
+/* test hook (tests/stub/san_main.c): every size and both misalignments against memcpy; 0 = all equal */
+int shim_bench_copy_selftest(void)
+{
+    enum { N = 4096 + 128 };
+    unsigned char *src = malloc(N + 64), *a = malloc(N + 64), *b = malloc(N + 64);
+    size_t n, so, dof;
+    int bad = !src || !a || !b;
+    for (n = 0; !bad && n < N + 64; n++)
+        src[n] = (unsigned char)(n * 131u + 7u);
+    for (n = 0; !bad && n <= N; n += (n < 600 ? 1 : 97)) {
+        for (so = 0; so < 3 && !bad; so++) {
+            for (dof = 0; dof < 33 && !bad; dof += (dof < 17 ? 1 : 15)) {
+                memset(a, 0xee, N + 64);
+                memset(b, 0xee, N + 64);
+                capture_copy(a + dof, src + so, n, 1);
+                memcpy(b + dof, src + so, n);
+                bad = memcmp(a, b, N + 64) != 0;
+            }
+        }
+    }
+    free(src); free(a); free(b);
+    return bad;
+}
+#endif
+
 static ssize_t cyc_read(void *userdata, void *buffer, size_t len)
 {
     cyc_src_t *m = userdata;

@@ -42,7 +42,9 @@ def build_stub(sanitize: str = "", main: bool = False) -> Path:
     cmd = ["gcc", "-std=gnu11", "-O1", "-g", "-fPIC", "-Wall", "-Wextra", "-pthread", f"-I{ROOT / 'include'}"]
     if sanitize:
         cmd += [f"-fsanitize={sanitize}", "-fno-omit-frame-pointer"]
-    if not main:
+    if main:
+        cmd += ["-DSHIM_BENCH_SELFTEST"]
+    else:
         cmd += ["-shared"]
     subprocess.run(cmd + ["-o", str(out)] + [str(s) for s in srcs] + ["-lm"], check=True)
     return out

@@ -18,6 +18,8 @@ long shimh_batch_ring(const void *in, size_t n_streams, size_t bytes_per_stream,
                       void *results, int *flags);
 int shimh_null_checks(void);
 
+int shim_bench_copy_selftest(void);
+
 int main(void)
 {
     enum { N = 37, CH = 3, BYTES = 2 * CH * 1777 + 5 };
@@ -54,6 +56,7 @@ int main(void)
         unsigned char *pcm = malloc((size_t)STREAMS * bps);
         for (i = 0; i < STREAMS * bps; i++)
             pcm[i] = (unsigned char)rand();
+        bad |= shim_bench_copy_selftest();      /* the capture copy with non-temporal stores == memcpy */
         bad |= coolmic_b200_bench_objects(0, 2, STREAMS, BLOCK, TICKS, 4, 6, bps, pcm, &secs, &check) != 0;
         bad |= check != (uint64_t)STREAMS * BLOCK * TICKS;
         bad |= coolmic_b200_bench_objects(0, 2, STREAMS, BLOCK, TICKS, 1, 3, bps, pcm, &secs, &check) != 0;
