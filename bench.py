@@ -513,9 +513,15 @@ def main():
         if comm is not None and world > 1 and not args.e2e_equal_shards:
             probe_bytes = min(256 << 20, max(16 << 20, streams_per_gpu * tick_frames * channels * 2))
             barrier()
-            mine = cm.link_probe(local, probe_bytes, reps=max(4, (1 << 30) // probe_bytes), both_only=True)["both_each_way_gbs"]
+            try:
+                mine = cm.link_probe(local, probe_bytes, reps=max(4, (1 << 30) // probe_bytes), both_only=True)["both_each_way_gbs"]
+            except Exception:            # the probe is a hint, not the metric: every rank then sees a 0 and all stay equal
+                mine = 0.0
             shard_gbs = [float(x) for x in comm.sum(*[mine if r == rank else 0.0 for r in range(world)])]
-            shard_counts = proportional_shards(shard_gbs, total_streams)
+            if min(shard_gbs) > 0.0:
+                shard_counts = proportional_shards(shard_gbs, total_streams)
+            else:
+                shard_gbs = None
         e2e_n = shard_counts[rank]
         e2e_first = sum(shard_counts[:rank])
         # host inputs: written by the same device generator into a scratch (identity, in-place) context
