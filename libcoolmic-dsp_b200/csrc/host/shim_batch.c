@@ -55,7 +55,8 @@ struct coolmic_b200_batch {
     pthread_t *workers;
     pthread_mutex_t mu;
     pthread_cond_t cv_work, cv_done;
-    uint64_t job;                      /* generation of the current pull job */
+    uint64_t job;                      /* generation of the current pull job (its own counter: a tick that
+                                          fails after its pull does not advance `epoch`, the next one is still a new job) */
     unsigned job_left;
     unsigned char *job_slot;           /* pinned slot being filled ... */
     size_t *job_ob;                    /* ... and its out_bytes row */
@@ -354,7 +355,7 @@ int coolmic_b200_batch_tick(coolmic_b200_batch_t *b)
         b->job_ob = ob;
         b->job_total = 0;
         b->job_left = b->n_workers;
-        b->job = b->epoch + 1;
+        b->job++;
         pthread_cond_broadcast(&b->cv_work);
         pthread_mutex_unlock(&b->mu);
         total = pull_range(b, slot_mem, ob, (unsigned)((uint64_t)b->max_streams * b->n_workers / (b->n_workers + 1)),

@@ -122,11 +122,19 @@ int cmgpu_submit(cmgpu_ctx_t *c, unsigned slot, const void *host)
     return CMGPU_OK;
 }
 
+/* test hook: the next `n` ticks fail the way a CUDA error would (called from the ticking thread only) */
+static int g_fail_process;
+void cmgpu_stub_fail_next_process(int n) { g_fail_process = n; }
+
 int cmgpu_process(cmgpu_ctx_t *c, unsigned slot, unsigned flags)
 {
     unsigned s;
     if (!c || slot >= c->slots)
         return c ? CMGPU_ERR_INVAL : CMGPU_ERR_FAULT;
+    if (g_fail_process > 0) {
+        g_fail_process--;
+        return CMGPU_ERR_GENERIC;
+    }
     pthread_mutex_lock(&c->mu);
     for (s = 0; s < c->max_streams; s++) {
         int16_t *p = (int16_t *)(c->dev + slot * c->slot_bytes + (size_t)s * c->stride);

@@ -19,6 +19,66 @@ long shimh_batch_ring(const void *in, size_t n_streams, size_t bytes_per_stream,
 int shimh_null_checks(void);
 
 int shim_bench_copy_selftest(void);
+void cmgpu_stub_fail_next_process(int n);
+
+/* a tick that fails after its pull (a CUDA error in the real engine): nothing of it is exposed, and the
+ * NEXT tick still hands the pull workers a new job instead of waiting for them forever */
+typedef struct { const unsigned char *p; size_t left; } src_t;
+static ssize_t src_read(void *u, void *buf, size_t len)
+{
+    src_t *m = u;
+    if (len > m->left)
+        len = m->left;
+    memcpy(buf, m->p, len);
+    m->p += len;
+    m->left -= len;
+    return (ssize_t)len;
+}
+static int src_eof(void *u) { return ((src_t *)u)->left == 0; }
+
+static int failed_tick_scenario(unsigned threads)
+{
+    enum { N = 9, BLOCK = 64, BYTES = 4 * BLOCK * 3 };
+    static unsigned char pcm[N][BYTES];
+    unsigned char got[BYTES];
+    coolmic_b200_batch_t *b = coolmic_b200_batch_new_ring(0, 2, N, BLOCK, 2, threads);
+    coolmic_transform_t *tr[N];
+    coolmic_iohandle_t *rd[N];
+    src_t src[N];
+    unsigned s, i;
+    int bad = !b, rc;
+    if (bad)
+        return 1;
+    for (s = 0; s < N; s++) {
+        coolmic_iohandle_t *h;
+        for (i = 0; i < BYTES; i++)
+            pcm[s][i] = (unsigned char)(s * 31 + i * 7);
+        src[s].p = pcm[s];
+        src[s].left = BYTES;
+        tr[s] = coolmic_b200_batch_transform_new(b, "tr", NULL, 48000);          /* no gain: output = input */
+        h = coolmic_iohandle_new("src", NULL, &src[s], NULL, src_read, src_eof);
+        coolmic_transform_attach_iohandle(tr[s], h);
+        coolmic_b200_unref(h);
+        rd[s] = coolmic_transform_get_iohandle(tr[s]);
+    }
+    cmgpu_stub_fail_next_process(1);
+    rc = coolmic_b200_batch_tick(b);
+    bad |= rc != COOLMIC_ERROR_GENERIC;
+    for (s = 0; s < N; s++)
+        bad |= coolmic_iohandle_read(rd[s], got, sizeof(got)) != 0;              /* the failed tick exposed nothing */
+    bad |= coolmic_b200_batch_pending(b) != 0;
+    rc = coolmic_b200_batch_tick(b);                                              /* hung here before the fix */
+    bad |= rc != N * BLOCK;
+    for (s = 0; s < N; s++) {
+        /* the block the failed tick had pulled is gone (a read error loses data in the reference too); the next one arrives intact */
+        bad |= coolmic_iohandle_read(rd[s], got, sizeof(got)) != 4 * BLOCK;
+        bad |= memcmp(got, pcm[s] + 4 * BLOCK, 4 * BLOCK) != 0;
+        coolmic_b200_unref(rd[s]);
+        coolmic_b200_unref(tr[s]);
+    }
+    coolmic_b200_unref(b);
+    return bad;
+}
 
 int main(void)
 {
@@ -42,6 +102,8 @@ int main(void)
             gain[s * CH + i] = (uint16_t)(700 + 97 * s + i);
     }
     bad |= shimh_null_checks() != 0;
+    bad |= failed_tick_scenario(1);
+    bad |= failed_tick_scenario(4);
     /* the synchronous batch and the ring batch (3 slots, 4 pull threads) must produce the same bytes */
     ticks = shimh_batch(in, N, BYTES, 48000, CH, scale, gain, 11, 200, 2, 333, out, out_bytes, results, 64, n_results, &mism);
     bad |= ticks <= 0 || mism != 0;
