@@ -592,6 +592,13 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
                 return brc;
 #endif
         assign_work(c, mpdl, captured, st, n_items, grid, (uint64_t)occ * c->num_sms, &m.work, &m.work_base);
+        // completion word, as for the plain ticks below
+        const bool mflagged = !captured && st == c->s_cmp && c->h_done != nullptr && c->idle_hint.exchange(false, std::memory_order_acq_rel);
+        if (mflagged) {
+            m.done_count = c->d_done_count;
+            m.done_flag = c->d_done_flag;
+            m.done_gen = c->done_gen_next;
+        }
         if (vec8 && in_meter)
             CU(launch_kernel(cmgpu::mix8to2_tick<true>, (unsigned)grid, 256, 0, st, mpdl, m));
         else if (vec8)
@@ -603,6 +610,11 @@ int launch_locked(cmgpu_ctx *c, unsigned slot, unsigned flags, cudaStream_t st =
             c->pending_ticks += 1;
             if (st == c->s_cmp)
                 c->last_first = slot;
+        }
+        if (mflagged) {
+            c->tail_gen.store(m.done_gen, std::memory_order_release);
+            if (++c->done_gen_next == 0)
+                c->done_gen_next = 1;
         }
         return CMGPU_OK;
     }

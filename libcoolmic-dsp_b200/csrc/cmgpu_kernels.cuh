@@ -167,7 +167,8 @@ __device__ __forceinline__ void launch_end() { asm volatile("griddepcontrol.wait
 // The count is touched only after griddepcontrol.wait, i.e. after the previous launch has finished
 // entirely, so consecutive launches -- overlapping or not -- can share one counter; every CTA's writes
 // are fenced before it counts itself, so whoever sees the word sees the launch's results.
-__device__ __forceinline__ void tick_end(const TickArgs &a)
+template <typename Args>          // TickArgs or MixArgs: both carry done_count / done_flag / done_gen
+__device__ __forceinline__ void tick_end(const Args &a)
 {
     launch_end();
     if (a.done_flag != nullptr) {

@@ -172,7 +172,8 @@ __global__ void __launch_bounds__(128) mix_tick(const __grid_constant__ MixArgs 
         mix_publish<16>(a.meters_in + (size_t)s * (2 * cin + 2), cin, in, pos_base, f0, lane, kin, pin);
         mix_publish<16>(a.meters_out + (size_t)s * (2 * cout + 2), cout, out, pos_base, f0, lane, kout, pout);
     }
-    launch_end();
+    // (tick_end rather than a bare launch_end: see mix8to2_tick)
+    tick_end(a);
 }
 
 __device__ __forceinline__ int dp2a_lo_su(uint32_t a_s16x2, uint32_t b_u8x4, int c)
@@ -188,11 +189,100 @@ __device__ __forceinline__ int dp2a_hi_su(uint32_t a_s16x2, uint32_t b_u8x4, int
     return d;
 }
 
+// ---- metering a BATCH of four frames per lane (the unrolled rounds of mix8to2_tick) -----------------
+// Same keys and sums as four calls of the per-frame code, with fewer instructions on the integer ALU pipe,
+// which is what bounds the fully metered kernel: the running key takes two 3-input maxima
+// per channel and batch instead of four 2-input ones, and the squares of a channel are added up in 32 bits
+// two at a time (2 * 2^30 fits) before ONE 64-bit accumulate per batch instead of four.
+__device__ __forceinline__ uint32_t max3_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+    return __vimax3_u32(a, b, c);
+}
+// x[u]: the channel's sample in frame u of the batch; radd0 = 0xffff - (step of frame 0), frame u has radd0 - u
+__device__ __forceinline__ void meter_batch4(const int (&x)[4], uint32_t radd0, uint32_t &kmax, uint64_t &pacc)
+{
+    uint32_t k[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+        k[u] = ((uint32_t)abs(x[u]) << 16) + (radd0 - (uint32_t)u);
+    kmax = max3_u32(kmax, k[0], k[1]);
+    kmax = max3_u32(kmax, k[2], k[3]);
+    const uint32_t s01 = (uint32_t)(x[0] * x[0]) + (uint32_t)(x[1] * x[1]);       // each square <= 2^30
+    const uint32_t s23 = (uint32_t)(x[2] * x[2]) + (uint32_t)(x[3] * x[3]);
+    pacc += (uint64_t)s01 + (uint64_t)s23;
+}
+
+// One output of one 8-channel frame: r = trunc(n / scale), n = sum_c x[c] * w[c], UNSATURATED wherever it lies
+// inside the clamp range and beyond it on the same side otherwise (the caller saturates to 16 bits).
+// xw: the frame's four words; Bm: the weights' low bytes (bytes 0-1 of each word) and high bytes (2-3).
+// n is never formed in 64 bits: with lo = sum x * w_lo and hi = sum x * w_hi, n = 256 * H + l where
+// H = hi + (lo >> 8) (arithmetic shift; the high-byte dot product is simply seeded with it) and l = lo & 255.
+// |H| <= 2^23 - 1: n = 256 * H + l fits 32 bits and is exact. Beyond that |n| >= 2^31 - 255, and the clamped
+// value 256 * (+-(2^23 - 1)) + l still has |.| >= 2^31 - 511 >= 32768.49 * 65535: both saturate on the same side.
+__device__ __forceinline__ int mix8_quot_raw(const uint32_t (&xw)[4], const uint32_t (&Bm)[4], uint32_t magic, uint32_t shift)
+{
+    int lo = 0;
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+        lo = dp2a_lo_su(xw[p], Bm[p], lo);
+    int hi = lo >> 8;
+#pragma unroll
+    for (int p = 0; p < 4; p++)
+        hi = dp2a_hi_su(xw[p], Bm[p], hi);
+    hi = max(min(hi, 0x7fffff), -0x7fffff);
+    const int ns = hi * 256 + (lo & 255);                 // |ns| <= 2^31 - 1
+    const uint32_t a = (uint32_t)abs(ns);
+    const uint32_t q = (uint32_t)(((unsigned long long)a * magic) >> shift);      // exact for a < 2^31
+    return (int)q * ((ns >> 31) | 1);                    // the sign goes back on with a multiply: the FMA pipe has room, the ALU pipe has not
+}
+
+// Four frames of one lane (one batch of the double-buffered loads): mix, store, meter.
+template <bool IN_METER>
+__device__ __forceinline__ void mix8to2_batch4(const uint4 (&buf)[4], uint32_t i0, const uint32_t (&B)[2][4], uint32_t magic,
+                                               uint32_t shift, uint32_t (&kin)[8], uint64_t (&pin)[8], uint32_t (&kout)[2],
+                                               uint64_t (&pout)[2], uint32_t *dst)
+{
+    const uint32_t radd0 = 0xffffu - i0;
+    uint32_t xw[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        xw[u][0] = buf[u].x;
+        xw[u][1] = buf[u].y;
+        xw[u][2] = buf[u].z;
+        xw[u][3] = buf[u].w;
+    }
+    if (IN_METER) {
+#pragma unroll
+        for (int p = 0; p < 4; p++) {                 // word p of a frame: channels 2p (low half) and 2p + 1
+            int lo[4], hi[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                lo[u] = (int)(short)(xw[u][p] & 0xffffu);
+                hi[u] = (int)xw[u][p] >> 16;
+            }
+            meter_batch4(lo, radd0, kin[2 * p], pin[2 * p]);
+            meter_batch4(hi, radd0, kin[2 * p + 1], pin[2 * p + 1]);
+        }
+    }
+    int y0[4], y1[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int r0 = mix8_quot_raw(xw[u], B[0], magic, shift), r1 = mix8_quot_raw(xw[u], B[1], magic, shift);
+        const uint32_t ow = pack_sat16(r1, r0);          // saturate both, pack: one instruction
+        y0[u] = (int)(short)(ow & 0xffffu);
+        y1[u] = (int)ow >> 16;
+        dst[(size_t)(i0 + (uint32_t)u) * 32] = ow;
+    }
+    meter_batch4(y0, radd0, kout[0], pout[0]);
+    meter_batch4(y1, radd0, kout[1], pout[1]);
+}
+
 // 8 -> 2 (the config-4b shape) with the fused kernels' memory pipeline: one warp per (stream, chunk
 // of frames), a frame = one 128-bit load, loads in double-buffered batches of 4 per lane, output =
-// one 32-bit word per frame. The input side is metered by the 8-channel hot loop itself
-// (do_vector<8, identity>); the mix is 8 dp2a (signed 16-bit x unsigned 8-bit, weights split into
-// low and high bytes) + one 64-bit recombination per output instead of 8 half-rate IMAD.WIDE.
+// one 32-bit word per frame. The mix is 8 dp2a per output (signed 16-bit x unsigned 8-bit, weights split
+// into low and high bytes) recombined and divided in 32 bits (mix8_quot_raw). Full batches meter their four
+// frames together (meter_batch4: 103 instructions per frame, 53 of them on the ALU pipe, where the per-frame
+// code -- do_vector<8, identity> for the inputs, still used for the last frames of an item -- took 120 / 71).
 // IN_METER false: the 8 input channels are not metered (cmgpu_mix_ctx_create flag CMGPU_MIX_OUTPUT_METER_ONLY):
 // half of the kernel's instructions, for callers that only want the levels of what they send on.
 // (without the input meter the kernel fits 80 registers: three resident CTAs instead of two hide the load
@@ -271,16 +361,8 @@ __global__ void __launch_bounds__(256, IN_METER ? 2 : 3) mix8to2_tick(const __gr
         if (IN_METER)                                                                       \
             do_vector<8, GM_IDENTITY, true, false, false>(vec_, none, radd, kin, pin, 8);   \
         const uint32_t xw[4] = {(vec_).x, (vec_).y, (vec_).z, (vec_).w};                    \
-        int r[2];                                                                           \
-        _Pragma("unroll") for (int m = 0; m < 2; m++) {                                     \
-            int lo = 0, hi = 0;                                                             \
-            _Pragma("unroll") for (int p = 0; p < 4; p++) {                                 \
-                lo = dp2a_lo_su(xw[p], B[m][p], lo);                                        \
-                hi = dp2a_hi_su(xw[p], B[m][p], hi);                                        \
-            }                                                                               \
-            r[m] = mix_divide_raw((long long)hi * 256 + lo, magic, shift);                  \
-        }                                                                                   \
-        const uint32_t ow = pack_sat16(r[1], r[0]);      /* saturate both, pack: one instruction */ \
+        const int r0 = mix8_quot_raw(xw, B[0], magic, shift), r1 = mix8_quot_raw(xw, B[1], magic, shift); \
+        const uint32_t ow = pack_sat16(r1, r0);          /* saturate both, pack: one instruction */ \
         const int y0 = (int)(short)(ow & 0xffffu), y1 = (int)ow >> 16;                      \
         kout[0] = max(kout[0], ((uint32_t)abs(y0) << 16) + radd);                           \
         kout[1] = max(kout[1], ((uint32_t)abs(y1) << 16) + radd);                           \
@@ -291,9 +373,7 @@ __global__ void __launch_bounds__(256, IN_METER ? 2 : 3) mix8to2_tick(const __gr
 #define CMGPU_MIX_LOAD(buf, b)                                                              \
     _Pragma("unroll") for (int u = 0; u < UNROLL; u++)                                      \
         buf[u] = ld_stream(it.src + (size_t)((b) * UNROLL + u) * kStep);
-#define CMGPU_MIX_DO(buf, b)                                                                \
-    _Pragma("unroll") for (int u = 0; u < UNROLL; u++)                                      \
-        CMGPU_MIX_FRAME(buf[u], (b) * UNROLL + u)
+#define CMGPU_MIX_DO(buf, b) mix8to2_batch4<IN_METER>(buf, (b) * UNROLL, B, magic, shift, kin, pin, kout, pout, dst);
         if (nb > 0) {
             CMGPU_MIX_LOAD(bufA, 0u)
         }
@@ -326,7 +406,10 @@ __global__ void __launch_bounds__(256, IN_METER ? 2 : 3) mix8to2_tick(const __gr
         mix_publish<2>(a.meters_out + (size_t)s * 6, 2, reinterpret_cast<const volatile int16_t *>(a.out + (size_t)s * a.stride_out),
                        pos_base, f0, lane, kout, pout);
     }
-    launch_end();
+    // (tick_end, not a bare launch_end: a kernel whose LAST statement is griddepcontrol.wait makes ptxas keep the
+    //  global-memory descriptor in a vector register and move it to a uniform one before every access -- R2UR, four
+    //  per frame in the 8 -> 2 loop; with the completion-word tail behind the wait it stays in a uniform register)
+    tick_end(a);
 }
 
 }  // namespace cmgpu

@@ -109,6 +109,9 @@ struct MixArgs {
     uint32_t cin, cout;
     unsigned int *work;           // work-claim counter, see TickArgs::work
     uint32_t work_base;
+    unsigned int *done_count;     // completion word, see TickArgs::done_flag
+    unsigned int *done_flag;
+    uint32_t done_gen;
 };
 
 }  // namespace cmgpu
