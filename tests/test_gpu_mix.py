@@ -85,3 +85,47 @@ def test_mix_argument_checks(cm):
     with cm.Engine(2, 2, 16) as eng:
         assert eng.L.cmgpu_stream_set_mix(eng.ctx, 0, 1, np.ones(4, np.uint16).ctypes.data_as(
             __import__("ctypes").POINTER(__import__("ctypes").c_uint16))) == -10   # not a mix context
+
+
+def test_downmix_sync_by_completion_word(cm, port):
+    """Downmix launches carry the completion word like every other tick (MixArgs::done_flag): cmgpu_sync straight after a
+    tick on resident data returns when the launch's last CTA has written the word, and everything the tick wrote is
+    visible by then -- the output ring is read with a plain cudaMemcpy that nothing but the host's wait orders after the
+    tick; the weights change from tick to tick."""
+    import ctypes as C
+    from tests.test_gpu_post import _cudart
+    rt = _cudart()
+    rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    rng = np.random.default_rng(77)
+    cin, cout, n_streams, block = 8, 2, 96, 700
+    with cm.Engine(cin, n_streams, block, out_channels=cout) as eng:
+        host = eng.host_slot(0)
+        got = np.empty_like(eng.host_out_slot(0))
+        m_in = [Meter() for _ in range(n_streams)]
+        m_out = [Meter() for _ in range(n_streams)]
+        for it in range(20):
+            scales = rng.integers(1, 65536, size=n_streams)
+            weights = rng.integers(0, 65536, size=(n_streams, cout, cin)).astype(np.uint16)
+            for s in range(n_streams):
+                assert eng.set_mix(s, int(scales[s]), weights[s]) == 0
+            host[:] = rng.integers(-32768, 32768, size=host.shape).astype(np.int16)
+            src = host.copy()
+            eng.submit(0)
+            eng.process(0)                      # consumes the upload (a streaming tick)
+            eng.sync()                          # a launch gets a word only on a stream that was just waited for
+            eng.process(0)                      # on resident data: a bare launch, the tail of the compute stream
+            eng.sync()                          # <- by completion word
+            assert rt.cudaMemcpy(got.ctypes.data, eng.device_out_slot(0), got.nbytes, 2) == 0
+            for s in range(n_streams):
+                port.mix(src[s, : block * cin], block, cin, cout, int(scales[s]), weights[s], m_in[s], m_out[s])
+                want = port.mix(src[s, : block * cin], block, cin, cout, int(scales[s]), weights[s], m_in[s], m_out[s])
+                assert np.array_equal(got[s, : block * cout], want), f"tick {it} stream {s}: output not complete when cmgpu_sync returned"
+        assert eng.word_waits() >= 20, "cmgpu_sync never took the completion-word path for downmix launches"
+        so = eng.snapshot()
+        si = eng.input_snapshot()
+        for s in range(n_streams):
+            for st, want, ch in ((so[s], m_out[s], cout), (si[s], m_in[s], cin)):
+                assert int(st.frames) == int(want.frames)
+                for c in range(ch):
+                    assert int(st.power[c]) == int(want.power[c])
+                    assert int(st.channel_peak[c]) == int(want.channel_peak[c])
