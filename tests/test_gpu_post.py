@@ -428,7 +428,9 @@ def test_sync_by_completion_word_sees_the_finished_tick(cm, port, channels, n_st
             assert rt.cudaMemcpy(got.ctypes.data, eng.device_out_slot(0), got.nbytes, 2) == 0
             n = block * channels
             assert np.array_equal(got[:, :n], want[:, :n]), f"tick {it}: output not complete when cmgpu_sync returned"
-        assert eng.word_waits() >= 40, "cmgpu_sync never took the completion-word path"
+        # (one sync per iteration can end by the word; a wait that outlasts the library's 60 us of polling -- a busy
+        #  box -- falls back to the driver and is not counted: leave some slack)
+        assert eng.word_waits() >= 30, "cmgpu_sync never took the completion-word path"
         snap = eng.snapshot(0, n_streams)
         for s in range(n_streams):
             assert int(snap[s].frames) == int(meters[s].frames)
