@@ -50,6 +50,34 @@ def build_stub(sanitize: str = "", main: bool = False) -> Path:
     return out
 
 
+REFERENCE = Path("/root/reference")
+DROPIN_REF_FILES = ["iohandle", "tee", "snddev", "snddev_sine", "snddev_null", "snddev_stdio", "logging", "coolmic-dsp"]
+
+
+def build_dropin_stub():
+    """The drop-in build of oracle/Makefile (`dropin`: the reference's own iohandle.c, tee.c, snddev*.c, logging.c and
+    coolmic-dsp.c, unmodified and compiled from where they lie, src/transform.c and src/vumeter.c left out, the product's
+    csrc/host/*.c with -DCOOLMIC_B200_WITH_IGLOO in their place, oracle/ref_harness.c on top) -- linked against the CPU
+    stand-in of the engine instead of the CUDA library, so that the INTEGRATION build's host logic (libigloo object
+    declarations, the reference's tee and iohandle driving the product's callbacks) runs without a GPU.
+    Returns None where the reference's sources are not present (e.g. on the GPU box)."""
+    if not (REFERENCE / "src" / "tee.c").exists():
+        return None
+    out = SO.parent / "libdropin_stub.so"
+    oracle = ROOT / "oracle"
+    srcs = ([REFERENCE / "src" / f"{f}.c" for f in DROPIN_REF_FILES] + HOST_SRC +
+            [oracle / "ref_harness.c", ROOT / "tests" / "stub" / "cmgpu_stub.c", oracle / "coolmic_oracle.c"])
+    if out.exists() and out.stat().st_mtime > max(s.stat().st_mtime for s in srcs):
+        return out
+    SO.parent.mkdir(exist_ok=True)
+    cmd = ["gcc", "-std=gnu11", "-Wall", "-Wextra", "-Wno-pointer-arith", "-O2", "-g", "-fPIC", "-D_GNU_SOURCE",
+           "-DHAVE_SNDDRV_DRIVER_STDIO", "-DCOOLMIC_B200_WITH_IGLOO", f"-I{oracle / 'igloo_shim'}",
+           f"-I{REFERENCE / 'include'}", f"-I{REFERENCE / 'src'}", f"-I{ROOT / 'include'}", "-shared", "-pthread",
+           "-Wl,-Bsymbolic", "-o", str(out)] + [str(s) for s in srcs] + ["-lm"]
+    subprocess.run(cmd, check=True)
+    return out
+
+
 class ShimLib:
     kind = "b200 shim"
 
