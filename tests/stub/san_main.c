@@ -20,6 +20,46 @@ int shimh_null_checks(void);
 
 int shim_bench_copy_selftest(void);
 void cmgpu_stub_fail_next_process(int n);
+long shimh_transform(const void *in, size_t in_bytes, unsigned rate, unsigned channels, int set_gain, unsigned gain_n,
+                     unsigned scale, const uint16_t *gain, size_t src_chunk, size_t pull, void *out, size_t out_cap, int *gain_rc);
+long shimh_chain(const void *in, size_t in_bytes, unsigned rate, unsigned channels, int set_gain, unsigned gain_n,
+                 unsigned scale, const uint16_t *gain, size_t src_chunk, long maxlen, unsigned result_every,
+                 void *results, size_t results_cap);
+long oracle_run_transform(const void *in, size_t in_bytes, unsigned channels, int set_gain, unsigned gain_n, unsigned scale,
+                          const uint16_t *gain, size_t src_chunk, size_t pull, void *out, size_t out_cap, int *gain_rc);
+
+/* the stand-alone objects: whole-frame reads with the partial-frame carry, odd chunkings and pull sizes, the gain
+ * setter's four cases (transform.c:126-165,195-222) -- bytes against the oracle port, memory under the sanitizers */
+static int standalone_objects_scenario(void)
+{
+    enum { BYTES = 9001 };
+    static const unsigned chans[] = {1, 2, 3, 8, 16};
+    static const size_t chunks[] = {0, 1, 3, 7, 100}, pulls[] = {1024, 33, 5, 8192};
+    unsigned char *in = malloc(BYTES), *a = malloc(BYTES + 64), *b = malloc(BYTES + 64);
+    void *results = calloc(64, 256);
+    uint16_t gain[16];
+    int bad = 0;
+    unsigned i, t = 0;
+    for (i = 0; i < BYTES; i++)
+        in[i] = (unsigned char)rand();
+    for (i = 0; i < 16; i++)
+        gain[i] = (uint16_t)(300 * i + 77);
+    for (i = 0; i < sizeof(chans) / sizeof(*chans); i++) {
+        unsigned gi;
+        for (gi = 0; gi < 4; gi++, t++) {
+            const unsigned ch = chans[i];
+            const unsigned gn = gi == 0 ? ch : gi == 1 ? 1 : gi == 2 ? 2 : 0;      /* copy, broadcast, mono average or INVAL, off */
+            const size_t chunk = chunks[t % 5], pull = pulls[t % 4];
+            int rc_a = 99, rc_b = 99;
+            const long na = shimh_transform(in, BYTES, 48000, ch, 1, gn, 1000 + 13 * t, gain, chunk, pull, a, BYTES + 64, &rc_a);
+            const long nb = oracle_run_transform(in, BYTES, ch, 1, gn, 1000 + 13 * t, gain, chunk, pull, b, BYTES + 64, &rc_b);
+            bad |= na != nb || rc_a != rc_b || (na > 0 && memcmp(a, b, (size_t)na) != 0);
+            bad |= shimh_chain(in, BYTES, 48000, ch, 1, gn, 1000 + 13 * t, gain, chunk, t % 2 ? -1 : 100, 3, results, 64) <= 0;
+        }
+    }
+    free(in); free(a); free(b); free(results);
+    return bad;
+}
 
 /* a tick that fails after its pull (a CUDA error in the real engine): nothing of it is exposed, and the
  * NEXT tick still hands the pull workers a new job instead of waiting for them forever */
@@ -102,6 +142,7 @@ int main(void)
             gain[s * CH + i] = (uint16_t)(700 + 97 * s + i);
     }
     bad |= shimh_null_checks() != 0;
+    bad |= standalone_objects_scenario();
     bad |= failed_tick_scenario(1);
     bad |= failed_tick_scenario(4);
     /* the synchronous batch and the ring batch (3 slots, 4 pull threads) must produce the same bytes */
