@@ -461,7 +461,15 @@ def main():
     prof = ROOT / "profiles" / "traffic.json"
     if prof.exists():
         try:
-            roofline["traffic"] = json.loads(prof.read_text()).get(args.workload, {}).get("dram_bytes_per_launch")
+            entry = json.loads(prof.read_text()).get(args.workload, {})
+            if entry.get("dram_bytes_per_launch"):
+                # the capture is of a ONE-GPU launch of this workload; a rank of a strong-scaling run launches over
+                # its share of the streams, so the capture's bytes are scaled by that share (and said so)
+                share = 1.0 / world if (wl.get("strong") and world > 1) else 1.0
+                roofline["traffic"] = entry["dram_bytes_per_launch"] * share
+                roofline["traffic_source"] = (f"ncu --set full capture profiles/{entry.get('from', '?')} (dram__bytes_read.sum + "
+                                              "dram__bytes_write.sum of one launch on one GPU"
+                                              + (f", x 1/{world}: this rank's share of the streams)" if share != 1.0 else ")"))
         except Exception:
             pass
 
