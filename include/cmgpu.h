@@ -221,8 +221,10 @@ int cmgpu_meter_results(cmgpu_ctx_t *ctx, unsigned first, unsigned count, uint32
  * A communicator is created from a 128-byte NCCL unique id that rank 0 makes and hands to the other
  * ranks by any means (cmgpu_comm_create), or through a file on a shared file system
  * (cmgpu_comm_create_file: rank 0 writes `path` atomically and removes it once every rank has joined;
- * the others wait up to timeout_ms for it) -- no PyTorch, no MPI. An existing ncclComm_t can be
- * adopted instead (cmgpu_comm_adopt; not destroyed by cmgpu_comm_destroy). */
+ * the others wait up to timeout_ms for it; `path` must be unique to the job -- a file left behind by
+ * a job that died before joining would be taken for this job's id, so name it after the launcher, as
+ * bench.py does with the launcher's pid, start time and port) -- no PyTorch, no MPI. An existing
+ * ncclComm_t can be adopted instead (cmgpu_comm_adopt; not destroyed by cmgpu_comm_destroy). */
 typedef struct cmgpu_comm cmgpu_comm_t;
 #define CMGPU_COMM_ID_BYTES 128
 int           cmgpu_comm_unique_id(unsigned char id[CMGPU_COMM_ID_BYTES]);
